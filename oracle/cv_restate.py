@@ -1,0 +1,482 @@
+"""TEST INFRASTRUCTURE (oracle) -- integer/float restatements of the OpenCV
+primitives on the reference hot path, in plain numpy.
+
+The reference delegates all pixel arithmetic to OpenCV 4.x
+(/root/reference/CMakeLists.txt:7, unpinned, not vendored).  These functions
+restate the *published algorithms* of the exact calls the reference makes
+(call sites cited per function) so that the CUDA kernels have a readable
+specification; tests/test_oracle_restate.py proves each of them equal to
+`cv2` 4.13.0 on seeded inputs (bit-exact unless a tolerance is stated).
+
+Never imported by the product path.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------
+# A.1  cvtColor(BGR2GRAY), 8U          call site: stabilizer.cpp:1175, :455
+# ----------------------------------------------------------------------------
+def bgr2gray(bgr: np.ndarray) -> np.ndarray:
+    b = bgr[..., 0].astype(np.int32)
+    g = bgr[..., 1].astype(np.int32)
+    r = bgr[..., 2].astype(np.int32)
+    return ((3735 * b + 19235 * g + 9798 * r + 16384) >> 15).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# A.2  resize(INTER_LINEAR), 8UC3      call site: stabilizer.cpp:1170-1171
+# ----------------------------------------------------------------------------
+def working_size(rows: int, cols: int, working_height: int):
+    """stabilizer.cpp:117-119: scaleFactor_ = wh/rows, (int(cols*s), wh)."""
+    s = float(working_height) / rows
+    return int(cols * s), working_height, s
+
+
+def _linear_coeffs(src: int, dst: int):
+    """Per-axis source index and Q11 coefficients of cv::resize INTER_LINEAR."""
+    scale = np.float64(src) / np.float64(dst)
+    d = np.arange(dst, dtype=np.float64)
+    fx = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(fx).astype(np.int64)
+    fx = (fx - s.astype(np.float32)).astype(np.float32)
+    lo = s < 0
+    s[lo] = 0
+    fx[lo] = 0
+    hi = s >= src - 1
+    s[hi] = src - 1
+    fx[hi] = 0
+    c1 = np.rint(fx * F32(2048)).astype(np.int32)
+    c0 = np.rint((F32(1.0) - fx) * F32(2048)).astype(np.int32)
+    s1 = np.minimum(s + 1, src - 1)
+    return s, s1, c0, c1
+
+
+def resize_linear_bgr(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    sh, sw = src.shape[:2]
+    if (dw, dh) == (sw, sh):
+        return src.copy()
+    if sw == 2 * dw and sh == 2 * dh:
+        # exact 2x decimation silently becomes INTER_AREA: rounded 2x2 box mean
+        a = src.astype(np.int32)
+        out = (a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8)
+    xs0, xs1, xc0, xc1 = _linear_coeffs(sw, dw)
+    ys0, ys1, yc0, yc1 = _linear_coeffs(sh, dh)
+    a = src.astype(np.int32)
+    # horizontal pass on the two needed source rows (x2048)
+    r0 = a[ys0][:, xs0] * xc0[None, :, None] + a[ys0][:, xs1] * xc1[None, :, None]
+    r1 = a[ys1][:, xs0] * xc0[None, :, None] + a[ys1][:, xs1] * xc1[None, :, None]
+    b0 = yc0[:, None, None]
+    b1 = yc1[:, None, None]
+    out = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def resize_nearest_bgr(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """resize(INTER_NEAREST), call site stabilizer.cpp:450-451."""
+    sh, sw = src.shape[:2]
+    fx = np.float64(sw) / dw   # inv_scale
+    fy = np.float64(sh) / dh
+    xi = np.minimum(np.floor(np.arange(dw) * fx).astype(np.int64), sw - 1)
+    yi = np.minimum(np.floor(np.arange(dh) * fy).astype(np.int64), sh - 1)
+    return src[yi][:, xi].copy()
+
+
+# ----------------------------------------------------------------------------
+# A.3  pyrDown, 8U   (inside calcOpticalFlowPyrLK, call site stabilizer.cpp:192)
+# ----------------------------------------------------------------------------
+def _reflect101(i: np.ndarray, n: int) -> np.ndarray:
+    i = np.where(i < 0, -i, i)
+    i = np.where(i >= n, 2 * n - 2 - i, i)
+    return i
+
+
+def pyr_down(img: np.ndarray) -> np.ndarray:
+    h, w = img.shape
+    dh, dw = (h + 1) // 2, (w + 1) // 2
+    k = np.array([1, 4, 6, 4, 1], dtype=np.int32)
+    a = img.astype(np.int32)
+    xs = 2 * np.arange(dw)[:, None] + np.arange(-2, 3)[None, :]
+    xs = _reflect101(xs, w)
+    rows = (a[:, xs] * k[None, None, :]).sum(axis=2)          # h x dw
+    ys = 2 * np.arange(dh)[:, None] + np.arange(-2, 3)[None, :]
+    ys = _reflect101(ys, h)
+    out = (rows[ys, :] * k[None, :, None]).sum(axis=1)        # dh x dw
+    return ((out + 128) >> 8).astype(np.uint8)
+
+
+def lk_pyramid(img: np.ndarray, max_level: int = 3):
+    levels = [img]
+    for _ in range(max_level):
+        levels.append(pyr_down(levels[-1]))
+    return levels
+
+
+# ----------------------------------------------------------------------------
+# A.5  goodFeaturesToTrack            call site: stabilizer.cpp:949-963
+# ----------------------------------------------------------------------------
+def _fma32(a, b, c):
+    """Correctly rounded float32 fma via float64 (products of two float32 are
+    exact in float64; the final sum rounds once to f64 then to f32 -- double
+    rounding can differ from a true fma by 1 ulp in rare cases)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def corner_min_eigen_val(gray: np.ndarray) -> np.ndarray:
+    """cornerMinEigenVal(gray, blockSize=3, ksize=3) as computed by OpenCV's
+    AVX2/FMA filter engine."""
+    h, w = gray.shape
+    scale = 1.0 / (4.0 * 3.0 * 255.0)      # 1/(2^(ksize-1) * blockSize * 255)
+    k1 = F32(scale)
+    k0 = F32(2 * scale)
+    yy = _reflect101(np.arange(-1, h + 1), h)
+    xx = _reflect101(np.arange(-1, w + 1), w)
+    p = gray[yy][:, xx].astype(np.float32)                    # (h+2) x (w+2)
+    # Dx: row filter [-1 0 1] (exact), column filter [1 2 1]*scale
+    S = p[:, 2:] - p[:, :-2]                                  # (h+2) x w
+    Dx = _fma32(S[:-2] + S[2:], np.broadcast_to(k1, S[:-2].shape), S[1:-1] * k0)
+    # Dy: row filter [1 2 1]*scale, column filter [-1 0 1]
+    t = p[:, :-2] * k1
+    t = _fma32(p[:, 1:-1], np.broadcast_to(k0, t.shape), t)
+    R = _fma32(p[:, 2:], np.broadcast_to(k1, t.shape), t)     # (h+2) x w
+    Dy = R[2:] - R[:-2]
+    dxx = Dx * Dx
+    dxy = Dx * Dy
+    dyy = Dy * Dy
+
+    def box3(m):
+        yy = _reflect101(np.arange(-1, h + 1), h)
+        xx = _reflect101(np.arange(-1, w + 1), w)
+        q = m[yy][:, xx].astype(np.float64)
+        acc = np.zeros((h, w), np.float64)
+        for dy in range(3):
+            for dx in range(3):
+                acc += q[dy:dy + h, dx:dx + w]
+        return acc.astype(np.float32)
+
+    a = box3(dxx) * F32(0.5)
+    b = box3(dxy)
+    c = box3(dyy) * F32(0.5)
+    d = a - c
+    return ((a + c) - np.sqrt(d * d + b * b)).astype(np.float32)
+
+
+def good_features_to_track(gray: np.ndarray, max_corners: int = 1300,
+                           quality: float = 0.01, min_distance: float = 5.0,
+                           eig: np.ndarray | None = None) -> np.ndarray:
+    """Selection part of goodFeaturesToTrack (threshold, 3x3 local max, sort,
+    greedy grid suppression).  Returns (N,2) float32 (x,y)."""
+    if eig is None:
+        eig = corner_min_eigen_val(gray)
+    h, w = eig.shape
+    max_val = float(eig.max())
+    thr = F32(max_val * quality)
+    e = np.where(eig > thr, eig, F32(0))
+    # dilate 3x3 (border: replicate of -inf has no effect => use edge padding with 0-safe max)
+    pad = np.pad(e, 1, mode="constant", constant_values=-np.inf)
+    dil = e.copy()
+    for dy in range(3):
+        for dx in range(3):
+            dil = np.maximum(dil, pad[dy:dy + h, dx:dx + w])
+    cand = (e != 0) & (e == dil)
+    cand[0, :] = cand[-1, :] = False
+    cand[:, 0] = cand[:, -1] = False
+    ys, xs = np.nonzero(cand)
+    vals = e[ys, xs]
+    addr = ys.astype(np.int64) * w + xs
+    order = np.lexsort((-addr, -vals.astype(np.float64)))      # value desc, address desc
+    ys, xs = ys[order], xs[order]
+    if min_distance < 1:
+        n = min(max_corners, len(ys)) if max_corners > 0 else len(ys)
+        return np.stack([xs[:n], ys[:n]], axis=1).astype(np.float32)
+    cell = int(round(min_distance))
+    gw = (w + cell - 1) // cell
+    gh = (h + cell - 1) // cell
+    grid = [[] for _ in range(gw * gh)]
+    md2 = min_distance * min_distance
+    out = []
+    for y, x in zip(ys.tolist(), xs.tolist()):
+        xc, yc = x // cell, y // cell
+        x1, y1 = max(0, xc - 1), max(0, yc - 1)
+        x2, y2 = min(gw - 1, xc + 1), min(gh - 1, yc + 1)
+        good = True
+        for gy in range(y1, y2 + 1):
+            for gx in range(x1, x2 + 1):
+                for (px, py) in grid[gy * gw + gx]:
+                    dx, dy = x - px, y - py
+                    if dx * dx + dy * dy < md2:
+                        good = False
+                        break
+                if not good:
+                    break
+            if not good:
+                break
+        if good:
+            grid[yc * gw + xc].append((x, y))
+            out.append((x, y))
+            if max_corners > 0 and len(out) == max_corners:
+                break
+    return np.array(out, dtype=np.float32).reshape(-1, 2)
+
+
+# ----------------------------------------------------------------------------
+# A.4  calcOpticalFlowPyrLK           call site: stabilizer.cpp:192-195
+# ----------------------------------------------------------------------------
+def scharr_deriv(img: np.ndarray):
+    """int16 (dx, dy) with REFLECT_101 borders inside the image."""
+    h, w = img.shape
+    yy = _reflect101(np.arange(-1, h + 1), h)
+    xx = _reflect101(np.arange(-1, w + 1), w)
+    p = img[yy][:, xx].astype(np.int32)
+    dx = 3 * (p[:-2, 2:] - p[:-2, :-2]) + 10 * (p[1:-1, 2:] - p[1:-1, :-2]) + 3 * (p[2:, 2:] - p[2:, :-2])
+    dy = 3 * (p[2:, :-2] - p[:-2, :-2]) + 10 * (p[2:, 1:-1] - p[:-2, 1:-1]) + 3 * (p[2:, 2:] - p[:-2, 2:])
+    return dx.astype(np.int16), dy.astype(np.int16)
+
+
+def _pad_reflect(img, pad):
+    h, w = img.shape
+    yy = _reflect101(np.arange(-pad, h + pad), h)
+    xx = _reflect101(np.arange(-pad, w + pad), w)
+    return img[yy][:, xx]
+
+
+def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
+                             win: int = 21, max_level: int = 3, max_iter: int = 50,
+                             eps: float = 0.01, min_eig: float = 1e-4):
+    """Sparse pyramidal LK, control flow and fixed-point formats of OpenCV's
+    LKTrackerInvoker.  Returns (next_pts float32 (N,2), status u8)."""
+    half = (win - 1) * 0.5
+    pp = lk_pyramid(prev, max_level)
+    np_ = lk_pyramid(nxt, max_level)
+    N = len(pts)
+    out = np.zeros((N, 2), np.float32)
+    status = np.ones(N, np.uint8)
+    W_BITS = 14
+    FLT_SCALE = F32(1.0 / (1 << 20))
+    PAD = win
+    for level in range(max_level, -1, -1):
+        I = pp[level]
+        J = np_[level]
+        rows, cols = I.shape
+        dIx, dIy = scharr_deriv(I)
+        Ipad = _pad_reflect(I, PAD).astype(np.int32)
+        Jpad = _pad_reflect(J, PAD).astype(np.int32)
+        dxpad = np.pad(dIx.astype(np.int32), PAD)
+        dypad = np.pad(dIy.astype(np.int32), PAD)
+        scale = F32(1.0 / (1 << level))
+        for i in range(N):
+            prevx = F32(pts[i, 0]) * scale
+            prevy = F32(pts[i, 1]) * scale
+            if level == max_level:
+                nx, ny = prevx, prevy
+            else:
+                nx, ny = F32(out[i, 0] * F32(2.0)), F32(out[i, 1] * F32(2.0))
+            out[i] = (nx, ny)
+            px = F32(prevx - F32(half))
+            py = F32(prevy - F32(half))
+            ipx = int(math.floor(px))
+            ipy = int(math.floor(py))
+            if ipx < -win or ipx >= cols or ipy < -win or ipy >= rows:
+                if level == 0:
+                    status[i] = 0
+                continue
+            a = F32(px - F32(ipx))
+            b = F32(py - F32(ipy))
+            one = F32(1.0)
+            s = F32(1 << W_BITS)
+            iw00 = int(np.rint((one - a) * (one - b) * s))
+            iw01 = int(np.rint(a * (one - b) * s))
+            iw10 = int(np.rint((one - a) * b * s))
+            iw11 = (1 << W_BITS) - iw00 - iw01 - iw10
+            y0, x0 = ipy + PAD, ipx + PAD
+            def interp(A, rnd, sh, y0=y0, x0=x0, w=(iw00, iw01, iw10, iw11)):
+                return (A[y0:y0 + win, x0:x0 + win] * w[0] + A[y0:y0 + win, x0 + 1:x0 + win + 1] * w[1]
+                        + A[y0 + 1:y0 + win + 1, x0:x0 + win] * w[2]
+                        + A[y0 + 1:y0 + win + 1, x0 + 1:x0 + win + 1] * w[3] + rnd) >> sh
+            Iw = interp(Ipad, 1 << (W_BITS - 5 - 1), W_BITS - 5)
+            Ix = interp(dxpad, 1 << (W_BITS - 1), W_BITS)
+            Iy = interp(dypad, 1 << (W_BITS - 1), W_BITS)
+            A11 = F32(F32(np.sum(Ix.astype(np.float32) * Ix.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+            A12 = F32(F32(np.sum(Ix.astype(np.float32) * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+            A22 = F32(F32(np.sum(Iy.astype(np.float32) * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+            D = F32(A11 * A22 - A12 * A12)
+            mineig = F32((A22 + A11 - np.sqrt(F32((A11 - A22) * (A11 - A22) + F32(4.0) * A12 * A12))) / F32(2 * win * win))
+            if mineig < min_eig or D < np.finfo(np.float32).eps:
+                if level == 0:
+                    status[i] = 0
+                continue
+            D = F32(one / D)
+            nx = F32(nx - F32(half))
+            ny = F32(ny - F32(half))
+            pdx = pdy = F32(0)
+            for j in range(max_iter):
+                inx = int(math.floor(nx))
+                iny = int(math.floor(ny))
+                if inx < -win or inx >= cols or iny < -win or iny >= rows:
+                    if level == 0:
+                        status[i] = 0
+                    break
+                a = F32(nx - F32(inx))
+                b = F32(ny - F32(iny))
+                w00 = int(np.rint((one - a) * (one - b) * s))
+                w01 = int(np.rint(a * (one - b) * s))
+                w10 = int(np.rint((one - a) * b * s))
+                w11 = (1 << W_BITS) - w00 - w01 - w10
+                Jw = interp(Jpad, 1 << (W_BITS - 5 - 1), W_BITS - 5, iny + PAD, inx + PAD, (w00, w01, w10, w11))
+                diff = (Jw - Iw).astype(np.float32)
+                b1 = F32(F32(np.sum(diff * Ix.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+                b2 = F32(F32(np.sum(diff * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+                ddx = F32((A12 * b2 - A22 * b1) * D)
+                ddy = F32((A12 * b1 - A11 * b2) * D)
+                nx = F32(nx + ddx)
+                ny = F32(ny + ddy)
+                out[i] = (F32(nx + F32(half)), F32(ny + F32(half)))
+                if ddx * ddx + ddy * ddy <= eps * eps:
+                    break
+                if j > 0 and abs(ddx + pdx) < 0.01 and abs(ddy + pdy) < 0.01:
+                    out[i, 0] = F32(out[i, 0] - ddx * F32(0.5))
+                    out[i, 1] = F32(out[i, 1] - ddy * F32(0.5))
+                    break
+                pdx, pdy = ddx, ddy
+    return out, status
+
+
+# ----------------------------------------------------------------------------
+# A.11 warpPerspective(INTER_LINEAR, BORDER_CONSTANT), 8UC3   stabilizer.cpp:1311
+# ----------------------------------------------------------------------------
+def invert3x3(H: np.ndarray) -> np.ndarray:
+    """Adjugate inverse in f64 (cv::invert uses LU for 3x3 via the same closed
+    form in its small-matrix fast path: det + cofactors)."""
+    a = H.astype(np.float64)
+    d = (a[0, 0] * (a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1])
+         - a[0, 1] * (a[1, 0] * a[2, 2] - a[1, 2] * a[2, 0])
+         + a[0, 2] * (a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]))
+    if d == 0:
+        return np.zeros((3, 3))
+    d = 1.0 / d
+    t = np.empty((3, 3))
+    t[0, 0] = (a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1]) * d
+    t[0, 1] = (a[0, 2] * a[2, 1] - a[0, 1] * a[2, 2]) * d
+    t[0, 2] = (a[0, 1] * a[1, 2] - a[0, 2] * a[1, 1]) * d
+    t[1, 0] = (a[1, 2] * a[2, 0] - a[1, 0] * a[2, 2]) * d
+    t[1, 1] = (a[0, 0] * a[2, 2] - a[0, 2] * a[2, 0]) * d
+    t[1, 2] = (a[0, 2] * a[1, 0] - a[0, 0] * a[1, 2]) * d
+    t[2, 0] = (a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]) * d
+    t[2, 1] = (a[0, 1] * a[2, 0] - a[0, 0] * a[2, 1]) * d
+    t[2, 2] = (a[0, 0] * a[1, 1] - a[0, 1] * a[1, 0]) * d
+    return t
+
+
+_WARP_TAB = None
+
+
+def warp_bilinear_tab() -> np.ndarray:
+    """32x32x4 int16 weights (order: (y0,x0),(y0,x1),(y1,x0),(y1,x1)) summing to
+    32768, as built by OpenCV's initInterTab2D(INTER_LINEAR, fixpt=true)."""
+    global _WARP_TAB
+    if _WARP_TAB is not None:
+        return _WARP_TAB
+    tab1 = np.zeros((32, 2), np.float32)
+    for i in range(32):
+        x = F32(i) * F32(1.0 / 32)
+        tab1[i, 0] = F32(1.0) - x
+        tab1[i, 1] = x
+    tab = np.zeros((32, 32, 4), np.int32)
+    for i in range(32):
+        for j in range(32):
+            isum = 0
+            v = np.zeros(4, np.int32)
+            for k1 in range(2):
+                for k2 in range(2):
+                    f = F32(tab1[i, k1] * tab1[j, k2])
+                    val = int(np.clip(np.rint(f * F32(32768)), -32768, 32767))
+                    v[k1 * 2 + k2] = val
+                    isum += val
+            if isum != 32768:
+                diff = isum - 32768
+                # OpenCV adjusts the largest tap (diff>0) or the smallest (diff<0)
+                # within the central 2x2 (the only taps for ksize 2)
+                mk = 0
+                if diff < 0:
+                    for k in range(4):
+                        if v[k] < v[mk]:
+                            mk = k
+                else:
+                    for k in range(4):
+                        if v[k] > v[mk]:
+                            mk = k
+                v[mk] -= diff
+            tab[i, j] = v
+    _WARP_TAB = tab
+    return tab
+
+
+def border_value(frame: np.ndarray):
+    """0.5 * cv::mean(frame) per channel (stabilizer.cpp:1309), f64."""
+    n = frame.shape[0] * frame.shape[1]
+    s = frame.reshape(-1, frame.shape[2]).astype(np.int64).sum(axis=0)
+    return tuple(0.5 * (float(v) / n) for v in s)
+
+
+def warp_perspective_bgr(src: np.ndarray, H: np.ndarray, border) -> np.ndarray:
+    h, w = src.shape[:2]
+    Mi = invert3x3(H)
+    bv = np.array([int(np.clip(np.rint(b), 0, 255)) for b in border[:3]], np.int32)
+    tab = warp_bilinear_tab()
+    xs = np.arange(w, dtype=np.float64)[None, :]
+    ys = np.arange(h, dtype=np.float64)[:, None]
+    # OpenCV evaluates per 32x32 block: X0 = M0*bx + M1*y + M2, then X0 + M0*x1.
+    bx = (np.arange(w) // 32 * 32).astype(np.float64)[None, :]
+    x1 = (np.arange(w) % 32).astype(np.float64)[None, :]
+    X = (Mi[0, 0] * bx + Mi[0, 1] * ys + Mi[0, 2]) + Mi[0, 0] * x1
+    Y = (Mi[1, 0] * bx + Mi[1, 1] * ys + Mi[1, 2]) + Mi[1, 0] * x1
+    Wd = (Mi[2, 0] * bx + Mi[2, 1] * ys + Mi[2, 2]) + Mi[2, 0] * x1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Wd = np.where(Wd != 0, 32.0 / Wd, 0.0)
+    fX = np.clip(X * Wd, -2147483648.0, 2147483647.0)
+    fY = np.clip(Y * Wd, -2147483648.0, 2147483647.0)
+    iX = np.rint(fX).astype(np.int64)
+    iY = np.rint(fY).astype(np.int64)
+    sx = (iX >> 5)
+    sy = (iY >> 5)
+    ax = (iX & 31)
+    ay = (iY & 31)
+    # remap stores coordinates as int16 (saturate_cast<short>)
+    sx = np.clip(sx, -32768, 32767)
+    sy = np.clip(sy, -32768, 32767)
+    wt = tab[ay, ax]                                          # h x w x 4
+    a = src.astype(np.int32)
+
+    def tap(yy, xx):
+        inside = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+        v = a[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)]
+        return np.where(inside[..., None], v, bv[None, None, :])
+
+    out = (tap(sy, sx) * wt[..., 0:1] + tap(sy, sx + 1) * wt[..., 1:2]
+           + tap(sy + 1, sx) * wt[..., 2:3] + tap(sy + 1, sx + 1) * wt[..., 3:4] + 16384) >> 15
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# A.10 estimateAffinePartial2D -> closed-form LS similarity on an inlier set
+# ----------------------------------------------------------------------------
+def ls_similarity(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
+    """argmin_{a,b,tx,ty} sum |[a -b;b a] p + t - q|^2 (f64, closed form)."""
+    p = src.astype(np.float64)
+    q = dst.astype(np.float64)
+    n = len(p)
+    mp = p.mean(axis=0)
+    mq = q.mean(axis=0)
+    pc = p - mp
+    qc = q - mq
+    den = (pc * pc).sum()
+    a = (pc[:, 0] * qc[:, 0] + pc[:, 1] * qc[:, 1]).sum() / den
+    b = (pc[:, 0] * qc[:, 1] - pc[:, 1] * qc[:, 0]).sum() / den
+    tx = mq[0] - (a * mp[0] - b * mp[1])
+    ty = mq[1] - (b * mp[0] + a * mp[1])
+    return np.array([[a, -b, tx], [b, a, ty]])
