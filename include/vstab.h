@@ -1,0 +1,213 @@
+/*
+ * vstab.h -- C ABI of the B200-native drop-in for the per-frame motion-estimation
+ * and warp hot path of joao-gueifao-924/Video-Stabilization.
+ *
+ * Every entry point cites the reference interface it replaces
+ * (paths relative to /root/reference).  There are no OpenCV, torch or C++ types
+ * in any signature: plain pointers, sizes and PODs only.  The library has NO CPU
+ * fallback: every compute entry point returns VSTAB_ERR_CUDA when no sm_100
+ * device is usable.
+ *
+ * Images are 8-bit BGR, HWC, row-major with an explicit row step in bytes
+ * (cv::Mat layout of include/stabilizer.hpp:67,86 and src/stabilizer.cpp:160).
+ * Homographies are 3x3 row-major doubles (CV_64F, src/stabilizer.cpp:212).
+ */
+#ifndef VSTAB_H_
+#define VSTAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSTAB_ABI_VERSION 1
+
+/* enum class StabilizationMode -- include/stabilizer.hpp:31-38 (same order/values) */
+enum vstab_mode {
+    VSTAB_ACCUMULATED_FULL_LOCK = 0,
+    VSTAB_ORB_FULL_LOCK = 1,
+    VSTAB_SIFT_FULL_LOCK = 2,
+    VSTAB_TRANSLATION_LOCK = 3,
+    VSTAB_ROTATION_LOCK = 4,
+    VSTAB_GLOBAL_SMOOTHING = 5
+};
+
+/* Error behaviour of the reference (std::invalid_argument at src/stabilizer.cpp:40-49,
+ * 99-114, 1438-1441) mapped to status codes; include/stabilizer.hpp re-raises them. */
+typedef enum vstab_status {
+    VSTAB_OK = 0,
+    VSTAB_ERR_INVALID_ARGUMENT = 1, /* ctor / frame-size argument checks        */
+    VSTAB_ERR_SIZE_CHANGED = 2,     /* "Frame size has changed" (:110-112)      */
+    VSTAB_ERR_CUDA = 3,             /* no device / CUDA runtime failure          */
+    VSTAB_ERR_UNSUPPORTED = 4,      /* mode not built yet        */
+    VSTAB_ERR_STATE = 5             /* call order the reference asserts against  */
+} vstab_status;
+
+/* struct HomographyParameters -- include/stabilizer.hpp:44-57 */
+typedef struct vstab_hparams {
+    double s;      /* isotropic scale          */
+    double theta;  /* in-plane rotation [rad]  */
+    double k;      /* anisotropy ratio k1      */
+    double delta;  /* shear                    */
+    double t[2];   /* translation              */
+    double v[2];   /* horizon-line shift       */
+} vstab_hparams;
+
+typedef struct vstab vstab_t;               /* one Stabilizer instance == one CUDA stream */
+
+/* ---- class Stabilizer ------------------------------------------------------------- */
+
+/* Stabilizer::Stabilizer(pastFrames=15, futureFrames=15, workingHeight=360)
+ * include/stabilizer.hpp:137, src/stabilizer.cpp:36-53 (same argument checks). */
+vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_height,
+                          int device, vstab_t** out);
+void vstab_destroy(vstab_t* s);
+
+/* Stabilizer::setStabilizationMode -- include/stabilizer.hpp:188, src/stabilizer.cpp:55-96 */
+vstab_status vstab_set_mode(vstab_t* s, int mode);
+int vstab_get_mode(const vstab_t* s);
+
+/* Stabilizer::totalFrameWindowSize -- include/stabilizer.hpp:196-198 */
+size_t vstab_total_frame_window_size(const vstab_t* s);
+
+/* cv::Mat Stabilizer::stabilizeFrame(const cv::Mat&) -- include/stabilizer.hpp:168,
+ * src/stabilizer.cpp:1158-1325.  Host buffers; `bgr` may be reused by the caller as
+ * soon as the call returns (the reference clones it, :160).  `out_bgr` receives the
+ * stabilized presentation frame (call 0: a copy of the input, :1181). */
+vstab_status vstab_stabilize_frame(vstab_t* s, const uint8_t* bgr, int rows, int cols,
+                                   size_t step, uint8_t* out_bgr, size_t out_step);
+
+/* Same call with device-resident input/output (both on the instance's device).
+ * Asynchronous with respect to the host: work is enqueued on the instance stream;
+ * call vstab_synchronize() before reading `d_out_bgr` from another stream. */
+vstab_status vstab_stabilize_frame_device(vstab_t* s, const uint8_t* d_bgr, int rows, int cols,
+                                          size_t step, uint8_t* d_out_bgr, size_t out_step);
+vstab_status vstab_synchronize(vstab_t* s);
+
+/* static bool Stabilizer::decomposeHomography(H, params_out, rot_center)
+ * include/stabilizer.hpp:227, src/stabilizer.cpp:1435-1533.
+ * returns 1 (true) / 0 (false: degenerate, out untouched) / -1 (bad argument,
+ * the reference throws std::invalid_argument).  Host-side double math, like the
+ * reference; the device pipeline uses the same inline function (homography.cuh). */
+int vstab_decompose_homography(const double H[9], double cx, double cy, vstab_hparams* out);
+
+/* static cv::Mat Stabilizer::composeHomography(params, rot_center)
+ * include/stabilizer.hpp:242, src/stabilizer.cpp:1535-1566 */
+void vstab_compose_homography(const vstab_hparams* p, double cx, double cy, double H[9]);
+
+const char* vstab_last_error(const vstab_t* s);      /* message of the last non-OK status */
+const char* vstab_status_string(vstab_status st);
+int vstab_abi_version(void);
+
+/* Pinned host memory for frame buffers (what cv::Mat's allocator is to the reference);
+ * vstab_stabilize_frame() is fastest with buffers from here. */
+void* vstab_host_alloc(size_t bytes);
+void vstab_host_free(void* p);
+
+/* ---- parity taps ------------------------------------------------------------------ */
+/* Device->host dumps of the per-stage state after the most recent stabilize call, for
+ * the parity tests (the reference has no equivalent; its state is private:
+ * include/stabilizer.hpp:430-474). Each returns the element count written. */
+typedef enum vstab_tap {
+    VSTAB_TAP_GRAY = 0,        /* u8  working_h*working_w   current gray (src/stabilizer.cpp:1175) */
+    VSTAB_TAP_PYR1 = 1,        /* u8  level-1 of the LK pyramid of the current gray               */
+    VSTAB_TAP_PYR2 = 2,
+    VSTAB_TAP_PYR3 = 3,
+    VSTAB_TAP_PREV_PTS = 4,    /* f32 2*n   corners tracked in this call (prevPoints_, :1187)     */
+    VSTAB_TAP_LK_PTS = 5,      /* f32 2*n   raw LK result for those corners                       */
+    VSTAB_TAP_LK_STATUS = 6,   /* u8  n                                                           */
+    VSTAB_TAP_NEW_PTS = 7,     /* f32 2*m   corners detected on the current gray (:1318)          */
+    VSTAB_TAP_T = 8,           /* f64 9     transform pushed into the window (:1209)              */
+    VSTAB_TAP_M = 9,           /* f64 6     similarity before scale kill (:224)                   */
+    VSTAB_TAP_H_STABILIZE = 10,/* f64 9     H_stabilize (working-res, :1266-1288)                 */
+    VSTAB_TAP_H_SCALED = 11,   /* f64 9     H_stabilize_scaled (:1291-1296)                       */
+    VSTAB_TAP_BORDER = 12,     /* u8  3     border colour after saturate_cast (:1309)             */
+    VSTAB_TAP_EIG = 13,        /* f32 working_h*working_w  min-eigenvalue map of the current gray  */
+    VSTAB_TAP_INLIERS = 14,    /* i32 2     {n tracked, n RANSAC inliers}                         */
+    VSTAB_TAP_CHANNEL_SUMS = 15/* u64 3     per-channel byte sums of the presentation frame       */
+} vstab_tap;
+long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes);
+int vstab_working_width(const vstab_t* s);
+int vstab_working_height(const vstab_t* s);
+long vstab_presentation_index(const vstab_t* s);    /* absolute index of the frame last output */
+
+/* ---- offline (frame-sharded) mode ---------------------------------------------------
+ * BASELINE.json north_star: a clip is sharded by contiguous frame ranges with a halo
+ * frame; each GPU estimates its frame-pair transforms, the per-frame 3x3 are
+ * all-gathered (by the caller, e.g. ncclAllGather on `d_T`), then each GPU smooths and
+ * warps its own frames.  Index algebra: SURVEY.md Appendix C; results equal the
+ * streaming calls above for every call index.  All pointers are DEVICE pointers. */
+typedef struct vstab_offline vstab_offline_t;
+
+vstab_status vstab_offline_create(size_t past_frames, size_t future_frames, int working_height,
+                                  int rows, int cols, int max_batch, int device,
+                                  vstab_offline_t** out);
+void vstab_offline_destroy(vstab_offline_t* o);
+
+/* Estimate T[f] (maps frame f-1 -> f, src/stabilizer.cpp:1187-1209) for the `n` frames
+ * d_frames[0..n) whose absolute indices are first..first+n-1.  `d_halo` is frame first-1
+ * (NULL when first == 0: T[0] is then identity and unused).  Writes 9 doubles per frame
+ * to d_T[0..9n) and, when d_sums != NULL, the per-channel byte sums of each frame
+ * (3 x u64 per frame: the cv::mean numerator of src/stabilizer.cpp:1309, a by-product of
+ * the ingest pass) to d_sums[0..3n).  n <= max_batch. */
+vstab_status vstab_offline_estimate(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
+                                    size_t step, int n, long first, const uint8_t* d_halo,
+                                    double* d_T, unsigned long long* d_sums);
+
+/* Produce the outputs of stabilizeFrame calls call_first..call_first+n-1 of a clip of
+ * `n_total` frames given ALL transforms d_T_all[9*n_total] (T[0] ignored).  Call c
+ * presents frame p = max(0, c - future); d_frames / d_sums are indexed by (p - frame_base).
+ * mode: VSTAB_GLOBAL_SMOOTHING, or VSTAB_ACCUMULATED_FULL_LOCK with `lock_call` = the call
+ * index at which setStabilizationMode was issued (>= future; earlier calls are smoothed). */
+vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
+                                  size_t step, long frame_base, int n, long call_first,
+                                  const double* d_T_all, long n_total, int mode, long lock_call,
+                                  const unsigned long long* d_sums,
+                                  uint8_t* d_out, size_t out_frame_stride, size_t out_step);
+/* Clip-wide preparation for a mode, given ALL transforms: for ACCUMULATED_FULL_LOCK the prefix
+ * scan acc[k] = T[k]*...*T[anchor+1] (anchor = lock_call - future) over the 3x3 transforms
+ * (src/stabilizer.cpp:317-338).  Must precede vstab_offline_render in that mode. */
+vstab_status vstab_offline_prepare(vstab_offline_t* o, const double* d_T_all, long n_total, int mode,
+                                   long lock_call);
+vstab_status vstab_offline_synchronize(vstab_offline_t* o);
+/* per-stage device time (CUDA events on the instance stream) accumulated since the last call:
+ * ms[8]/counts[8] = ingest, pyramid, gftt, lk, fit, smooth, warp, acc-scan */
+void vstab_offline_set_timing(vstab_offline_t* o, int enable);
+vstab_status vstab_offline_stage_times(vstab_offline_t* o, float* ms, int* counts);
+/* number of this library's kernels launched by the process so far */
+long long vstab_launch_count(void);
+/* device-side H_stabilize_scaled of the last render (9 doubles per call) for parity tests */
+long vstab_offline_read_h(vstab_offline_t* o, double* dst, size_t n_calls);
+/* cudaStream_t of the instance, as an integer handle, so callers can order NCCL work after it */
+uintptr_t vstab_offline_stream(vstab_offline_t* o);
+
+/* ---- simulator frame source (CameraEngine::renderFrame, src/camera_engine.cpp:158-172) --
+ * Renders `n` frames on the device from a device-resident BGR texture; poses are
+ * (x, y, z, pan, tilt, roll) doubles per frame (CameraParams, include/camera_engine.hpp:44-74),
+ * host pointer.  Used to feed synthetic clips without PCIe traffic. */
+vstab_status vstab_render_frames(int device, const uint8_t* d_texture, int tex_rows, int tex_cols,
+                                 const double* poses, int n, int rows, int cols, double focal,
+                                 uint8_t* d_out, size_t frame_stride, size_t step);
+
+/* ---- single-kernel entry points (host buffers; used by the kernel parity tests) ------ */
+vstab_status vstab_k_ingest(int device, const uint8_t* bgr, int rows, int cols, size_t step,
+                            int working_height, uint8_t* gray_out, uint64_t sums_out[3]);
+vstab_status vstab_k_pyramid(int device, const uint8_t* gray, int rows, int cols,
+                             uint8_t* l1, uint8_t* l2, uint8_t* l3);
+vstab_status vstab_k_gftt(int device, const uint8_t* gray, int rows, int cols, int max_corners,
+                          double quality, int min_distance, float* pts_out, int* n_out,
+                          float* eig_out /* may be NULL */);
+vstab_status vstab_k_lk(int device, const uint8_t* prev, const uint8_t* next, int rows, int cols,
+                        const float* pts, int n, float* out_pts, uint8_t* status);
+vstab_status vstab_k_fit(int device, const float* prev_pts, const float* next_pts,
+                         const uint8_t* status, int n, double thresh, int work_w, int work_h,
+                         double M_out[6], double T_out[9], int counts_out[2]);
+vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, int cols, size_t step,
+                          const double H[9], const uint8_t border[3], uint8_t* out, size_t out_step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSTAB_H_ */

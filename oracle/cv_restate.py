@@ -306,7 +306,7 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
             A22 = F32(F32(np.sum(Iy.astype(np.float32) * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
             D = F32(A11 * A22 - A12 * A12)
             mineig = F32((A22 + A11 - np.sqrt(F32((A11 - A22) * (A11 - A22) + F32(4.0) * A12 * A12))) / F32(2 * win * win))
-            if mineig < min_eig or D < np.finfo(np.float32).eps:
+            if float(mineig) < min_eig or D < np.finfo(np.float32).eps:   # OpenCV compares in double
                 if level == 0:
                     status[i] = 0
                 continue
@@ -336,9 +336,9 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
                 nx = F32(nx + ddx)
                 ny = F32(ny + ddy)
                 out[i] = (F32(nx + F32(half)), F32(ny + F32(half)))
-                if ddx * ddx + ddy * ddy <= eps * eps:
+                if float(ddx) * float(ddx) + float(ddy) * float(ddy) <= eps * eps:   # Point2f::ddot -> double
                     break
-                if j > 0 and abs(ddx + pdx) < 0.01 and abs(ddy + pdy) < 0.01:
+                if j > 0 and float(abs(F32(ddx + pdx))) < 0.01 and float(abs(F32(ddy + pdy))) < 0.01:
                     out[i, 0] = F32(out[i, 0] - ddx * F32(0.5))
                     out[i, 1] = F32(out[i, 1] - ddy * F32(0.5))
                     break
@@ -480,3 +480,101 @@ def ls_similarity(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
     tx = mq[0] - (a * mp[0] - b * mp[1])
     ty = mq[1] - (b * mp[0] + a * mp[1])
     return np.array([[a, -b, tx], [b, a, ty]])
+
+
+class CvRNG:
+    """cv::RNG (multiply-with-carry), state seeded with (uint64)-1 by
+    RANSACPointSetRegistrator::run."""
+    COEFF = 4164903690
+
+    def __init__(self, state: int = 0xFFFFFFFFFFFFFFFF):
+        self.state = state if state else 0xFFFFFFFF
+
+    def next(self) -> int:
+        self.state = ((self.state & 0xFFFFFFFF) * self.COEFF + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform(self, a: int, b: int) -> int:
+        return a if a == b else int(self.next() % (b - a) + a)
+
+
+def ransac_update_num_iters(p: float, ep: float, model_points: int, max_iters: int) -> int:
+    p = min(max(p, 0.0), 1.0)
+    ep = min(max(ep, 0.0), 1.0)
+    num = max(1.0 - p, 2.2250738585072014e-308)
+    denom = 1.0 - (1.0 - ep) ** model_points
+    if denom < 2.2250738585072014e-308:
+        return 0
+    num = math.log(num)
+    denom = math.log(denom)
+    if denom >= 0 or -num >= max_iters * (-denom):
+        return max_iters
+    return int(np.rint(num / denom))
+
+
+def similarity_from_2(p0, p1, q0, q1):
+    """AffinePartial2DEstimatorCallback::runKernel (2-point similarity), f64."""
+    x1, y1, x2, y2 = float(p0[0]), float(p0[1]), float(p1[0]), float(p1[1])
+    X1, Y1, X2, Y2 = float(q0[0]), float(q0[1]), float(q1[0]), float(q1[1])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.float64(1.0) / np.float64((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2))
+        S0 = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2))
+        S1 = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2))
+        S2 = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2))
+        S3 = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2))
+    return np.array([[S0, -S1, S2], [S1, S0, S3]], dtype=np.float64)
+
+
+def similarity_errors(M, src, dst):
+    """Affine2DEstimatorCallback::computeError: model cast to float, float math."""
+    F = M.astype(np.float32).reshape(-1)
+    fx, fy = src[:, 0].astype(np.float32), src[:, 1].astype(np.float32)
+    a = ((F[0] * fx + F[1] * fy) + F[2]) - dst[:, 0].astype(np.float32)
+    b = ((F[3] * fx + F[4] * fy) + F[5]) - dst[:, 1].astype(np.float32)
+    return (a * a + b * b).astype(np.float32)
+
+
+def ransac_similarity(src, dst, thresh=3.0, max_iters=2000, confidence=0.99):
+    """RANSACPointSetRegistrator::run for the 2-point similarity model.
+    Returns (best_model 2x3 f64 or None, inlier mask u8)."""
+    count = len(src)
+    if count < 2:
+        return None, np.zeros(count, np.uint8)
+    rng = CvRNG()
+    niters = max(max_iters, 1)
+    best_mask = np.zeros(count, np.uint8)
+    best_model = None
+    max_good = 0
+    t = np.float32(thresh * thresh)
+    if count == 2:
+        return similarity_from_2(src[0], src[1], dst[0], dst[1]), np.ones(2, np.uint8)
+    it = 0
+    while it < niters:
+        i0 = rng.uniform(0, count)
+        while True:
+            i1 = rng.uniform(0, count)
+            if i1 != i0:
+                break
+        M = similarity_from_2(src[i0], src[i1], dst[i0], dst[i1])
+        with np.errstate(invalid="ignore", over="ignore"):
+            err = similarity_errors(M, src, dst)
+            mask = (err <= t).astype(np.uint8)
+        good = int(mask.sum())
+        if good > max(max_good, 1):
+            best_mask, best_model, max_good = mask, M, good
+            niters = ransac_update_num_iters(confidence, float(count - good) / count, 2, niters)
+        it += 1
+    if max_good > 0:
+        return best_model, best_mask
+    return None, np.zeros(count, np.uint8)
+
+
+def estimate_affine_partial_2d(src, dst, thresh=3.0):
+    """cv::estimateAffinePartial2D(RANSAC) = RANSAC consensus + LM refinement, the
+    latter restated by its fixed point: closed-form LS similarity on the inliers."""
+    M, mask = ransac_similarity(src, dst, thresh)
+    if M is None:
+        return None, mask
+    if len(src) > 2 and mask.sum() > 0:
+        M = ls_similarity(src[mask == 1], dst[mask == 1])
+    return M, mask

@@ -1,0 +1,115 @@
+"""T0: the numpy restatements of the OpenCV primitives (oracle/cv_restate.py) against cv2
+4.13.0 and against the committed golden vectors.  CPU only."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import cv_restate as R
+
+
+def test_gray_bit_exact():
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    assert np.array_equal(R.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+@pytest.mark.parametrize("sh,sw,wh", [(720, 1280, 360), (1080, 1920, 360), (540, 960, 135), (480, 854, 360),
+                                      (600, 800, 240), (360, 640, 360), (250, 333, 100)])
+def test_resize_linear_bit_exact(sh, sw, wh):
+    rng = np.random.default_rng(sh + wh)
+    src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    dw, dh, _ = R.working_size(sh, sw, wh)
+    assert np.array_equal(R.resize_linear_bgr(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_golden_gray(golden):
+    f0 = golden["f0"]
+    for wh in (180, 120, 100, 360):
+        dw, dh, _ = R.working_size(f0.shape[0], f0.shape[1], wh)
+        assert np.array_equal(R.bgr2gray(R.resize_linear_bgr(f0, dw, dh)), golden[f"gray_wh{wh}"])
+
+
+@pytest.mark.parametrize("shape", [(360, 640), (180, 320), (45, 80), (91, 173)])
+def test_pyrdown_bit_exact(shape):
+    rng = np.random.default_rng(shape[0])
+    g = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(R.pyr_down(g), cv2.pyrDown(g))
+
+
+def test_golden_pyramid(golden):
+    lv = R.lk_pyramid(golden["g0"])
+    for l in (1, 2, 3):
+        assert np.array_equal(lv[l], golden[f"g0_pyr{l}"])
+
+
+def test_warp_bit_exact(golden):
+    f0 = golden["f0"]
+    bd = tuple(golden["warp_border"])
+    assert np.allclose(R.border_value(f0), bd, rtol=0, atol=1e-9)
+    for i in range(2):
+        out = R.warp_perspective_bgr(f0, golden[f"warp_H{i}"], bd)
+        assert np.array_equal(out, golden[f"warp_out{i}"])
+
+
+def test_warp_weight_table_is_arithmetic():
+    """The Q15 weights are (32-ay)(32-ax)*32 etc. except the saturated (0,0) entry."""
+    tab = R.warp_bilinear_tab()
+    for ay in range(32):
+        for ax in range(32):
+            w = [(32 - ay) * (32 - ax) * 32, (32 - ay) * ax * 32, ay * (32 - ax) * 32, ay * ax * 32]
+            if ax == 0 and ay == 0:
+                assert list(tab[ay, ax]) == [32767, 1, 0, 0]
+            else:
+                assert list(tab[ay, ax]) == w
+
+
+def test_invert3_matches_cv():
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        H = np.eye(3) + rng.normal(0, 0.05, (3, 3))
+        assert np.array_equal(R.invert3x3(H), cv2.invert(H)[1])
+
+
+def test_gftt_identical_list(golden):
+    g0 = golden["g0"]
+    md = int(golden["gftt_min_distance"])
+    e = R.corner_min_eigen_val(g0)
+    eref = golden["eig0"]
+    # f64 running column sums inside OpenCV's box filter leave 1-ulp residues on a few pixels
+    assert (e != eref).mean() < 2e-3
+    assert np.abs(e - eref).max() <= 1e-7 * eref.max()
+    pts = R.good_features_to_track(g0, 1300, 0.01, md, eig=e)
+    assert np.array_equal(pts, golden["corners0"])
+
+
+def test_lk_matches_golden(golden):
+    pts = golden["corners0"][::3]
+    out, st = R.calc_optical_flow_pyr_lk(golden["g0"], golden["g1"], pts)
+    assert np.array_equal(st, golden["lk_status"][::3])
+    ok = st == 1
+    assert np.abs(out[ok] - golden["lk_pts"][::3][ok]).max() <= 1e-3    # tolerance: 0.05 px (north star)
+
+
+def test_ransac_exact_consensus(golden):
+    p, q = golden["ransac_p"], golden["ransac_q"]
+    corners = np.array([[0, 0, 1], [320, 0, 1], [0, 180, 1], [320, 180, 1]], float).T
+    for thr in (3, 5):
+        M, mask = R.estimate_affine_partial_2d(p, q, float(thr))
+        assert np.array_equal(mask, golden[f"ransac_inl_thr{thr}"])
+        assert np.abs(M @ corners - golden[f"ransac_M_thr{thr}"] @ corners).max() < 1e-9
+
+
+def test_ransac_random_vs_cv2():
+    rng = np.random.default_rng(6)
+    for trial in range(25):
+        n = int(rng.integers(12, 900))
+        p = np.stack([rng.uniform(0, 640, n), rng.uniform(0, 360, n)], 1).astype(np.float32)
+        th = rng.uniform(-0.03, 0.03)
+        A = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        q = (p @ A.T + rng.uniform(-8, 8, 2) + rng.normal(0, 0.3, (n, 2))).astype(np.float32)
+        bad = rng.random(n) < rng.choice([0, 0.05, 0.3, 0.7])
+        q[bad] += rng.uniform(-40, 40, (bad.sum(), 2)).astype(np.float32)
+        Mr, inl = cv2.estimateAffinePartial2D(p.reshape(-1, 1, 2), q.reshape(-1, 1, 2), method=cv2.RANSAC)
+        M, mask = R.estimate_affine_partial_2d(p, q, 3.0)
+        assert np.array_equal(mask, inl.reshape(-1))
+        assert np.abs(M - Mr).max() < 1e-8

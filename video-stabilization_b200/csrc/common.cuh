@@ -1,0 +1,50 @@
+// Shared helpers for the sm_100a kernels of the stabilizer hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vstabk {
+
+#define VSTAB_HD __host__ __device__ __forceinline__
+#define VSTAB_D __device__ __forceinline__
+
+constexpr int kMaxCorners = 1300;          // MAX_FEATURES_TO_DETECT, src/stabilizer.cpp:935
+constexpr int kLkWin = 21;                 // WINDOW_SIZE, src/stabilizer.cpp:185
+constexpr int kLkLevels = 4;               // MAX_PYRAMID_LEVEL 3 => 4 levels, :186
+constexpr int kLkMaxIter = 50;             // TERM_CRITERIA count, :187-188
+constexpr int kMinPointsForMotion = 10;    // MIN_POINTS_FOR_MOTION_ESTIMATION, :20
+
+// BORDER_REFLECT_101 index for i in [-n+1, 2n-2]
+VSTAB_HD int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+// cv::COLOR_BGR2GRAY 8U: (3735 B + 19235 G + 9798 R + 16384) >> 15   
+VSTAB_HD int luma_q15(int b, int g, int r) {
+    return (3735 * b + 19235 * g + 9798 * r + 16384) >> 15;
+}
+
+// A device-resident gray pyramid of one frame: level l is (w[l] x h[l]) u8, tight rows.
+struct PyrDesc {
+    int w[kLkLevels];
+    int h[kLkLevels];
+    size_t off[kLkLevels];   // byte offset of level l inside one frame's pyramid block
+    size_t frame_bytes;      // bytes of one frame's pyramid block (all levels)
+};
+
+template <typename T>
+VSTAB_D T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+VSTAB_D long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace vstabk

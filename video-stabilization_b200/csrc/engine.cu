@@ -1,0 +1,855 @@
+// Host side of the C ABI (include/vstab.h): the streaming Stabilizer instance, the offline
+// (frame-sharded) runner and the single-kernel test entry points.  This file only
+// orchestrates: all arithmetic of the hot path runs in the kernels of this directory,
+// there is no CPU fallback (every entry point needs a CUDA device).
+//
+// Streaming state mirrors class Stabilizer (/root/reference/include/stabilizer.hpp:430-474)
+// but lives in device memory: a ring of W = past+1+future full-resolution frames (the
+// reference's deque of cloned cv::Mat, :437), the per-slot channel sums, two gray pyramids
+// (prevGray_/gray, :439), the corner list (prevPoints_, :440), a ring of 3x3 transforms
+// and the accumulated transform (:444).  The host keeps only integer indices, so a call
+// enqueues kernels and copies without ever reading a result back except the output frame.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/vstab.h"
+#include "homography.cuh"
+#include "kernels.h"
+
+using namespace vstabk;
+
+namespace vstabk {
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace vstabk
+
+namespace {
+
+// Per-stage device timing with CUDA events on the instance stream (bench.py's roofline numbers).
+enum Stage { ST_INGEST = 0, ST_PYRAMID, ST_GFTT, ST_LK, ST_FIT, ST_SMOOTH, ST_WARP, ST_ACC, ST_COUNT };
+struct StageTimer {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[ST_COUNT];
+    void begin(int s, cudaStream_t q) {
+        if (!enabled) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        ev[s].push_back({a, b});
+        cudaEventRecord(a, q);
+    }
+    void end(int s, cudaStream_t q) { if (enabled) cudaEventRecord(ev[s].back().second, q); }
+    // sums and clears; returns launches (event pairs) per stage in counts
+    void collect(float* ms, int* counts) {
+        for (int s = 0; s < ST_COUNT; ++s) {
+            float tot = 0.f;
+            for (auto& pr : ev[s]) {
+                float t = 0.f;
+                cudaEventSynchronize(pr.second);
+                cudaEventElapsedTime(&t, pr.first, pr.second);
+                tot += t;
+                cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+            }
+            ms[s] = tot; counts[s] = (int)ev[s].size();
+            ev[s].clear();
+        }
+    }
+    ~StageTimer() { float m[ST_COUNT]; int c[ST_COUNT]; collect(m, c); }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+            return VSTAB_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+thread_local std::string g_err;   // for entry points without an instance
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) {
+        if (p) { cudaFree(p); p = nullptr; }
+        return cudaMalloc(&p, bytes ? bytes : 1);
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+// Everything that depends only on (rows, cols, working height) and a frame-batch capacity.
+struct Geometry {
+    int rows = 0, cols = 0, wh = 0, ww = 0;
+    double scale = 1.0;
+    size_t pitch = 0, frame_bytes = 0;
+    PyrDesc pd{};
+    IngestPlan plan{};
+    DevBuf xtab, ytab;
+    int min_distance = 0;
+
+    vstab_status init(int r, int c, int working_height, std::string& err) {
+        rows = r; cols = c; wh = working_height;
+        scale = (double)working_height / (double)r;                     // stabilizer.cpp:117
+        ww = (int)(c * scale);                                         // stabilizer.cpp:118
+        if (ww < 8 || wh < 8) { err = "working size too small"; return VSTAB_ERR_INVALID_ARGUMENT; }
+        pitch = align_up((size_t)c * 3, 16);
+        frame_bytes = align_up(pitch * (size_t)r, 256);
+        pd = make_pyr_desc(ww, wh);
+        plan.src_w = c; plan.src_h = r; plan.dst_w = ww; plan.dst_h = wh;
+        plan.mode = (ww == c && wh == r) ? 0 : ((c == 2 * ww && r == 2 * wh) ? 1 : 2);
+        plan.rows_per_band = wh >= 360 ? 2 : 1;
+        if (wh >= 1080) plan.rows_per_band = 4;
+        plan.nbands = (wh + plan.rows_per_band - 1) / plan.rows_per_band;
+        std::vector<int4> hx(ww), hy(wh);
+        build_ingest_tables(c, ww, plan.mode, hx.data());
+        build_ingest_tables(r, wh, plan.mode, hy.data());
+        if (xtab.alloc(sizeof(int4) * ww) != cudaSuccess || ytab.alloc(sizeof(int4) * wh) != cudaSuccess) {
+            err = "cudaMalloc(ingest tables) failed"; return VSTAB_ERR_CUDA;
+        }
+        if (cudaMemcpy(xtab.p, hx.data(), sizeof(int4) * ww, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(ytab.p, hy.data(), sizeof(int4) * wh, cudaMemcpyHostToDevice) != cudaSuccess) {
+            err = "cudaMemcpy(ingest tables) failed"; return VSTAB_ERR_CUDA;
+        }
+        plan.xtab = xtab.as<int4>();
+        plan.ytab = ytab.as<int4>();
+        min_distance = (int)(10 * ((double)wh / 720.0));                // stabilizer.cpp:938-940
+        return VSTAB_OK;
+    }
+};
+
+bool device_ok(int device, std::string& err) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return false;
+    }
+    if (device < 0 || device >= n) { err = "bad device index"; return false; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; return false; }
+    if (p.major < 10) {
+        err = "device is sm_" + std::to_string(p.major * 10 + p.minor) + "; kernels are built for sm_100a only";
+        return false;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
+    return true;
+}
+
+}  // namespace
+
+// =====================================================================================
+// streaming instance
+// =====================================================================================
+struct vstab {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    size_t P = 15, F = 15;
+    int working_height = 360;
+    int mode = VSTAB_GLOBAL_SMOOTHING;
+    long lock_call = 0;          // call index at which the current mode was set
+    bool acc_valid = false;      // accumulatedTransform_.H non-empty
+    long acc_to = -1;            // accumulatedTransform_.to_frame_idx
+    long n = 0;                  // number of frames pushed so far == index of the next call
+    long last_presented = 0;
+    bool inited = false;
+    Geometry g;
+    long W = 0;                  // window size in frames
+    DevBuf ring, sums, pyr0, pyr1, corners0, corners1, ccount, lkpts, lkstat, T, Mtap, fitc, acc, wp, gmem, dout;
+    long t_mod = 0;
+    GfttWorkspace gws{};
+    std::string err;
+
+    void set_err(const std::string& e) { err = e; }
+    uint8_t* pyr(int i) { return (i & 1) ? pyr1.as<uint8_t>() : pyr0.as<uint8_t>(); }
+    float2* corners(int i) { return (i & 1) ? corners1.as<float2>() : corners0.as<float2>(); }
+};
+
+static vstab_status stream_init(vstab* s, int rows, int cols) {
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    vstab_status st = s->g.init(rows, cols, s->working_height, s->err);
+    if (st != VSTAB_OK) return st;
+    Geometry& g = s->g;
+    s->W = (long)(s->P + 1 + s->F);
+    s->t_mod = s->W + 2;
+    CK(s->ring.alloc(g.frame_bytes * (size_t)s->W + 64));
+    CK(s->sums.alloc(sizeof(unsigned long long) * 3 * s->W));
+    CK(s->pyr0.alloc(g.pd.frame_bytes));
+    CK(s->pyr1.alloc(g.pd.frame_bytes));
+    CK(s->corners0.alloc(sizeof(float2) * kMaxCorners));
+    CK(s->corners1.alloc(sizeof(float2) * kMaxCorners));
+    CK(s->ccount.alloc(sizeof(int) * 2));
+    CK(s->lkpts.alloc(sizeof(float2) * kMaxCorners));
+    CK(s->lkstat.alloc(kMaxCorners));
+    CK(s->T.alloc(sizeof(double) * 9 * s->t_mod));
+    CK(s->Mtap.alloc(sizeof(double) * 6));
+    CK(s->fitc.alloc(sizeof(int) * 2));
+    CK(s->acc.alloc(sizeof(double) * 9));
+    CK(s->wp.alloc(sizeof(WarpParams)));
+    CK(s->dout.alloc(g.frame_bytes + 64));
+    size_t gbytes = gftt_workspace_bytes(g.ww, g.wh, g.min_distance, 1, &s->gws);
+    CK(s->gmem.alloc(gbytes));
+    gftt_bind_workspace(s->gmem.p, &s->gws);
+    CK(cudaMemsetAsync(s->ccount.p, 0, sizeof(int) * 2, s->stream));
+    CK(cudaMemsetAsync(s->T.p, 0, sizeof(double) * 9 * s->t_mod, s->stream));
+    s->inited = true;
+    return VSTAB_OK;
+}
+
+// Enqueue the whole per-frame pipeline for frame index s->n whose pixels are already in
+// ring slot n % W.  `d_out`/`out_pitch`: where the warped presentation frame goes.
+static vstab_status stream_process(vstab* s, uint8_t* d_out, size_t out_pitch) {
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    Geometry& g = s->g;
+    cudaStream_t q = s->stream;
+    const long n = s->n;
+    const long slot = n % s->W;
+    const int cur = (int)(n & 1), prev = cur ^ 1;
+    const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)slot * g.frame_bytes;
+    unsigned long long* sums = s->sums.as<unsigned long long>() + slot * 3;
+    int* ccount = s->ccount.as<int>();
+
+    CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3, q));
+    launch_ingest(g.plan, frame, g.pitch, g.frame_bytes, 1, s->pyr(cur), g.pd.frame_bytes, sums, q);   // :1169-1175
+    launch_pyramid(g.pd, s->pyr(cur), 1, q);
+    if (n == 0) {                                                                                      // :1178-1182
+        launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
+                    s->corners(cur), ccount + cur, q);
+        CK(cudaGetLastError());
+        s->last_presented = 0;
+        return VSTAB_OK;
+    }
+    // :1187 trackFeatures
+    launch_lk(s->pyr(prev), s->pyr(cur), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
+              s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), q);
+    // :1203 estimateMotion, :1209 updateTransformations
+    launch_fit(s->corners(prev), s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), ccount + prev, 1, 3.0,
+               g.ww / 2.0, g.wh / 2.0, s->T.as<double>() + (size_t)(n % s->t_mod) * 9, s->Mtap.as<double>(),
+               s->fitc.as<int>(), nullptr, n, q);
+    const long p = n - (long)s->F > 0 ? n - (long)s->F : 0;                                            // :1226-1229
+    if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) {                                                      // :317-338
+        launch_acc_update(s->T.as<double>(), s->t_mod, p, s->acc_valid ? 0 : 1, s->acc.as<double>(), q);
+        s->acc_valid = true;
+        s->acc_to = p;
+    }
+    SmoothArgs a{};
+    a.T = s->T.as<double>(); a.t_mod = s->t_mod;
+    a.P = (int)s->P; a.F = (int)s->F;
+    a.mode = s->mode; a.lock_call = s->lock_call;
+    a.acc = s->acc.as<double>(); a.acc_mod = 0;
+    a.scale = g.scale;
+    a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
+    a.npix = (double)g.rows * (double)g.cols;
+    launch_smooth(a, n, 1, s->wp.as<WarpParams>(), q);                                                 // :1234-1296
+    launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
+                d_out, out_pitch, 0, q);                                                               // :1309-1313
+    launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
+                s->corners(cur), ccount + cur, q);                                                     // :1318
+    CK(cudaGetLastError());
+    s->last_presented = p;
+    return VSTAB_OK;
+}
+
+static vstab_status stream_check_args(vstab* s, const void* in, int rows, int cols, size_t step, const void* out,
+                                      size_t out_step) {
+    if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!in || !out) { s->err = "null image pointer"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (rows <= 10 || cols <= 10) {                                                                    // :99-103
+        s->err = "Stabilizer: Frame has invalid size. Rows: " + std::to_string(rows) + ", Cols: " + std::to_string(cols);
+        return VSTAB_ERR_INVALID_ARGUMENT;
+    }
+    if (step < (size_t)cols * 3 || out_step < (size_t)cols * 3) { s->err = "row step smaller than 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (s->inited && (s->g.rows != rows || s->g.cols != cols)) {                                        // :110-112
+        s->err = "Stabilizer: Frame size has changed. This is not supported.";
+        return VSTAB_ERR_SIZE_CHANGED;
+    }
+    if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK && s->acc_valid) {
+        // the reference asserts presentation_frame_idx > 0 and from_frame_idx == acc.to (:329-332);
+        // both fail exactly when the presentation frame did not advance
+        const long p = s->n - (long)s->F > 0 ? s->n - (long)s->F : 0;
+        if (p != s->acc_to + 1) {
+            s->err = "ACCUMULATED_FULL_LOCK before the window can advance (reference asserts, stabilizer.cpp:329)";
+            return VSTAB_ERR_STATE;
+        }
+    }
+    return VSTAB_OK;
+}
+
+extern "C" {
+
+int vstab_abi_version(void) { return VSTAB_ABI_VERSION; }
+
+const char* vstab_status_string(vstab_status st) {
+    switch (st) {
+        case VSTAB_OK: return "ok";
+        case VSTAB_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case VSTAB_ERR_SIZE_CHANGED: return "frame size changed";
+        case VSTAB_ERR_CUDA: return "CUDA error";
+        case VSTAB_ERR_UNSUPPORTED: return "unsupported";
+        case VSTAB_ERR_STATE: return "invalid state";
+    }
+    return "?";
+}
+
+vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_height, int device, vstab_t** out) {
+    if (!out) return VSTAB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    // argument checks of Stabilizer::Stabilizer, stabilizer.cpp:40-49
+    if (past_frames == 0 && future_frames == 0) { g_err = "Stabilizer: pastFrames and futureFrames cannot both be 0"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if ((double)working_height <= 90.0) { g_err = "Stabilizer: workingHeight must be greater than 90.000000"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (working_height > 2160) { g_err = "Stabilizer: workingHeight must be no more than 2160"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    vstab* s = new (std::nothrow) vstab();
+    if (!s) return VSTAB_ERR_CUDA;
+    s->device = device; s->P = past_frames; s->F = future_frames; s->working_height = working_height;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_err = "cudaStreamCreate failed"; delete s; return VSTAB_ERR_CUDA;
+    }
+    *out = s;
+    return VSTAB_OK;
+}
+
+void vstab_destroy(vstab_t* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    delete s;
+}
+
+vstab_status vstab_set_mode(vstab_t* s, int mode) {
+    if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (mode < 0 || mode > 5) { s->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (mode == VSTAB_ORB_FULL_LOCK || mode == VSTAB_SIFT_FULL_LOCK) {
+        s->err = "ORB/SIFT registration modes are not built yet (DESIGN.md, SURVEY 8a rows a11-a16)";
+        return VSTAB_ERR_UNSUPPORTED;
+    }
+    // stabilizer.cpp:55-70: reset reference + accumulator, keep window / prevGray_ / prevPoints_
+    s->acc_valid = false;
+    s->acc_to = -1;
+    s->mode = mode;
+    s->lock_call = s->n;
+    return VSTAB_OK;
+}
+
+int vstab_get_mode(const vstab_t* s) { return s ? s->mode : -1; }
+
+size_t vstab_total_frame_window_size(const vstab_t* s) { return s ? s->P + 1 + s->F : 0; }
+
+vstab_status vstab_synchronize(vstab_t* s) {
+    if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    return VSTAB_OK;
+}
+
+vstab_status vstab_stabilize_frame(vstab_t* s, const uint8_t* bgr, int rows, int cols, size_t step,
+                                   uint8_t* out_bgr, size_t out_step) {
+    vstab_status st = stream_check_args(s, bgr, rows, cols, step, out_bgr, out_step);
+    if (st != VSTAB_OK) return st;
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    CK(cudaSetDevice(s->device));
+    if (!s->inited) { st = stream_init(s, rows, cols); if (st != VSTAB_OK) return st; }
+    Geometry& g = s->g;
+    uint8_t* slot = s->ring.as<uint8_t>() + (size_t)(s->n % s->W) * g.frame_bytes;
+    CK(cudaMemcpy2DAsync(slot, g.pitch, bgr, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice, s->stream));
+    st = stream_process(s, s->dout.as<uint8_t>(), g.pitch);
+    if (st != VSTAB_OK) return st;
+    if (s->n == 0) {
+        // call 0 returns the input frame itself (:1181)
+        CK(cudaMemcpy2DAsync(out_bgr, out_step, slot, g.pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(out_bgr, out_step, s->dout.p, g.pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->n += 1;
+    return VSTAB_OK;
+}
+
+vstab_status vstab_stabilize_frame_device(vstab_t* s, const uint8_t* d_bgr, int rows, int cols, size_t step,
+                                          uint8_t* d_out_bgr, size_t out_step) {
+    vstab_status st = stream_check_args(s, d_bgr, rows, cols, step, d_out_bgr, out_step);
+    if (st != VSTAB_OK) return st;
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    CK(cudaSetDevice(s->device));
+    if (!s->inited) { st = stream_init(s, rows, cols); if (st != VSTAB_OK) return st; }
+    Geometry& g = s->g;
+    uint8_t* slot = s->ring.as<uint8_t>() + (size_t)(s->n % s->W) * g.frame_bytes;
+    CK(cudaMemcpy2DAsync(slot, g.pitch, d_bgr, step, (size_t)cols * 3, rows, cudaMemcpyDeviceToDevice, s->stream));
+    st = stream_process(s, d_out_bgr, out_step);
+    if (st != VSTAB_OK) return st;
+    if (s->n == 0)
+        CK(cudaMemcpy2DAsync(d_out_bgr, out_step, slot, g.pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToDevice, s->stream));
+    s->n += 1;
+    return VSTAB_OK;
+}
+
+int vstab_decompose_homography(const double H[9], double cx, double cy, vstab_hparams* out) {
+    if (!H || !out) return -1;
+    HParams hp;
+    if (!decompose_h(H, cx, cy, &hp)) return 0;
+    out->s = hp.s; out->theta = hp.theta; out->k = hp.k; out->delta = hp.delta;
+    out->t[0] = hp.t[0]; out->t[1] = hp.t[1]; out->v[0] = hp.v[0]; out->v[1] = hp.v[1];
+    return 1;
+}
+
+void vstab_compose_homography(const vstab_hparams* p, double cx, double cy, double H[9]) {
+    if (!p || !H) return;
+    HParams hp;
+    hp.s = p->s; hp.theta = p->theta; hp.k = p->k; hp.delta = p->delta;
+    hp.t[0] = p->t[0]; hp.t[1] = p->t[1]; hp.v[0] = p->v[0]; hp.v[1] = p->v[1];
+    compose_h(&hp, cx, cy, H);
+}
+
+const char* vstab_last_error(const vstab_t* s) { return s ? s->err.c_str() : g_err.c_str(); }
+
+void* vstab_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void vstab_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int vstab_working_width(const vstab_t* s) { return s && s->inited ? s->g.ww : 0; }
+int vstab_working_height(const vstab_t* s) { return s && s->inited ? s->g.wh : 0; }
+long vstab_presentation_index(const vstab_t* s) { return s ? s->last_presented : -1; }
+
+long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
+    if (!s || !s->inited || !dst || s->n == 0) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+    Geometry& g = s->g;
+    const long last = s->n - 1;                 // index of the most recent frame
+    const int cur = (int)(last & 1), prev = cur ^ 1;
+    auto copy = [&](const void* src, size_t bytes, long count) -> long {
+        if (bytes > dst_bytes) return -2;
+        if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return count;
+    };
+    int counts[2] = {0, 0};
+    if (cudaMemcpy(counts, s->ccount.p, sizeof(counts), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    switch (tap) {
+        case VSTAB_TAP_GRAY: return copy(s->pyr(cur) + g.pd.off[0], (size_t)g.ww * g.wh, (long)g.ww * g.wh);
+        case VSTAB_TAP_PYR1: case VSTAB_TAP_PYR2: case VSTAB_TAP_PYR3: {
+            const int l = tap - VSTAB_TAP_PYR1 + 1;
+            return copy(s->pyr(cur) + g.pd.off[l], (size_t)g.pd.w[l] * g.pd.h[l], (long)g.pd.w[l] * g.pd.h[l]);
+        }
+        case VSTAB_TAP_PREV_PTS: if (last == 0) return 0; return copy(s->corners(prev), sizeof(float2) * counts[prev], counts[prev]);
+        case VSTAB_TAP_LK_PTS: if (last == 0) return 0; return copy(s->lkpts.p, sizeof(float2) * counts[prev], counts[prev]);
+        case VSTAB_TAP_LK_STATUS: if (last == 0) return 0; return copy(s->lkstat.p, counts[prev], counts[prev]);
+        case VSTAB_TAP_NEW_PTS: return copy(s->corners(cur), sizeof(float2) * counts[cur], counts[cur]);
+        case VSTAB_TAP_T: if (last == 0) return 0; return copy(s->T.as<double>() + (size_t)(last % s->t_mod) * 9, sizeof(double) * 9, 9);
+        case VSTAB_TAP_M: if (last == 0) return 0; return copy(s->Mtap.p, sizeof(double) * 6, 6);
+        case VSTAB_TAP_H_STABILIZE: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, Hw), sizeof(double) * 9, 9);
+        case VSTAB_TAP_H_SCALED: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, Hs), sizeof(double) * 9, 9);
+        case VSTAB_TAP_BORDER: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, border), 3, 3);
+        case VSTAB_TAP_EIG: return copy(s->gws.eig, sizeof(float) * g.ww * g.wh, (long)g.ww * g.wh);
+        case VSTAB_TAP_INLIERS: if (last == 0) return 0; return copy(s->fitc.p, sizeof(int) * 2, 2);
+        case VSTAB_TAP_CHANNEL_SUMS:
+            return copy(s->sums.as<unsigned long long>() + (s->last_presented % s->W) * 3, sizeof(unsigned long long) * 3, 3);
+    }
+    return -1;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// offline (frame-sharded) runner
+// =====================================================================================
+struct vstab_offline {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    size_t P = 0, F = 0;
+    int max_batch = 0;
+    Geometry g;
+    DevBuf pyr, corners, ccount, lkpts, lkstat, Mtap, fitc, wp, gmem, acc, halo_sums;
+    GfttWorkspace gws{};
+    long acc_n_total = 0, acc_anchor = -1;
+    size_t acc_capacity = 0;
+    const double* acc_T = nullptr;
+    int last_ncalls = 0;
+    StageTimer timer;
+    std::string err;
+    void set_err(const std::string& e) { err = e; }
+};
+
+extern "C" {
+
+vstab_status vstab_offline_create(size_t past_frames, size_t future_frames, int working_height, int rows, int cols,
+                                  int max_batch, int device, vstab_offline_t** out) {
+    if (!out) return VSTAB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (past_frames == 0 && future_frames == 0) { g_err = "Stabilizer: pastFrames and futureFrames cannot both be 0"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if ((double)working_height <= 90.0 || working_height > 2160) { g_err = "Stabilizer: workingHeight out of range"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (rows <= 10 || cols <= 10 || max_batch < 1) { g_err = "invalid frame size or batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    vstab_offline* o = new (std::nothrow) vstab_offline();
+    if (!o) return VSTAB_ERR_CUDA;
+    auto fail = [&](vstab_status st, const std::string& m) { g_err = m; delete o; return st; };
+    o->device = device; o->P = past_frames; o->F = future_frames; o->max_batch = max_batch;
+    if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VSTAB_ERR_CUDA, "cudaStreamCreate failed");
+    vstab_status st = o->g.init(rows, cols, working_height, g_err);
+    if (st != VSTAB_OK) { delete o; return st; }
+    Geometry& g = o->g;
+    const size_t nb = (size_t)max_batch + 1;   // + halo
+    bool ok = o->pyr.alloc(g.pd.frame_bytes * nb) == cudaSuccess &&
+              o->corners.alloc(sizeof(float2) * kMaxCorners * nb) == cudaSuccess &&
+              o->ccount.alloc(sizeof(int) * nb) == cudaSuccess &&
+              o->lkpts.alloc(sizeof(float2) * kMaxCorners * nb) == cudaSuccess &&
+              o->lkstat.alloc(kMaxCorners * nb) == cudaSuccess &&
+              o->Mtap.alloc(sizeof(double) * 6 * nb) == cudaSuccess &&
+              o->fitc.alloc(sizeof(int) * 2 * nb) == cudaSuccess &&
+              o->wp.alloc(sizeof(WarpParams) * nb) == cudaSuccess &&
+              o->halo_sums.alloc(sizeof(unsigned long long) * 3) == cudaSuccess;
+    if (!ok) return fail(VSTAB_ERR_CUDA, "cudaMalloc(offline buffers) failed");
+    size_t gbytes = gftt_workspace_bytes(g.ww, g.wh, g.min_distance, (int)nb, &o->gws);
+    if (o->gmem.alloc(gbytes) != cudaSuccess) return fail(VSTAB_ERR_CUDA, "cudaMalloc(gftt workspace) failed");
+    gftt_bind_workspace(o->gmem.p, &o->gws);
+    *out = o;
+    return VSTAB_OK;
+}
+
+void vstab_offline_destroy(vstab_offline_t* o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    if (o->stream) { cudaStreamSynchronize(o->stream); cudaStreamDestroy(o->stream); }
+    delete o;
+}
+
+uintptr_t vstab_offline_stream(vstab_offline_t* o) { return o ? (uintptr_t)o->stream : 0; }
+
+vstab_status vstab_offline_synchronize(vstab_offline_t* o) {
+    if (!o) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    CK(cudaSetDevice(o->device));
+    CK(cudaStreamSynchronize(o->stream));
+    return VSTAB_OK;
+}
+
+}  // extern "C"
+
+// d_sums: [n][3] u64 per-channel byte sums of the n frames (device), may be NULL
+extern "C" vstab_status vstab_offline_estimate(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
+                                                size_t step, int n, long first, const uint8_t* d_halo,
+                                                double* d_T, unsigned long long* d_sums) {
+    if (!o || !d_frames || !d_T || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    if (n > o->max_batch) { o->err = "n exceeds max_batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (first > 0 && !d_halo) { o->err = "halo frame required when first > 0"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (step < (size_t)o->g.cols * 3) { o->err = "row step smaller than 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    CK(cudaSetDevice(o->device));
+    Geometry& g = o->g;
+    cudaStream_t q = o->stream;
+    uint8_t* pyr = o->pyr.as<uint8_t>();
+    // pyramid slot 0 = halo (frame first-1), slots 1..n = the batch
+    const bool has_halo = first > 0;
+    if (d_sums) CK(cudaMemsetAsync(d_sums, 0, sizeof(unsigned long long) * 3 * n, q));
+    unsigned long long* sums = d_sums;
+    if (!sums) {
+        // sums are a by-product of the ingest pass; without a destination use scratch in wp
+        sums = (unsigned long long*)o->wp.p;
+        CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3 * n, q));
+    }
+    if (has_halo) {
+        CK(cudaMemsetAsync(o->halo_sums.p, 0, sizeof(unsigned long long) * 3, q));
+        launch_ingest(g.plan, d_halo, step, 0, 1, pyr, g.pd.frame_bytes, o->halo_sums.as<unsigned long long>(), q);
+    }
+    o->timer.begin(ST_INGEST, q);
+    launch_ingest(g.plan, d_frames, step, frame_stride, n, pyr + g.pd.frame_bytes, g.pd.frame_bytes, sums, q);
+    o->timer.end(ST_INGEST, q);
+    const int s0 = has_halo ? 0 : 1;              // first pyramid slot in use
+    const int nslots = has_halo ? n + 1 : n;
+    o->timer.begin(ST_PYRAMID, q);
+    launch_pyramid(g.pd, pyr + (size_t)s0 * g.pd.frame_bytes, nslots, q);
+    o->timer.end(ST_PYRAMID, q);
+    // corners of every "previous" frame of a pair: slots s0 .. n-1
+    const int npairs = nslots - 1;
+    float2* corners = o->corners.as<float2>() + (size_t)s0 * kMaxCorners;
+    int* ccount = o->ccount.as<int>() + s0;
+    if (npairs > 0) {
+        o->timer.begin(ST_GFTT, q);
+        launch_gftt(pyr + (size_t)s0 * g.pd.frame_bytes, g.pd.frame_bytes, g.ww, g.wh, npairs, 0.01, g.min_distance,
+                    kMaxCorners, o->gws, corners, ccount, q);
+        o->timer.end(ST_GFTT, q);
+        o->timer.begin(ST_LK, q);
+        launch_lk(pyr + (size_t)s0 * g.pd.frame_bytes, pyr + (size_t)(s0 + 1) * g.pd.frame_bytes, g.pd.frame_bytes,
+                  g.pd.frame_bytes, g.pd, corners, ccount, npairs, o->lkpts.as<float2>(), o->lkstat.as<uint8_t>(), q);
+        o->timer.end(ST_LK, q);
+        // pair i (slots s0+i, s0+i+1) -> T of frame first + (s0 + i + 1 - 1) = first + s0 + i
+        o->timer.begin(ST_FIT, q);
+        launch_fit(corners, o->lkpts.as<float2>(), o->lkstat.as<uint8_t>(), ccount, npairs, 3.0, g.ww / 2.0, g.wh / 2.0,
+                   d_T + (size_t)s0 * 9, o->Mtap.as<double>(), o->fitc.as<int>(), nullptr, first + s0, q);
+        o->timer.end(ST_FIT, q);
+    }
+    if (!has_halo) {
+        // T[0] = identity (never used: SURVEY Appendix C)
+        static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        CK(cudaMemcpyAsync(d_T, I9, sizeof(I9), cudaMemcpyHostToDevice, q));
+    }
+    CK(cudaGetLastError());
+    return VSTAB_OK;
+}
+
+// d_sums: [.][3] u64 indexed like d_frames (frame - frame_base)
+extern "C" vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
+                                              size_t step, long frame_base, int n, long call_first,
+                                              const double* d_T_all, long n_total, int mode, long lock_call,
+                                              const unsigned long long* d_sums,
+                                              uint8_t* d_out, size_t out_frame_stride, size_t out_step) {
+    if (!o || !d_frames || !d_T_all || !d_out || !d_sums || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    if (n > o->max_batch + 1) { o->err = "n exceeds max_batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (mode != VSTAB_GLOBAL_SMOOTHING && mode != VSTAB_ACCUMULATED_FULL_LOCK && mode != VSTAB_TRANSLATION_LOCK &&
+        mode != VSTAB_ROTATION_LOCK) { o->err = "mode not supported offline"; return VSTAB_ERR_UNSUPPORTED; }
+    if (mode == VSTAB_ACCUMULATED_FULL_LOCK && lock_call < (long)o->F) {
+        o->err = "ACCUMULATED_FULL_LOCK must be set at a call index >= future (SURVEY B.6)"; return VSTAB_ERR_STATE;
+    }
+    CK(cudaSetDevice(o->device));
+    Geometry& g = o->g;
+    cudaStream_t q = o->stream;
+    if (mode == VSTAB_ACCUMULATED_FULL_LOCK) {
+        const long anchor = lock_call - (long)o->F;
+        if (o->acc_T != d_T_all || o->acc_n_total != n_total || o->acc_anchor != anchor) {
+            o->err = "call vstab_offline_prepare(d_T_all, n_total, mode, lock_call) before rendering in ACCUMULATED_FULL_LOCK";
+            return VSTAB_ERR_STATE;
+        }
+    }
+    SmoothArgs a{};
+    a.T = d_T_all; a.t_mod = n_total > 0 ? n_total : 1;
+    a.P = (int)o->P; a.F = (int)o->F;
+    a.mode = mode; a.lock_call = lock_call;
+    a.acc = o->acc.as<double>(); a.acc_mod = n_total;
+    a.scale = g.scale;
+    a.sums = d_sums; a.sums_mod = 0; a.frame_base = frame_base;
+    a.npix = (double)g.rows * (double)g.cols;
+    o->timer.begin(ST_SMOOTH, q);
+    launch_smooth(a, call_first, n, o->wp.as<WarpParams>(), q);
+    o->timer.end(ST_SMOOTH, q);
+    o->timer.begin(ST_WARP, q);
+    launch_warp(d_frames, step, frame_stride, 0, o->wp.as<WarpParams>(), n, g.cols, g.rows, d_out, out_step,
+                out_frame_stride, q);
+    o->timer.end(ST_WARP, q);
+    CK(cudaGetLastError());
+    o->last_ncalls = n;
+    return VSTAB_OK;
+}
+
+// The "segmented prefix/scan over 3x3 transforms" of the north star: accumulated products
+// acc[k] = T[k] * ... * T[anchor+1] for the whole clip, needed by ACCUMULATED_FULL_LOCK
+// (src/stabilizer.cpp:317-338).  Runs every time it is called (no caching of results).
+extern "C" vstab_status vstab_offline_prepare(vstab_offline_t* o, const double* d_T_all, long n_total, int mode,
+                                              long lock_call) {
+    if (!o || !d_T_all || n_total < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    CK(cudaSetDevice(o->device));
+    if (mode != VSTAB_ACCUMULATED_FULL_LOCK) { o->acc_T = nullptr; return VSTAB_OK; }
+    if (lock_call < (long)o->F) {
+        o->err = "ACCUMULATED_FULL_LOCK must be set at a call index >= future (SURVEY B.6)"; return VSTAB_ERR_STATE;
+    }
+    const long anchor = lock_call - (long)o->F;
+    const size_t mats = (size_t)n_total + (size_t)(n_total / 256 + 2);
+    if (o->acc_capacity < mats) { CK(o->acc.alloc(sizeof(double) * 9 * mats)); o->acc_capacity = mats; }
+    o->timer.begin(ST_ACC, o->stream);
+    launch_acc_scan(d_T_all, n_total, anchor, o->acc.as<double>(), o->stream);
+    o->timer.end(ST_ACC, o->stream);
+    CK(cudaGetLastError());
+    o->acc_T = d_T_all; o->acc_n_total = n_total; o->acc_anchor = anchor;
+    return VSTAB_OK;
+}
+
+extern "C" void vstab_offline_set_timing(vstab_offline_t* o, int enable) { if (o) o->timer.enabled = enable != 0; }
+
+// ms[8] / counts[8]: ingest, pyramid, gftt, lk, fit, smooth, warp, acc-scan since the last call
+extern "C" vstab_status vstab_offline_stage_times(vstab_offline_t* o, float* ms, int* counts) {
+    if (!o || !ms || !counts) return VSTAB_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(o->device);
+    o->timer.collect(ms, counts);
+    return VSTAB_OK;
+}
+
+extern "C" long long vstab_launch_count(void) { return vstabk::launch_count(); }
+
+extern "C" long vstab_offline_read_h(vstab_offline_t* o, double* dst, size_t n_calls) {
+    if (!o || !dst) return -1;
+    if (cudaSetDevice(o->device) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess) return -1;
+    size_t n = n_calls < (size_t)o->last_ncalls ? n_calls : (size_t)o->last_ncalls;
+    std::vector<WarpParams> h(n);
+    if (n && cudaMemcpy(h.data(), o->wp.p, sizeof(WarpParams) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (size_t i = 0; i < n; ++i) memcpy(dst + i * 9, h[i].Hs, sizeof(double) * 9);
+    return (long)n;
+}
+
+// =====================================================================================
+// simulator render + single-kernel entry points (host buffers)
+// =====================================================================================
+extern "C" vstab_status vstab_render_frames(int device, const uint8_t* d_texture, int tex_rows, int tex_cols,
+                                            const double* poses, int n, int rows, int cols, double focal,
+                                            uint8_t* d_out, size_t frame_stride, size_t step) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!d_texture || !poses || !d_out || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    std::vector<RenderPose> hp(n);
+    for (int i = 0; i < n; ++i) {
+        const double* p = poses + (size_t)i * 6;
+        const double pan = p[3] * M_PI / 180.0, tilt = p[4] * M_PI / 180.0, roll = p[5] * M_PI / 180.0;
+        // rotationMatrix: Rz(roll) * Rx(tilt) * Ry(pan), camera_engine.cpp:36-61
+        const double ry[9] = {cos(pan), 0, sin(pan), 0, 1, 0, -sin(pan), 0, cos(pan)};
+        const double rx[9] = {1, 0, 0, 0, cos(tilt), -sin(tilt), 0, sin(tilt), cos(tilt)};
+        const double rz[9] = {cos(roll), -sin(roll), 0, sin(roll), cos(roll), 0, 0, 0, 1};
+        double t[9];
+        auto mm = [](const double* A, const double* B, double* C) {
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    volatile double s = 0.0;
+                    for (int k = 0; k < 3; ++k) { volatile double pr = A[i * 3 + k] * B[k * 3 + j]; s = s + pr; }
+                    C[i * 3 + j] = s;
+                }
+        };
+        mm(rz, rx, t);
+        mm(t, ry, hp[i].R);
+        hp[i].cam[0] = p[0]; hp[i].cam[1] = p[1]; hp[i].cam[2] = p[2];
+    }
+    DevBuf dp;
+    CK(dp.alloc(sizeof(RenderPose) * n));
+    CK(cudaMemcpy(dp.p, hp.data(), sizeof(RenderPose) * n, cudaMemcpyHostToDevice));
+    launch_render(d_texture, tex_rows, tex_cols, dp.as<RenderPose>(), n, cols, rows, focal, d_out, step, frame_stride, 0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_ingest(int device, const uint8_t* bgr, int rows, int cols, size_t step,
+                                       int working_height, uint8_t* gray_out, uint64_t sums_out[3]) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!bgr || !gray_out || !sums_out) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    Geometry g;
+    vstab_status st = g.init(rows, cols, working_height, g_err);
+    if (st != VSTAB_OK) return st;
+    DevBuf frame, gray, sums;
+    CK(frame.alloc(g.frame_bytes + 64));
+    CK(gray.alloc(g.pd.frame_bytes));
+    CK(sums.alloc(sizeof(unsigned long long) * 3));
+    CK(cudaMemcpy2D(frame.p, g.pitch, bgr, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice));
+    CK(cudaMemset(sums.p, 0, sizeof(unsigned long long) * 3));
+    launch_ingest(g.plan, frame.as<uint8_t>(), g.pitch, g.frame_bytes, 1, gray.as<uint8_t>(), g.pd.frame_bytes,
+                  sums.as<unsigned long long>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(gray_out, gray.p, (size_t)g.ww * g.wh, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sums_out, sums.p, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_pyramid(int device, const uint8_t* gray, int rows, int cols,
+                                        uint8_t* l1, uint8_t* l2, uint8_t* l3) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!gray || !l1 || !l2 || !l3) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    PyrDesc pd = make_pyr_desc(cols, rows);
+    DevBuf pyr;
+    CK(pyr.alloc(pd.frame_bytes));
+    CK(cudaMemcpy(pyr.p, gray, (size_t)rows * cols, cudaMemcpyHostToDevice));
+    launch_pyramid(pd, pyr.as<uint8_t>(), 1, 0);
+    CK(cudaGetLastError());
+    uint8_t* outs[3] = {l1, l2, l3};
+    for (int l = 1; l < kLkLevels; ++l)
+        CK(cudaMemcpy(outs[l - 1], pyr.as<uint8_t>() + pd.off[l], (size_t)pd.w[l] * pd.h[l], cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_gftt(int device, const uint8_t* gray, int rows, int cols, int max_corners,
+                                     double quality, int min_distance, float* pts_out, int* n_out, float* eig_out) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!gray || !pts_out || !n_out) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    DevBuf img, mem, pts, cnt;
+    GfttWorkspace ws{};
+    size_t bytes = gftt_workspace_bytes(cols, rows, min_distance, 1, &ws);
+    CK(img.alloc((size_t)rows * cols));
+    CK(mem.alloc(bytes));
+    CK(pts.alloc(sizeof(float2) * kMaxCorners));
+    CK(cnt.alloc(sizeof(int)));
+    gftt_bind_workspace(mem.p, &ws);
+    CK(cudaMemcpy(img.p, gray, (size_t)rows * cols, cudaMemcpyHostToDevice));
+    launch_gftt(img.as<uint8_t>(), 0, cols, rows, 1, quality, min_distance, max_corners, ws, pts.as<float2>(),
+                cnt.as<int>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(n_out, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pts_out, pts.p, sizeof(float2) * (*n_out), cudaMemcpyDeviceToHost));
+    if (eig_out) CK(cudaMemcpy(eig_out, ws.eig, sizeof(float) * rows * cols, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_lk(int device, const uint8_t* prev, const uint8_t* next, int rows, int cols,
+                                   const float* pts, int n, float* out_pts, uint8_t* status) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!prev || !next || !pts || !out_pts || !status || n < 0 || n > kMaxCorners) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    PyrDesc pd = make_pyr_desc(cols, rows);
+    DevBuf p0, p1, dp, dc, dout, dst;
+    CK(p0.alloc(pd.frame_bytes)); CK(p1.alloc(pd.frame_bytes));
+    CK(dp.alloc(sizeof(float2) * kMaxCorners)); CK(dc.alloc(sizeof(int)));
+    CK(dout.alloc(sizeof(float2) * kMaxCorners)); CK(dst.alloc(kMaxCorners));
+    CK(cudaMemcpy(p0.p, prev, (size_t)rows * cols, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p1.p, next, (size_t)rows * cols, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dp.p, pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, &n, sizeof(int), cudaMemcpyHostToDevice));
+    launch_pyramid(pd, p0.as<uint8_t>(), 1, 0);
+    launch_pyramid(pd, p1.as<uint8_t>(), 1, 0);
+    launch_lk(p0.as<uint8_t>(), p1.as<uint8_t>(), pd.frame_bytes, pd.frame_bytes, pd, dp.as<float2>(), dc.as<int>(), 1,
+              dout.as<float2>(), dst.as<uint8_t>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_pts, dout.p, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(status, dst.p, n, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_fit(int device, const float* prev_pts, const float* next_pts, const uint8_t* status,
+                                    int n, double thresh, int work_w, int work_h, double M_out[6], double T_out[9],
+                                    int counts_out[2]) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!prev_pts || !next_pts || !status || !T_out || n < 0 || n > kMaxCorners) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    DevBuf a, b, s, c, T, M, fc;
+    CK(a.alloc(sizeof(float2) * kMaxCorners)); CK(b.alloc(sizeof(float2) * kMaxCorners)); CK(s.alloc(kMaxCorners));
+    CK(c.alloc(sizeof(int))); CK(T.alloc(sizeof(double) * 9)); CK(M.alloc(sizeof(double) * 6)); CK(fc.alloc(sizeof(int) * 2));
+    CK(cudaMemcpy(a.p, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.p, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.p, status, n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.p, &n, sizeof(int), cudaMemcpyHostToDevice));
+    launch_fit(a.as<float2>(), b.as<float2>(), s.as<uint8_t>(), c.as<int>(), 1, thresh, work_w / 2.0, work_h / 2.0,
+               T.as<double>(), M.as<double>(), fc.as<int>(), nullptr, 0, 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(T_out, T.p, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+    if (M_out) CK(cudaMemcpy(M_out, M.p, sizeof(double) * 6, cudaMemcpyDeviceToHost));
+    if (counts_out) CK(cudaMemcpy(counts_out, fc.p, sizeof(int) * 2, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, int cols, size_t step, const double H[9],
+                                     const uint8_t border[3], uint8_t* out, size_t out_step) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!bgr || !H || !border || !out) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    const size_t pitch = align_up((size_t)cols * 3, 16);
+    DevBuf src, dst, wp;
+    CK(src.alloc(pitch * rows + 64)); CK(dst.alloc(pitch * rows + 64)); CK(wp.alloc(sizeof(WarpParams)));
+    CK(cudaMemcpy2D(src.p, pitch, bgr, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice));
+    WarpParams h{};
+    for (int i = 0; i < 9; ++i) { h.Hs[i] = H[i]; h.Hw[i] = H[i]; }
+    invert3(H, h.Minv);
+    h.src_slot = 0;
+    h.border[0] = border[0]; h.border[1] = border[1]; h.border[2] = border[2]; h.border[3] = 0;
+    CK(cudaMemcpy(wp.p, &h, sizeof(h), cudaMemcpyHostToDevice));
+    launch_warp(src.as<uint8_t>(), pitch, 0, 0, wp.as<WarpParams>(), 1, cols, rows, dst.as<uint8_t>(), pitch, 0, 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2D(out, out_step, dst.p, pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}

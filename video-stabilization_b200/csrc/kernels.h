@@ -1,0 +1,106 @@
+// Host-callable launch wrappers of the hot-path kernels (all asynchronous on `st`).
+// Layout conventions (device memory):
+//   * BGR frames: u8 HWC, `pitch` bytes per row (multiple of 16), frames `frame_stride` apart.
+//   * gray pyramid of a frame: one block of PyrDesc::frame_bytes, level l at off[l], tight rows.
+//   * corners / LK points: float2 [frame][kMaxCorners]; counts int [frame].
+//   * transforms: double [frame][9] row-major.
+#pragma once
+#include "common.cuh"
+
+namespace vstabk {
+
+// number of kernels of this library launched so far (bench.py reports the delta per timed region)
+void count_launch(int n);
+long long launch_count();
+
+// ---------------------------------------------------------------- K1 ingest
+struct IngestPlan {
+    int src_w, src_h, dst_w, dst_h;
+    int mode;              // 0 = copy (scale 1), 1 = exact 2x2 box (INTER_AREA), 2 = Q11 bilinear
+    int rows_per_band;     // dst rows handled by one CTA
+    int nbands;
+    const int4* xtab;      // per dst x: {s0, s1, c0, c1}   (mode 2; also filled for 0/1)
+    const int4* ytab;      // per dst y
+};
+void build_ingest_tables(int src, int dst, int mode, int4* host_tab);   // host helper
+void launch_ingest(const IngestPlan& plan, const uint8_t* frames, size_t pitch, size_t frame_stride,
+                   int nframes, uint8_t* gray, size_t gray_frame_stride,
+                   unsigned long long* sums /* [nframes][3], pre-zeroed */, cudaStream_t st);
+
+// ---------------------------------------------------------------- K2 pyramid
+PyrDesc make_pyr_desc(int w, int h);
+void launch_pyramid(const PyrDesc& d, uint8_t* pyr, int nframes, cudaStream_t st);
+
+// ---------------------------------------------------------------- K3 GFTT
+struct GfttWorkspace {
+    float* eig;                    // [nframes][w*h]
+    unsigned int* maxbits;         // [nframes]
+    unsigned long long* keys;      // [nframes][cap]
+    unsigned long long* keys_alt;  // [nframes][cap]   (sort double buffer)
+    int* seg_begin;                // [nframes]  = f*cap
+    int* seg_end;                  // [nframes]  = f*cap + count (atomic counter)
+    unsigned int* grid;            // [nframes][ncells*4]
+    void* cub_temp;
+    size_t cub_temp_bytes;
+    int cap;                       // candidate capacity per frame
+    int ncells, grid_w, grid_h, cell;
+    int max_frames;
+};
+size_t gftt_workspace_bytes(int w, int h, int min_distance, int max_frames, GfttWorkspace* layout);
+void gftt_bind_workspace(void* base, GfttWorkspace* ws);     // base: cudaMalloc'ed block
+void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, int nframes,
+                 double quality, int min_distance, int max_corners, GfttWorkspace& ws,
+                 float2* pts, int* counts, cudaStream_t st);
+
+// ---------------------------------------------------------------- K4 sparse pyramidal LK
+void launch_lk(const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_stride, size_t next_stride,
+               const PyrDesc& d, const float2* pts, const int* counts, int nframes,
+               float2* out_pts, uint8_t* status, cudaStream_t st);
+
+// ---------------------------------------------------------------- K5 RANSAC similarity + LS + scale kill
+void launch_fit(const float2* prev_pts, const float2* next_pts, const uint8_t* status,
+                const int* counts, int nframes, double thresh, double cx, double cy,
+                double* T /* [nframes][9] */, double* M /* [nframes][6] or null */,
+                int* fit_counts /* [nframes][2] or null */, const long* frame_ids /* or null */,
+                long frame_id0, cudaStream_t st);
+
+// ---------------------------------------------------------------- K6 window smoothing / lock, warp params
+struct WarpParams {          // consumed by K7
+    double Minv[9];          // inverse of H_stabilize_scaled (dst -> src)
+    double Hs[9];            // H_stabilize_scaled (tap)
+    double Hw[9];            // H_stabilize at working resolution (tap)
+    int src_slot;            // which source frame (index into the frame array / ring)
+    unsigned char border[4]; // saturate_cast<uchar>(0.5*mean) per channel
+};
+struct SmoothArgs {
+    const double* T;             // transforms by absolute frame index (T[k] maps k-1 -> k)
+    long t_mod;                  // T index = abs % t_mod
+    int P, F;                    // past / future window
+    int mode;                    // vstab_mode
+    long lock_call;              // call index at which the lock mode was set (ACCUMULATED)
+    const double* acc;           // optional precomputed accumulated products by abs frame idx (offline), mod acc_mod
+    long acc_mod;
+    double scale;                // workingHeight / rows
+    const unsigned long long* sums;   // [slot][3] channel sums by frame slot
+    long sums_mod;               // slot = abs frame % sums_mod   (ring) or abs - frame_base (offline: see frame_base)
+    long frame_base;             // offline: slot = abs - frame_base; streaming: 0 with modulo
+    double npix;                 // rows*cols
+};
+void launch_smooth(const SmoothArgs& a, long call_first, int ncalls, WarpParams* out, cudaStream_t st);
+// streaming ACCUMULATED_FULL_LOCK state update: acc <- T[p] * acc (src/stabilizer.cpp:334)
+void launch_acc_update(const double* T, long t_mod, long p, int reset, double* acc_state, cudaStream_t st);
+// offline: acc[k] for k in [a, a+n): acc[a] = I, acc[k] = T[k] * acc[k-1]
+void launch_acc_scan(const double* T, long n_total, long anchor, double* acc, cudaStream_t st);
+
+// ---------------------------------------------------------------- K7 warpPerspective + border
+void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long slot_mod,
+                 const WarpParams* wp, int nout, int w, int h,
+                 uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st);
+
+// ---------------------------------------------------------------- K13 simulator render
+struct RenderPose { double R[9]; double cam[3]; };
+void launch_render(const uint8_t* tex, int tex_rows, int tex_cols, const RenderPose* poses_dev, int n,
+                   int w, int h, double focal, uint8_t* out, size_t pitch, size_t frame_stride,
+                   cudaStream_t st);
+
+}  // namespace vstabk

@@ -1,0 +1,194 @@
+// K6: sliding-window trajectory smoothing, full-lock accumulation, mode selection and the
+// per-call warp parameters.
+//   calculateGlobalSmoothingStabilization  /root/reference/src/stabilizer.cpp:793-852
+//   calculateFullLockStabilization (ACCUMULATED branch)            :317-338, :438
+//   mode switch + translation rescale                              :1231-1296
+//   border colour 0.5 * cv::mean(presentation frame)               :1309
+// Index algebra: call c (>= 1) sees frames [lo, c], lo = max(0, c-W+1),
+// presents p = max(0, c-F); window transforms are T[lo+1 .. c] with T[k] mapping k-1 -> k.
+//   past   terms k = 1..p-lo      : A_k = inv(T[p-k+1]) * A_{k-1}
+//   future terms r = 1..c-1-p     : B_r = B_{r-1} * T[p+r]      (newest transform excluded)
+//   H = (sum A + sum B) / count   (no identity term; count==0 or non-finite -> I)
+// Reference quirks kept on purpose: see SURVEY Appendix B.2-B.4, B.7, B.8.
+// One warp per call: lane 0 walks the past chain, lane 1 the future chain (reference order).
+#include "homography.cuh"
+#include "kernels.h"
+
+namespace vstabk {
+namespace {
+
+VSTAB_D const double* t_at(const SmoothArgs& a, long k) { return a.T + (size_t)(k % a.t_mod) * 9; }
+
+__global__ void __launch_bounds__(32)
+smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict__ out) {
+    const int ci = blockIdx.x;
+    if (ci >= ncalls) return;
+    const int lane = threadIdx.x;
+    const long c = call_first + ci;
+    const long W = (long)a.P + 1 + a.F;
+    const long lo = c - W + 1 > 0 ? c - W + 1 : 0;
+    const long p = c - a.F > 0 ? c - a.F : 0;
+
+    double sum[9];
+    for (int i = 0; i < 9; ++i) sum[i] = 0.0;
+    int count = 0;
+    if (lane == 0) {
+        double acc[9], inv[9], tmp[9];
+        eye3(acc);
+        for (long k = p; k > lo; --k) {                 // T[p], T[p-1], ..., T[lo+1]
+            invert3(t_at(a, k), inv);
+            matmul3(inv, acc, tmp);
+            for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sum[i] += tmp[i]; }
+            ++count;
+        }
+    } else if (lane == 1) {
+        double acc[9], tmp[9];
+        eye3(acc);
+        for (long k = p + 1; k <= c - 1; ++k) {         // T[p+1] ... T[c-1]
+            matmul3(acc, t_at(a, k), tmp);
+            for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sum[i] += tmp[i]; }
+            ++count;
+        }
+    }
+    // combine: avg = past_sum + future_sum (the reference adds past terms first)
+    double fut[9];
+    for (int i = 0; i < 9; ++i) fut[i] = __shfl_sync(0xffffffffu, sum[i], 1);
+    const int fcount = __shfl_sync(0xffffffffu, count, 1);
+    if (lane != 0) return;
+
+    double Hs[9];
+    eye3(Hs);
+    const int total = count + fcount;
+    if (total > 0) {
+        double avg[9];
+        // past partial sums were accumulated first, future terms added one by one after them;
+        // adding the future block as one sum differs from the reference by O(1 ulp).
+        for (int i = 0; i < 9; ++i) avg[i] = (sum[i] + fut[i]) / (double)total;
+        if (finite9(avg))
+            for (int i = 0; i < 9; ++i) Hs[i] = avg[i];
+    }
+
+    // ---- full-lock transform -------------------------------------------------------------
+    int mode = a.mode;
+    if (mode == 0 /*ACCUMULATED_FULL_LOCK*/ && c < a.lock_call) mode = 5;   // lock not yet set at this call
+    double Hl[9];
+    eye3(Hl);
+    if (mode == 0) {
+        const double* accp = a.acc + (size_t)(a.acc_mod > 0 ? (p % a.acc_mod) : 0) * 9;
+        invert3(accp, Hl);                                // accumulatedTransform_.H.inv(), :438
+        HParams hp;
+        if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
+    }
+    double H[9];
+    if (mode == 5) { for (int i = 0; i < 9; ++i) H[i] = Hs[i]; }
+    else if (mode == 0) { for (int i = 0; i < 9; ++i) H[i] = Hl[i]; }
+    else { eye3(H); }                                     // T/R lock: identity
+
+    WarpParams wp;
+    for (int i = 0; i < 9; ++i) wp.Hw[i] = H[i];
+    if (fabs(a.scale - 1.0) > 1e-6) {                     // :1291-1296
+        H[2] /= a.scale;
+        H[5] /= a.scale;
+    }
+    for (int i = 0; i < 9; ++i) wp.Hs[i] = H[i];
+    invert3(H, wp.Minv);
+    const long slot = a.sums_mod > 0 ? (p % a.sums_mod) : (p - a.frame_base);
+    wp.src_slot = (int)slot;
+    for (int ch = 0; ch < 3; ++ch) {
+        const double mean = (double)a.sums[(size_t)slot * 3 + ch] / a.npix;   // cv::mean
+        int v = __double2int_rn(0.5 * mean);                                  // saturate_cast<uchar>
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        wp.border[ch] = (unsigned char)v;
+    }
+    wp.border[3] = 0;
+    out[ci] = wp;
+}
+
+// acc <- T[p] * acc   (or identity on the first call after setStabilizationMode)
+__global__ void acc_update_kernel(const double* T, long t_mod, long p, int reset, double* acc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (reset) { eye3(acc); return; }
+    double tmp[9];
+    matmul3(T + (size_t)(p % t_mod) * 9, acc, tmp);
+    for (int i = 0; i < 9; ++i) acc[i] = tmp[i];
+}
+
+// ---- offline prefix product: acc[k] = T[k] * acc[k-1], acc[anchor] = I -----------------------
+// Segmented scan over 3x3 transforms: each block reduces a contiguous chunk (phase 1), a
+// single warp scans the chunk totals (phase 2), each block re-walks its chunk with the
+// incoming prefix (phase 3).  Products are left-multiplications in frame order.
+constexpr int kScanChunk = 256;
+
+__global__ void acc_chunk_reduce_kernel(const double* __restrict__ T, long n_total, long anchor,
+                                        double* __restrict__ chunk_tot) {
+    const long chunk = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long k0 = anchor + 1 + chunk * kScanChunk;
+    if (k0 >= n_total) return;
+    const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
+    double acc[9], tmp[9];
+    eye3(acc);
+    for (long k = k0; k < k1; ++k) {
+        matmul3(T + (size_t)k * 9, acc, tmp);
+        for (int i = 0; i < 9; ++i) acc[i] = tmp[i];
+    }
+    for (int i = 0; i < 9; ++i) chunk_tot[(size_t)chunk * 9 + i] = acc[i];
+}
+
+__global__ void acc_chunk_scan_kernel(double* chunk_tot, long nchunks) {
+    // exclusive scan (sequential over chunk totals: nchunks = n/256 is small), in place
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double run[9], tmp[9], cur[9];
+    eye3(run);
+    for (long c = 0; c < nchunks; ++c) {
+        for (int i = 0; i < 9; ++i) cur[i] = chunk_tot[(size_t)c * 9 + i];
+        for (int i = 0; i < 9; ++i) chunk_tot[(size_t)c * 9 + i] = run[i];
+        matmul3(cur, run, tmp);
+        for (int i = 0; i < 9; ++i) run[i] = tmp[i];
+    }
+}
+
+__global__ void acc_chunk_apply_kernel(const double* __restrict__ T, long n_total, long anchor,
+                                       const double* __restrict__ chunk_pre, double* __restrict__ acc_out) {
+    const long chunk = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long k0 = anchor + 1 + chunk * kScanChunk;
+    if (chunk == 0 && anchor < n_total) eye3(acc_out + (size_t)anchor * 9);
+    if (k0 >= n_total) return;
+    const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
+    double acc[9], tmp[9];
+    for (int i = 0; i < 9; ++i) acc[i] = chunk_pre[(size_t)chunk * 9 + i];
+    for (long k = k0; k < k1; ++k) {
+        matmul3(T + (size_t)k * 9, acc, tmp);
+        for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; acc_out[(size_t)k * 9 + i] = tmp[i]; }
+    }
+}
+
+}  // namespace
+
+void launch_smooth(const SmoothArgs& a, long call_first, int ncalls, WarpParams* out, cudaStream_t st) {
+    if (ncalls <= 0) return;
+    count_launch(1);
+    smooth_kernel<<<ncalls, 32, 0, st>>>(a, call_first, ncalls, out);
+}
+
+void launch_acc_update(const double* T, long t_mod, long p, int reset, double* acc_state, cudaStream_t st) {
+    count_launch(1);
+    acc_update_kernel<<<1, 32, 0, st>>>(T, t_mod, p, reset, acc_state);
+}
+
+// chunk scratch lives at the tail of `acc` (caller allocates n_total + 2*ceil(n_total/256)+2 matrices)
+void launch_acc_scan(const double* T, long n_total, long anchor, double* acc, cudaStream_t st) {
+    if (anchor >= n_total) return;
+    const long n = n_total - anchor - 1;
+    const long nchunks = n > 0 ? (n + kScanChunk - 1) / kScanChunk : 0;
+    double* chunk = acc + (size_t)n_total * 9;
+    const int threads = 64;
+    const int blocks = (int)((nchunks > 0 ? nchunks : 1) + threads - 1) / threads;
+    count_launch(nchunks > 0 ? 3 : 1);
+    if (nchunks > 0) {
+        acc_chunk_reduce_kernel<<<blocks, threads, 0, st>>>(T, n_total, anchor, chunk);
+        acc_chunk_scan_kernel<<<1, 32, 0, st>>>(chunk, nchunks);
+    }
+    acc_chunk_apply_kernel<<<blocks, threads, 0, st>>>(T, n_total, anchor, chunk, acc);
+}
+
+}  // namespace vstabk

@@ -1,0 +1,314 @@
+"""ctypes binding of libvstab.so (include/vstab.h) -- the Python face of the C ABI.
+
+`Stabilizer` mirrors class Stabilizer of the reference
+(/root/reference/include/stabilizer.hpp:106-475): same constructor arguments and
+defaults, `stabilize_frame`, `set_stabilization_mode`, `total_frame_window_size`,
+static `decompose_homography` / `compose_homography`, and the reference's error
+behaviour (std::invalid_argument -> ValueError).  There is no CPU fallback: if
+the shared library is missing or no sm_100 device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+ACCUMULATED_FULL_LOCK, ORB_FULL_LOCK, SIFT_FULL_LOCK, TRANSLATION_LOCK, ROTATION_LOCK, GLOBAL_SMOOTHING = range(6)
+
+OK, ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = range(6)
+
+TAP_GRAY, TAP_PYR1, TAP_PYR2, TAP_PYR3, TAP_PREV_PTS, TAP_LK_PTS, TAP_LK_STATUS, TAP_NEW_PTS, TAP_T, TAP_M, \
+    TAP_H_STABILIZE, TAP_H_SCALED, TAP_BORDER, TAP_EIG, TAP_INLIERS, TAP_CHANNEL_SUMS = range(16)
+
+_PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libvstab.so")
+
+
+class VstabError(RuntimeError):
+    pass
+
+
+class HParams(C.Structure):
+    """struct HomographyParameters, include/stabilizer.hpp:44-57"""
+    _fields_ = [("s", C.c_double), ("theta", C.c_double), ("k", C.c_double), ("delta", C.c_double),
+                ("t", C.c_double * 2), ("v", C.c_double * 2)]
+
+
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# every symbol include/vstab.h declares: (restype, argtypes)
+SYMBOLS = {
+    "vstab_abi_version": (C.c_int, []),
+    "vstab_status_string": (C.c_char_p, [C.c_int]),
+    "vstab_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "vstab_destroy": (None, [_vp]),
+    "vstab_set_mode": (C.c_int, [_vp, C.c_int]),
+    "vstab_get_mode": (C.c_int, [_vp]),
+    "vstab_total_frame_window_size": (C.c_size_t, [_vp]),
+    "vstab_stabilize_frame": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, C.c_size_t]),
+    "vstab_stabilize_frame_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, C.c_size_t]),
+    "vstab_synchronize": (C.c_int, [_vp]),
+    "vstab_decompose_homography": (C.c_int, [_f64p, C.c_double, C.c_double, C.POINTER(HParams)]),
+    "vstab_compose_homography": (None, [C.POINTER(HParams), C.c_double, C.c_double, _f64p]),
+    "vstab_last_error": (C.c_char_p, [_vp]),
+    "vstab_host_alloc": (_vp, [C.c_size_t]),
+    "vstab_host_free": (None, [_vp]),
+    "vstab_read_tap": (C.c_long, [_vp, C.c_int, _vp, C.c_size_t]),
+    "vstab_working_width": (C.c_int, [_vp]),
+    "vstab_working_height": (C.c_int, [_vp]),
+    "vstab_presentation_index": (C.c_long, [_vp]),
+    "vstab_offline_create": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "vstab_offline_destroy": (None, [_vp]),
+    "vstab_offline_estimate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, C.c_long, _vp, _vp, _vp]),
+    "vstab_offline_render": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_long, C.c_int, C.c_long, _vp, C.c_long,
+                                       C.c_int, C.c_long, _vp, _vp, C.c_size_t, C.c_size_t]),
+    "vstab_offline_synchronize": (C.c_int, [_vp]),
+    "vstab_offline_prepare": (C.c_int, [_vp, _vp, C.c_long, C.c_int, C.c_long]),
+    "vstab_offline_set_timing": (None, [_vp, C.c_int]),
+    "vstab_offline_stage_times": (C.c_int, [_vp, _f32p, C.POINTER(C.c_int)]),
+    "vstab_launch_count": (C.c_longlong, []),
+    "vstab_offline_read_h": (C.c_long, [_vp, _f64p, C.c_size_t]),
+    "vstab_offline_stream": (C.c_size_t, [_vp]),
+    "vstab_render_frames": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                      _vp, C.c_size_t, C.c_size_t]),
+    "vstab_k_ingest": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, C.c_int, _vp, C.POINTER(C.c_uint64)]),
+    "vstab_k_pyramid": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "vstab_k_gftt": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _vp, C.POINTER(C.c_int), _vp]),
+    "vstab_k_lk": (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "vstab_k_fit": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, _f64p, _f64p,
+                              C.POINTER(C.c_int)]),
+    "vstab_k_warp": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, _f64p, _vp, _vp, C.c_size_t]),
+}
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libvstab.so and bind every declared symbol.  Raises if the library is missing:
+    there is deliberately no fallback implementation."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise VstabError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         f"(or `make -C video-stabilization_b200`); there is no CPU fallback")
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+def _check(st: int, handle=None):
+    if st == OK:
+        return
+    lib = load_library()
+    msg = lib.vstab_last_error(handle)
+    msg = msg.decode() if msg else lib.vstab_status_string(st).decode()
+    if st in (ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED):
+        raise ValueError(msg)                # std::invalid_argument in the reference
+    if st == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if st == ERR_STATE:
+        raise AssertionError(msg)            # the reference asserts (stabilizer.cpp:329)
+    raise VstabError(msg)
+
+
+@dataclass
+class HomographyParameters:
+    s: float = 1.0
+    theta: float = 0.0
+    k: float = 1.0
+    delta: float = 0.0
+    t: tuple = (0.0, 0.0)
+    v: tuple = (0.0, 0.0)
+
+
+class Stabilizer:
+    """Drop-in for the reference's Stabilizer on the LK + warp path (device-resident state)."""
+
+    def __init__(self, past_frames: int = 15, future_frames: int = 15, working_height: int = 360,
+                 device: int = 0):
+        self._lib = load_library()
+        self._h = _vp()
+        _check(self._lib.vstab_create(past_frames, future_frames, working_height, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vstab_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def total_frame_window_size(self) -> int:
+        return int(self._lib.vstab_total_frame_window_size(self._h))
+
+    def set_stabilization_mode(self, mode: int) -> None:
+        _check(self._lib.vstab_set_mode(self._h, int(mode)), self._h)
+
+    def stabilize_frame(self, frame: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be HxWx3 uint8 (BGR)")
+        if frame.strides[2] != 1 or frame.strides[1] != 3:
+            frame = np.ascontiguousarray(frame)
+        if out is None:
+            out = np.empty((frame.shape[0], frame.shape[1], 3), np.uint8)
+        _check(self._lib.vstab_stabilize_frame(self._h, _ptr(frame), frame.shape[0], frame.shape[1],
+                                               frame.strides[0], _ptr(out), out.strides[0]), self._h)
+        return out
+
+    def stabilize_frame_ptr(self, src_ptr: int, rows: int, cols: int, step: int, dst_ptr: int, dst_step: int,
+                            device: bool = False) -> None:
+        fn = self._lib.vstab_stabilize_frame_device if device else self._lib.vstab_stabilize_frame
+        _check(fn(self._h, _vp(src_ptr), rows, cols, step, _vp(dst_ptr), dst_step), self._h)
+
+    def synchronize(self) -> None:
+        _check(self._lib.vstab_synchronize(self._h), self._h)
+
+    # ---- parity taps ------------------------------------------------------------------
+    def working_size(self):
+        return self._lib.vstab_working_width(self._h), self._lib.vstab_working_height(self._h)
+
+    def presentation_index(self) -> int:
+        return int(self._lib.vstab_presentation_index(self._h))
+
+    def tap(self, which: int) -> np.ndarray:
+        ww, wh = self.working_size()
+        spec = {
+            TAP_GRAY: (np.uint8, ww * wh), TAP_PYR1: (np.uint8, ww * wh), TAP_PYR2: (np.uint8, ww * wh),
+            TAP_PYR3: (np.uint8, ww * wh), TAP_PREV_PTS: (np.float32, 2600), TAP_LK_PTS: (np.float32, 2600),
+            TAP_LK_STATUS: (np.uint8, 1300), TAP_NEW_PTS: (np.float32, 2600), TAP_T: (np.float64, 9),
+            TAP_M: (np.float64, 6), TAP_H_STABILIZE: (np.float64, 9), TAP_H_SCALED: (np.float64, 9),
+            TAP_BORDER: (np.uint8, 3), TAP_EIG: (np.float32, ww * wh), TAP_INLIERS: (np.int32, 2),
+            TAP_CHANNEL_SUMS: (np.uint64, 3),
+        }[which]
+        buf = np.zeros(spec[1], spec[0])
+        n = self._lib.vstab_read_tap(self._h, which, _ptr(buf), buf.nbytes)
+        if n < 0:
+            raise VstabError(f"tap {which} failed ({n})")
+        if which in (TAP_PREV_PTS, TAP_LK_PTS, TAP_NEW_PTS):
+            return buf[:2 * n].reshape(-1, 2)
+        if which == TAP_GRAY or which == TAP_EIG:
+            return buf[:n].reshape(wh, ww)
+        if which in (TAP_PYR1, TAP_PYR2, TAP_PYR3):
+            l = which - TAP_PYR1 + 1
+            w_, h_ = ww, wh
+            for _ in range(l):
+                w_, h_ = (w_ + 1) // 2, (h_ + 1) // 2
+            return buf[:n].reshape(h_, w_)
+        if which in (TAP_T, TAP_H_STABILIZE, TAP_H_SCALED):
+            return buf[:n].reshape(3, 3)
+        if which == TAP_M:
+            return buf[:n].reshape(2, 3)
+        return buf[:n]
+
+    # ---- static helpers ----------------------------------------------------------------
+    @staticmethod
+    def decompose_homography(H: np.ndarray, center=(0.0, 0.0)):
+        H = np.asarray(H)
+        if H.shape != (3, 3) or H.dtype != np.float64:
+            raise ValueError("Error: Input homography matrix must be a non-empty 3x3 CV_64F matrix.")
+        Hc = np.ascontiguousarray(H)
+        hp = HParams()
+        r = load_library().vstab_decompose_homography(Hc.ctypes.data_as(_f64p), center[0], center[1], C.byref(hp))
+        if r < 0:
+            raise ValueError("bad argument")
+        if r == 0:
+            return None
+        return HomographyParameters(hp.s, hp.theta, hp.k, hp.delta, (hp.t[0], hp.t[1]), (hp.v[0], hp.v[1]))
+
+    @staticmethod
+    def compose_homography(p: HomographyParameters, center=(0.0, 0.0)) -> np.ndarray:
+        hp = HParams(p.s, p.theta, p.k, p.delta, (C.c_double * 2)(*p.t), (C.c_double * 2)(*p.v))
+        H = np.zeros((3, 3))
+        load_library().vstab_compose_homography(C.byref(hp), center[0], center[1], H.ctypes.data_as(_f64p))
+        return H
+
+
+# ---- single-kernel entry points (host arrays) ----------------------------------------------
+def k_ingest(bgr: np.ndarray, working_height: int, device: int = 0):
+    lib = load_library()
+    rows, cols = bgr.shape[:2]
+    s = float(working_height) / rows
+    ww = int(cols * s)
+    gray = np.empty((working_height, ww), np.uint8)
+    sums = (C.c_uint64 * 3)()
+    bgr = np.ascontiguousarray(bgr)
+    _check(lib.vstab_k_ingest(device, _ptr(bgr), rows, cols, bgr.strides[0], working_height, _ptr(gray), sums))
+    return gray, np.array(list(sums), dtype=np.uint64)
+
+
+def k_pyramid(gray: np.ndarray, device: int = 0):
+    lib = load_library()
+    h, w = gray.shape
+    outs = []
+    for _ in range(3):
+        w, h = (w + 1) // 2, (h + 1) // 2
+        outs.append(np.empty((h, w), np.uint8))
+    gray = np.ascontiguousarray(gray)
+    _check(lib.vstab_k_pyramid(device, _ptr(gray), gray.shape[0], gray.shape[1], *[_ptr(o) for o in outs]))
+    return outs
+
+
+def k_gftt(gray: np.ndarray, max_corners=1300, quality=0.01, min_distance=5, want_eig=False, device: int = 0):
+    lib = load_library()
+    gray = np.ascontiguousarray(gray)
+    pts = np.zeros((1300, 2), np.float32)
+    n = C.c_int(0)
+    eig = np.zeros(gray.shape, np.float32) if want_eig else None
+    _check(lib.vstab_k_gftt(device, _ptr(gray), gray.shape[0], gray.shape[1], max_corners, quality, min_distance,
+                            _ptr(pts), C.byref(n), _ptr(eig) if want_eig else None))
+    return (pts[:n.value].copy(), eig) if want_eig else pts[:n.value].copy()
+
+
+def k_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, device: int = 0):
+    lib = load_library()
+    prev = np.ascontiguousarray(prev)
+    nxt = np.ascontiguousarray(nxt)
+    pts = np.ascontiguousarray(pts, np.float32)
+    n = len(pts)
+    out = np.zeros((n, 2), np.float32)
+    st = np.zeros(n, np.uint8)
+    _check(lib.vstab_k_lk(device, _ptr(prev), _ptr(nxt), prev.shape[0], prev.shape[1], _ptr(pts), n, _ptr(out), _ptr(st)))
+    return out, st
+
+
+def k_fit(prev_pts, next_pts, status, work_w, work_h, thresh=3.0, device: int = 0):
+    lib = load_library()
+    a = np.ascontiguousarray(prev_pts, np.float32)
+    b = np.ascontiguousarray(next_pts, np.float32)
+    s = np.ascontiguousarray(status, np.uint8)
+    M = np.zeros((2, 3))
+    T = np.zeros((3, 3))
+    cnt = (C.c_int * 2)()
+    _check(lib.vstab_k_fit(device, _ptr(a), _ptr(b), _ptr(s), len(a), thresh, work_w, work_h,
+                           M.ctypes.data_as(_f64p), T.ctypes.data_as(_f64p), cnt))
+    return M, T, (cnt[0], cnt[1])
+
+
+def k_warp(bgr: np.ndarray, H: np.ndarray, border, device: int = 0):
+    lib = load_library()
+    bgr = np.ascontiguousarray(bgr)
+    H = np.ascontiguousarray(H, np.float64)
+    b = np.array(list(border)[:3], np.uint8)
+    out = np.empty_like(bgr)
+    _check(lib.vstab_k_warp(device, _ptr(bgr), bgr.shape[0], bgr.shape[1], bgr.strides[0], H.ctypes.data_as(_f64p),
+                            _ptr(b), _ptr(out), out.strides[0]))
+    return out

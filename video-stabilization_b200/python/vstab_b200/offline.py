@@ -1,0 +1,169 @@
+"""Offline (frame-sharded) stabilization over torch device tensors.
+
+BASELINE.json north_star: "the frame sequence is sharded across the 8 B200s of one box by
+contiguous frame ranges with halo frames.  Each GPU estimates its frame-pair transforms, a
+single small NCCL all-gather over NVLink exchanges the per-frame homographies for the global
+prefix accumulation and window smoothing, and each GPU then warps its own frames."
+
+Frame pairs are independent units (corners are re-detected every frame and tracked one step,
+/root/reference/src/stabilizer.cpp:1187,1318), so there is no data-path collective besides
+that one all-gather of 72 bytes per frame.  The index algebra (which call presents which
+frame, which transforms a call needs) is SURVEY.md Appendix C; `tests/test_sharding_gloo.py`
+checks it on CPU with world_size 2 and the oracle as estimator.
+
+torch is plumbing here (device memory, streams, torch.distributed); all pixel work happens
+in libvstab.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import (ACCUMULATED_FULL_LOCK, GLOBAL_SMOOTHING, _check, _vp, load_library)  # noqa: F401
+
+
+# ----------------------------------------------------------------------------------------------
+# pure index algebra (no torch, no GPU): testable on CPU
+# ----------------------------------------------------------------------------------------------
+def plan_shards(n_total: int, world: int):
+    """Contiguous, balanced frame ranges [first, last) per rank (first ranks get the remainder)."""
+    base, rem = divmod(n_total, world)
+    out, first = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((first, first + n))
+        first += n
+    return out
+
+
+def calls_of_shard(first: int, last: int, n_total: int, future: int):
+    """Call indices [c0, c1) whose presentation frame p(c) = max(0, c - future) lies in
+    [first, last).  The owner of frame 0 also produces the `future` warm-up calls; the last
+    `future` frames of a clip are never presented."""
+    if last <= first:
+        return (0, 0)
+    c0 = 0 if first == 0 else first + future
+    c1 = min(last + future, n_total)
+    return (c0, max(c0, c1))
+
+
+def padded_shard_len(n_total: int, world: int) -> int:
+    return -(-n_total // world)
+
+
+# ----------------------------------------------------------------------------------------------
+# device runner
+# ----------------------------------------------------------------------------------------------
+class OfflineStabilizer:
+    """One rank's share of an offline clip.  Tensors are CUDA tensors of this rank's device:
+    frames uint8 [n, rows, cols, 3] (contiguous), transforms float64 [n, 9], sums int64 [n, 3]."""
+
+    def __init__(self, past_frames: int, future_frames: int, working_height: int, rows: int, cols: int,
+                 max_batch: int, device: int = 0):
+        import torch
+        self._torch = torch
+        self._lib = load_library()
+        self._h = _vp()
+        self.P, self.F, self.rows, self.cols, self.max_batch, self.device = past_frames, future_frames, rows, cols, max_batch, device
+        _check(self._lib.vstab_offline_create(past_frames, future_frames, working_height, rows, cols, max_batch,
+                                              device, C.byref(self._h)))
+        self.stream = torch.cuda.ExternalStream(int(self._lib.vstab_offline_stream(self._h)), device=device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vstab_offline_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _frames_ok(self, t):
+        assert t.is_cuda and t.dtype == self._torch.uint8 and t.dim() == 4 and t.shape[1:] == (self.rows, self.cols, 3)
+        assert t.stride(3) == 1 and t.stride(2) == 3
+
+    def estimate(self, frames, first: int, halo, T_out, sums_out=None):
+        """T_out[i] <- transform frame (first+i-1) -> (first+i); sums_out[i] <- channel byte sums."""
+        self._frames_ok(frames)
+        n = frames.shape[0]
+        done = 0
+        while done < n:
+            m = min(self.max_batch, n - done)
+            h = None
+            if first + done > 0:
+                h = frames[done - 1] if done > 0 else halo
+                assert h is not None, "halo frame required for a shard that does not start at frame 0"
+            _check(self._lib.vstab_offline_estimate(
+                self._h, _vp(frames[done].data_ptr()), frames.stride(0), frames.stride(1), m, first + done,
+                _vp(h.data_ptr()) if h is not None else None, _vp(T_out[done].data_ptr()),
+                _vp(sums_out[done].data_ptr()) if sums_out is not None else None), self._h)
+            done += m
+
+    def prepare(self, T_all, mode: int, lock_call: int = 0):
+        _check(self._lib.vstab_offline_prepare(self._h, _vp(T_all.data_ptr()), T_all.shape[0], mode, lock_call), self._h)
+
+    def render(self, frames, frame_base: int, call_first: int, ncalls: int, T_all, mode: int, lock_call: int,
+               sums, out):
+        """out[i] <- output of stabilizeFrame call (call_first + i); frames/sums indexed by frame - frame_base."""
+        self._frames_ok(frames)
+        self._frames_ok(out)
+        assert out.shape[0] >= ncalls
+        done = 0
+        while done < ncalls:
+            m = min(self.max_batch, ncalls - done)
+            _check(self._lib.vstab_offline_render(
+                self._h, _vp(frames.data_ptr()), frames.stride(0), frames.stride(1), frame_base, m, call_first + done,
+                _vp(T_all.data_ptr()), T_all.shape[0], mode, lock_call, _vp(sums.data_ptr()),
+                _vp(out[done].data_ptr()), out.stride(0), out.stride(1)), self._h)
+            done += m
+
+    def read_h(self, ncalls: int):
+        import numpy as np
+        buf = np.zeros((ncalls, 9))
+        n = self._lib.vstab_offline_read_h(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), ncalls)
+        return buf[:n].reshape(-1, 3, 3)
+
+    def synchronize(self):
+        _check(self._lib.vstab_offline_synchronize(self._h), self._h)
+
+    def set_timing(self, on: bool):
+        self._lib.vstab_offline_set_timing(self._h, 1 if on else 0)
+
+    def stage_times(self):
+        ms = (C.c_float * 8)()
+        cnt = (C.c_int * 8)()
+        _check(self._lib.vstab_offline_stage_times(self._h, ms, cnt), self._h)
+        names = ("ingest", "pyramid", "gftt", "lk", "fit", "smooth", "warp", "acc_scan")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(names)}
+
+
+def gather_transforms(T_local, n_total: int, world: int, group=None):
+    """The one collective of the path: all-gather of the per-frame 3x3 transforms
+    (72 B/frame) so that every rank holds T[0..n_total).  T_local is [padded_len, 9]."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return T_local[:n_total]
+    pad = T_local.shape[0]
+    gathered = torch.empty((world * pad, 9), dtype=T_local.dtype, device=T_local.device)
+    dist.all_gather_into_tensor(gathered, T_local.contiguous(), group=group)
+    shards = plan_shards(n_total, world)
+    parts = [gathered[r * pad: r * pad + (l - f)] for r, (f, l) in enumerate(shards)]
+    return torch.cat(parts, dim=0)
+
+
+def stabilize_clip_sharded(frames_local, halo, n_total: int, rank: int, world: int, past: int, future: int,
+                           estimate_fn, render_fn, gather_fn, mode: int = GLOBAL_SMOOTHING, lock_call: int = 0):
+    """Backend-agnostic driver (the GPU runner and the CPU gloo test share it).
+
+    estimate_fn(frames_local, first, halo) -> (T_local [n,9], sums_local [n,3])
+    gather_fn(T_local_padded)              -> T_all [n_total, 9]
+    render_fn(frames_local, frame_base, call_first, ncalls, T_all, sums_local) -> outputs
+    Returns (call_first, outputs) for this rank's calls."""
+    first, last = plan_shards(n_total, world)[rank]
+    T_local, sums_local = estimate_fn(frames_local, first, halo)
+    T_all = gather_fn(T_local)
+    c0, c1 = calls_of_shard(first, last, n_total, future)
+    outs = render_fn(frames_local, first, c0, c1 - c0, T_all, sums_local)
+    return c0, outs
