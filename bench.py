@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- stabilized frames/s of the LK + warp hot path (BASELINE.json configs[1]).
+
+Workload ("c2_lk_full_lock_1080p"): synthetic 1920x1080 simulator clip (seeded texture +
+scripted camera path), working height 360, window 60/45, mode switched to
+ACCUMULATED_FULL_LOCK at call 46.  One *step* = one pass of the whole hot path over this
+rank's shard of the clip (frames resident in HBM):
+
+    ingest(resize+gray+channel sums) -> pyramid -> Shi-Tomasi -> pyramidal LK -> RANSAC fit
+    -> [all-gather of the 3x3 transforms when N > 1] -> prefix scan / window smoothing -> warp
+
+`value`  = frames of all ranks / device time (CUDA events on the library stream, max over ranks).
+`e2e`    = the same metric through the host-buffer C ABI (pinned host frames in, stabilized host
+           frames out, copies inside the timed region).
+`roofline` = dominant stage against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+`cpu_baseline` = the oracle (cv2 restatement of the reference, all host threads) on a bounded
+           sample of the same clip, rank 0 at N = 1 only.
+
+`--impl reference` times the reference's CPU path (the oracle; the C++ binary cannot be built
+offline: no OpenCV SDK) on the same config and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "video-stabilization_b200", "python")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+W, H, WH = 1920, 1080, 360
+PAST, FUTURE = 60, 45            # int(2.0*fps), int(1.5*fps) at the simulator's 30 fps (main.cpp:205-206)
+LOCK_CALL = 46                   # setStabilizationMode(ACCUMULATED_FULL_LOCK) issued at this call (>= FUTURE)
+METRIC = "stabilized_frames_per_sec_1080p_lk_full_lock"
+UNIT = "frames/s"
+WORKLOAD = "c2_lk_full_lock_1080p_wh360_window60_45"
+
+
+def working_width():
+    return int(W * (WH / H))
+
+
+def stage_bytes_per_frame():
+    """Algorithmic (minimum) HBM bytes per frame per stage -- SURVEY.md 8d / DESIGN.md."""
+    B = 3 * W * H
+    px = working_width() * WH
+    return {
+        "ingest": B + px,
+        "pyramid": px * (1 + 1 / 4 + 1 / 16) + px * (1 / 4 + 1 / 16 + 1 / 64),
+        "gftt": 2 * px + 1300 * 8,
+        "lk": 2 * 1.328125 * px + 1300 * 17,
+        "fit": 1300 * 17 + 72,
+        "smooth": 105 * 72 + 72,
+        "warp": 2 * B,
+        "acc_scan": 2 * 72,
+    }
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(stage):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(stage)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
+            rows = [r for r in rows if len(r) >= 7]
+            sm = sorted(float(r[0]) for r in rows)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["power_w_max"] = max(float(r[2]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i].strip() == "Active" for r in rows)]
+                out["samples"] = len(rows)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (reference restatement over cv2) -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+def _render_one(args):
+    from oracle import camera_engine_ref as ce
+    from vstab_b200 import synth
+    i, n = args
+    tex = synth.make_texture(2048)
+    return ce.render_frame(tex, synth.camera_path(n)[i], W, H, synth.focal_for_width(W))
+
+
+def cpu_frames(n):
+    """n distinct frames of the workload clip rendered on the host (numpy restatement of CameraEngine)."""
+    import multiprocessing as mp
+    from vstab_b200 import synth
+    synth.make_texture(2048)          # populate the on-disk cache once before forking
+    procs = max(1, min(os.cpu_count() or 1, n, 32))
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(_render_one, [(i, n) for i in range(n)])
+
+
+def pingpong(i, n):
+    """frame index of call i when n distinct frames are played forward/backward (motion stays small)."""
+    period = 2 * (n - 1)
+    j = i % period
+    return j if j < n else period - j
+
+
+class CpuArm:
+    """Streams the workload through oracle.StabilizerRef (the reference's per-frame loop over the
+    same OpenCV kernels, all quirks kept incl. GFTT twice and the three full-frame clones)."""
+
+    def __init__(self, frames):
+        import cv2
+        from oracle import stabilizer_ref as sr
+        cv2.setNumThreads(os.cpu_count() or 1)
+        self.cores = int(cv2.getNumThreads())
+        self.sr = sr
+        self.frames = frames
+        self.ref = sr.StabilizerRef(PAST, FUTURE, WH, faithful_waste=True)
+        self.ref.collect_taps = False
+        self.i = 0
+
+    def run(self, ncalls):
+        t0 = time.perf_counter()
+        for _ in range(ncalls):
+            if self.i == LOCK_CALL:
+                self.ref.set_stabilization_mode(self.sr.ACCUMULATED_FULL_LOCK)
+            self.ref.stabilize_frame(self.frames[pingpong(self.i, len(self.frames))])
+            self.i += 1
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_distinct = args.cpu_distinct_frames
+    frames = cpu_frames(n_distinct)
+    arm = CpuArm(frames)
+    per_step = args.cpu_frames_per_step
+    for _ in range(args.warmup):
+        arm.run(per_step)
+    t = 0.0
+    for _ in range(args.steps):
+        t += arm.run(per_step)
+    fps = args.steps * per_step / t
+    sample = (f"{per_step} stabilizeFrame calls per step over {n_distinct} distinct 1080p simulator frames played "
+              f"ping-pong, oracle.StabilizerRef (cv2 {__import__('cv2').__version__}, reference control flow incl. "
+              f"GFTT x2 and frame clones), continuous stream across steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST, "future": FUTURE,
+                   "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL, "frames_per_step": per_step},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "kind=port: the C++ reference needs the OpenCV C++ SDK (absent, no network); the port calls the same "
+                "OpenCV kernels through cv2 at the reference's call sites (Python overhead < 4 %)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vstab_b200 as vs
+    from vstab_b200 import offline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    vs.load_library()
+    lib = vs.load_library()
+
+    n_local = args.frames_per_gpu
+    n_total = n_local * world
+    first, last = offline.plan_shards(n_total, world)[rank]
+    pad = offline.padded_shard_len(n_total, world)
+    c0, c1 = offline.calls_of_shard(first, last, n_total, FUTURE)
+    ncalls = c1 - c0
+
+    # ---- synthetic clip, rendered on the device (K13), shard [first-1, last) ------------------------
+    tex = torch.from_numpy(synth.make_texture(2048)).to(dev)
+    path = synth.camera_path(n_total)
+    has_halo = first > 0
+    buf = torch.empty((n_local + 1, H, W, 3), dtype=torch.uint8, device=dev)
+    lo = first - 1 if has_halo else first
+    chunk = 64
+    for s in range(lo, last, chunk):
+        e = min(last, s + chunk)
+        offline.render_frames(tex, path[s:e], H, W, synth.focal_for_width(W), buf[s - lo: e - lo], device=local)
+    frames = buf[1:] if has_halo else buf[:n_local]
+    halo = buf[0] if has_halo else None
+    out = torch.empty((max(ncalls, 1), H, W, 3), dtype=torch.uint8, device=dev)
+    T_local = torch.zeros((pad, 9), dtype=torch.float64, device=dev)
+    sums = torch.zeros((n_local, 3), dtype=torch.int64, device=dev)
+
+    off = offline.OfflineStabilizer(PAST, FUTURE, WH, H, W, args.batch, device=local)
+    mode = vs.ACCUMULATED_FULL_LOCK
+
+    def step():
+        off.estimate(frames, first, halo, T_local, sums)
+        if world > 1:
+            with torch.cuda.stream(off.stream):
+                T_all = offline.gather_transforms(T_local, n_total, world)
+        else:
+            T_all = T_local[:n_total]
+        off.prepare(T_all, mode, LOCK_CALL)
+        if ncalls > 0:
+            off.render(frames, first, c0, ncalls, T_all, mode, LOCK_CALL, sums, out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region -----------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    off.set_timing(True)
+    off.stage_times()
+    launches0 = lib.vstab_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(off.stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(off.stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vstab_launch_count() - launches0
+    stages = off.stage_times()
+    off.set_timing(False)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- per-stage roofline -----------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    bpf = stage_bytes_per_frame()
+    stage_rows = {}
+    tot_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    for name, (sms, cnt) in stages.items():
+        if cnt == 0:
+            continue
+        frames_done = (n_local + (1 if has_halo and name in ("pyramid",) else 0)) * args.steps
+        if name in ("smooth", "warp"):
+            frames_done = ncalls * args.steps
+        gbs = bpf[name] * frames_done / (sms * 1e-3) / 1e9 if sms > 0 else 0.0
+        stage_rows[name] = {"ms_per_step": sms / args.steps, "share": sms / tot_stage_ms, "launches": cnt,
+                            "avg_launch_ms": sms / cnt, "bytes_per_frame": bpf[name], "achieved_gbs": gbs,
+                            "frac": gbs / peak}
+    dom = max(stage_rows, key=lambda k: stage_rows[k]["ms_per_step"])
+    d = stage_rows[dom]
+    bytes_per_launch = d["achieved_gbs"] * 1e9 * d["avg_launch_ms"] * 1e-3
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": d["avg_launch_ms"],
+                "share_of_step": d["share"]}
+
+    # ---- e2e: host-buffer C ABI (pinned host frames in, stabilized host frames out) ------------------
+    e2e = run_e2e(args, torch, vs, lib, frames, local, world, dev, dist)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        nd = args.cpu_distinct_frames
+        host_frames = [frames[i].cpu().numpy() for i in range(nd)]     # same bytes as the numpy renderer (tests)
+        arm = CpuArm(host_frames)
+        arm.run(50)
+        ncpu = args.cpu_sample_frames
+        t = arm.run(ncpu)
+        cpu = {"value": ncpu / t, "unit": UNIT, "cores": arm.cores, "kind": "port",
+               "sample": f"{ncpu} stabilizeFrame calls after 50 warm-up calls over the first {nd} frames of the clip "
+                         f"(ping-pong), oracle.StabilizerRef over cv2 with {arm.cores} threads; host has "
+                         f"{os.cpu_count()} logical cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST,
+                       "future": FUTURE, "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL,
+                       "frames_per_gpu": n_local, "frames_total": n_total, "batch": args.batch,
+                       "l2_policy": f"inputs_exceed_l2 ({n_local * 3 * W * H / 1e6:.0f} MB of frames per GPU per step vs 126 MB L2)",
+                       "parallelism": f"frame-sharded x{world}, one all-gather of 72 B/frame" if world > 1 else "single GPU"},
+            "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
+    """Host-buffer path: vstab_stabilize_frame (the reference-facing call, include/vstab.h) fed from
+    pinned host memory, output read back to pinned host memory, every call synchronous."""
+    n_host = min(args.e2e_distinct_frames, frames.shape[0])
+    nbytes = H * W * 3
+    lib.vstab_host_alloc.restype = C.c_void_p
+    hin = lib.vstab_host_alloc(n_host * nbytes)
+    hout = lib.vstab_host_alloc(nbytes)
+    if not hin or not hout:
+        raise SystemExit("pinned host allocation failed")
+    hin_np = np.ctypeslib.as_array((C.c_uint8 * (n_host * nbytes)).from_address(hin)).reshape(n_host, H, W, 3)
+    hin_np[:] = frames[:n_host].cpu().numpy()
+    st = vs.Stabilizer(PAST, FUTURE, WH, device=local)
+    per_step = args.e2e_frames_per_step
+    i = 0
+
+    def run(n):
+        nonlocal i
+        for _ in range(n):
+            if i == LOCK_CALL:
+                st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
+            st.stabilize_frame_ptr(hin + pingpong(i, n_host) * nbytes, H, W, W * 3, hout, W * 3)
+            i += 1
+
+    run(max(per_step, LOCK_CALL + 4))     # warm-up incl. the mode switch
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(per_step)
+    st.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    st.close()
+    lib.vstab_host_free(C.c_void_p(hin))
+    lib.vstab_host_free(C.c_void_p(hout))
+    return {"value": world * per_step * args.steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": per_step * nbytes, "d2h_bytes_per_step": per_step * nbytes,
+            "api": "vstab_stabilize_frame (streaming, synchronous per frame, pinned host buffers)",
+            "frames_per_step": per_step, "timer": "host wall clock around synchronous calls, max over ranks"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=128, help="frames per kernel launch (offline batch)")
+    ap.add_argument("--e2e-frames-per-step", type=int, default=128)
+    ap.add_argument("--e2e-distinct-frames", type=int, default=96)
+    ap.add_argument("--cpu-distinct-frames", type=int, default=48)
+    ap.add_argument("--cpu-sample-frames", type=int, default=400)
+    ap.add_argument("--cpu-frames-per-step", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,3 +167,19 @@ def stabilize_clip_sharded(frames_local, halo, n_total: int, rank: int, world: i
     c0, c1 = calls_of_shard(first, last, n_total, future)
     outs = render_fn(frames_local, first, c0, c1 - c0, T_all, sums_local)
     return c0, outs
+
+
+def render_frames(texture, poses, rows: int, cols: int, focal: float, out, device: int = 0):
+    """CameraEngine::renderFrame for a batch of poses on the device (K13;
+    /root/reference/src/camera_engine.cpp:158-172).  `texture` uint8 [th, tw, 3] and `out`
+    uint8 [n, rows, cols, 3] are CUDA tensors; `poses` is a host float64 array [n, 6] of
+    (x, y, z, pan, tilt, roll).  Synchronous."""
+    import numpy as np
+    poses = np.ascontiguousarray(poses, np.float64)
+    n = poses.shape[0]
+    assert out.is_cuda and out.shape[0] >= n and tuple(out.shape[1:]) == (rows, cols, 3)
+    assert texture.is_cuda and texture.is_contiguous()
+    lib = load_library()
+    _check(lib.vstab_render_frames(device, _vp(texture.data_ptr()), texture.shape[0], texture.shape[1],
+                                   poses.ctypes.data_as(C.POINTER(C.c_double)), n, rows, cols, float(focal),
+                                   _vp(out.data_ptr()), out.stride(0), out.stride(1)))
