@@ -331,7 +331,7 @@ def run_ours(args):
                 "share_of_step": d["share"]}
 
     # ---- e2e: host-buffer C ABI (pinned host frames in, stabilized host frames out) ------------------
-    e2e = run_e2e(args, torch, vs, lib, frames, local, world, dev, dist)
+    e2e = None if args.no_e2e else run_e2e(args, torch, vs, lib, frames, local, world, dev, dist)
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
@@ -427,6 +427,7 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=400)
     ap.add_argument("--cpu-frames-per-step", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -144,6 +144,12 @@ def corner_min_eigen_val(gray: np.ndarray) -> np.ndarray:
     t = p[:, :-2] * k1
     t = _fma32(p[:, 1:-1], np.broadcast_to(k0, t.shape), t)
     R = _fma32(p[:, 2:], np.broadcast_to(k1, t.shape), t)     # (h+2) x w
+    # [probe] the FMA vector body of OpenCV's row filter covers the first floor(w/32)*32 columns
+    # (cv2 4.13.0, AVX-512 dispatch); the remaining columns go through the scalar tail, which is
+    # not contracted: ((p[x-1]*k1) + (p[x]*k0)) + (p[x+1]*k1).  640/1280/1920/3840 have no tail.
+    tail = (w // 32) * 32
+    if tail < w:
+        R[:, tail:] = ((p[:, tail:w] * k1) + (p[:, tail + 1:w + 1] * k0)) + (p[:, tail + 2:w + 2] * k1)
     Dy = R[2:] - R[:-2]
     dxx = Dx * Dx
     dxy = Dx * Dy
@@ -343,6 +349,14 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
                     out[i, 1] = F32(out[i, 1] - ddy * F32(0.5))
                     break
                 pdx, pdy = ddx, ddy
+            # the `err` block of LKTrackerInvoker (the reference passes an err vector,
+            # stabilizer.cpp:192-195): at level 0 a still-valid point whose final window origin
+            # lies outside the image gets status 0 (its coordinates are kept).
+            if level == 0 and status[i]:
+                fx = int(math.floor(F32(out[i, 0] - F32(half))))
+                fy = int(math.floor(F32(out[i, 1] - F32(half))))
+                if fx < -win or fx >= cols or fy < -win or fy >= rows:
+                    status[i] = 0
     return out, status
 
 

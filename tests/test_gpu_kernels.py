@@ -132,6 +132,14 @@ def test_lk_golden_and_edge_cases(golden):
     _, st = vs.k_lk(flat, flat, pts)
     _, ref = _cv_lk(flat, flat, pts)
     assert np.array_equal(st, ref) and (st == 0).all()
+    # points tracked beyond the border keep their coordinates but lose their status
+    g0 = golden["g0"]
+    g1 = np.roll(g0, (3, 16), axis=(0, 1))
+    pts = np.array([[g0.shape[1] - 6, 100], [g0.shape[1] - 3, 40], [150, g0.shape[0] - 2], [160, 90], [2, 3]], np.float32)
+    out, st = vs.k_lk(g0, g1, pts)
+    cur, ref = _cv_lk(g0, g1, pts)
+    assert np.array_equal(st, ref) and (ref == 0).any() and (ref == 1).any()
+    assert np.abs(out[ref == 1] - cur[ref == 1]).max() <= 2e-3
 
 
 # ------------------------------------------------------------------ K5 fit

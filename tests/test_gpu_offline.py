@@ -35,7 +35,7 @@ def test_render_matches_camera_engine(texture_small, W, H):
 def test_render_sky_and_tilted_pose(texture_small):
     """A tilted camera sees the horizon: sky colour above it (camera_engine.cpp:119), floor below."""
     W, H = 320, 240
-    poses = np.array([[0.5, -0.3, 0.7, 10.0, 120.0, 175.0], [0.2, 0.1, 1.5, -30.0, 95.0, 182.0]])
+    poses = np.array([[0.5, -0.3, 0.7, 5.0, 80.0, 170.0], [0.2, 0.1, 1.5, -30.0, 95.0, 182.0]])
     tex = torch.from_numpy(texture_small).cuda()
     out = torch.empty((2, H, W, 3), dtype=torch.uint8, device="cuda")
     offline.render_frames(tex, poses, H, W, 250.0, out)

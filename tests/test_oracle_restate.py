@@ -90,6 +90,23 @@ def test_lk_matches_golden(golden):
     assert np.abs(out[ok] - golden["lk_pts"][::3][ok]).max() <= 1e-3    # tolerance: 0.05 px (north star)
 
 
+def test_lk_point_leaving_the_image_loses_status(golden):
+    """A point tracked beyond the right/bottom border keeps its coordinates but gets status 0
+    (the `err` block of OpenCV's LK at level 0; seen on the 720p clip at frame 38)."""
+    import cv2
+    g0 = golden["g0"]
+    g1 = np.roll(g0, (3, 16), axis=(0, 1))               # content moves +16 px in x, +3 in y
+    pts = np.array([[g0.shape[1] - 6, 100], [g0.shape[1] - 3, 40], [150, g0.shape[0] - 2], [160, 90]], np.float32)
+    ref, st, _ = cv2.calcOpticalFlowPyrLK(g0, g1, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3,
+                                          criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 50, 0.01),
+                                          flags=0, minEigThreshold=1e-4)
+    out, got = R.calc_optical_flow_pyr_lk(g0, g1, pts)
+    assert np.array_equal(got, st.reshape(-1))
+    assert (st.reshape(-1) == 0).any() and (st.reshape(-1) == 1).any()
+    ok = st.reshape(-1) == 1
+    assert np.abs(out[ok] - ref.reshape(-1, 2)[ok]).max() <= 1e-3
+
+
 def test_ransac_exact_consensus(golden):
     p, q = golden["ransac_p"], golden["ransac_q"]
     corners = np.array([[0, 0, 1], [320, 0, 1], [0, 180, 1], [320, 180, 1]], float).T

@@ -60,10 +60,19 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h,
         const float sp = g[tr + 1][tc + 1] - g[tr + 1][tc - 1];
         const float dx = __fmaf_rn(__fadd_rn(sm, sp), k1, __fmul_rn(s0, k0));
         // Dy = R[y+1] - R[y-1],  R[y] = fma(p[x+1], k1, fma(p[x], k0, p[x-1]*k1))
-        const float rm = __fmaf_rn(g[tr - 1][tc + 1], k1,
-                                   __fmaf_rn(g[tr - 1][tc], k0, __fmul_rn(g[tr - 1][tc - 1], k1)));
-        const float rp = __fmaf_rn(g[tr + 1][tc + 1], k1,
-                                   __fmaf_rn(g[tr + 1][tc], k0, __fmul_rn(g[tr + 1][tc - 1], k1)));
+        // OpenCV's row filter runs its FMA vector body over the first floor(w/32)*32 columns and a
+        // scalar, un-contracted tail over the rest ([probe] cv2 4.13.0 on AVX-512 hosts; all
+        // production widths 640/1280/1920/3840 are multiples of 32 and never reach the tail).
+        float rm, rp;
+        if (px < (w & ~31)) {
+            rm = __fmaf_rn(g[tr - 1][tc + 1], k1, __fmaf_rn(g[tr - 1][tc], k0, __fmul_rn(g[tr - 1][tc - 1], k1)));
+            rp = __fmaf_rn(g[tr + 1][tc + 1], k1, __fmaf_rn(g[tr + 1][tc], k0, __fmul_rn(g[tr + 1][tc - 1], k1)));
+        } else {
+            rm = __fadd_rn(__fadd_rn(__fmul_rn(g[tr - 1][tc - 1], k1), __fmul_rn(g[tr - 1][tc], k0)),
+                           __fmul_rn(g[tr - 1][tc + 1], k1));
+            rp = __fadd_rn(__fadd_rn(__fmul_rn(g[tr + 1][tc - 1], k1), __fmul_rn(g[tr + 1][tc], k0)),
+                           __fmul_rn(g[tr + 1][tc + 1], k1));
+        }
         const float dy = __fsub_rn(rp, rm);
         pxx[r][c] = __fmul_rn(dx, dx);
         pxy[r][c] = __fmul_rn(dx, dy);

@@ -211,6 +211,13 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
             }
             pdx = ddx; pdy = ddy;
         }
+        // the `err` block of OpenCV's LKTrackerInvoker (the reference passes an err vector,
+        // stabilizer.cpp:192-195): at level 0 a still-valid point whose final window origin lies
+        // outside the image loses its status (coordinates are kept).
+        if (L == 0 && st) {
+            const int fx = (int)floorf(__fsub_rn(outx, half)), fy = (int)floorf(__fsub_rn(outy, half));
+            if (fx < -kLkWin || fx >= cols || fy < -kLkWin || fy >= rows) st = 0;
+        }
     }
     if (lane == 0) {
         out_pts[(size_t)frame * kMaxCorners + fi] = make_float2(outx, outy);
