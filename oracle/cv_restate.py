@@ -257,6 +257,14 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
     """Sparse pyramidal LK, control flow and fixed-point formats of OpenCV's
     LKTrackerInvoker.  Returns (next_pts float32 (N,2), status u8)."""
     half = (win - 1) * 0.5
+    # buildOpticalFlowPyramid drops every level that is not larger than the window in both
+    # dimensions ([probe] 128x96 with win 21 keeps levels 0..2), lowering the effective maxLevel
+    hh, ww = prev.shape
+    for lvl in range(1, max_level + 1):
+        ww, hh = (ww + 1) // 2, (hh + 1) // 2
+        if ww <= win or hh <= win:
+            max_level = lvl - 1
+            break
     pp = lk_pyramid(prev, max_level)
     np_ = lk_pyramid(nxt, max_level)
     N = len(pts)

@@ -142,6 +142,19 @@ def test_lk_golden_and_edge_cases(golden):
     assert np.abs(out[ref == 1] - cur[ref == 1]).max() <= 2e-3
 
 
+def test_lk_small_image_drops_pyramid_levels(golden):
+    """128x96: OpenCV keeps levels 0..2 only (level 3 would not exceed the 21 px window); tiny levels
+    also exercise the multiply-reflected padding."""
+    for (w, h) in ((128, 96), (177, 100), (120, 91)):
+        gray = lambda f: cv2.cvtColor(cv2.resize(f, (w, h), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
+        a, b = gray(golden["clip"][3]), gray(golden["clip"][4])
+        pts = cv2.goodFeaturesToTrack(a, 1300, 0.01, 1).reshape(-1, 2)
+        cur, ref = _cv_lk(a, b, pts)
+        out, st = vs.k_lk(a, b, pts)
+        assert np.array_equal(st, ref)
+        assert np.abs(out[ref == 1] - cur[ref == 1]).max() <= 2e-3
+
+
 # ------------------------------------------------------------------ K5 fit
 def _kill_scale(M, w, h):
     o = sr.StabilizerRef(15, 15, 360)

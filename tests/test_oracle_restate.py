@@ -107,6 +107,21 @@ def test_lk_point_leaving_the_image_loses_status(golden):
     assert np.abs(out[ok] - ref.reshape(-1, 2)[ok]).max() <= 1e-3
 
 
+def test_lk_small_image_drops_pyramid_levels(golden):
+    """On 128x96 OpenCV keeps pyramid levels 0..2 only (level 3 would be 16x12 <= the 21 px window)."""
+    import cv2
+    gray = lambda f: cv2.cvtColor(cv2.resize(f, (128, 96), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
+    a, b = gray(golden["clip"][3]), gray(golden["clip"][4])
+    pts = cv2.goodFeaturesToTrack(a, 1300, 0.01, 1).reshape(-1, 2)[:60]
+    ref, st, _ = cv2.calcOpticalFlowPyrLK(a, b, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3,
+                                          criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 50, 0.01),
+                                          flags=0, minEigThreshold=1e-4)
+    out, got = R.calc_optical_flow_pyr_lk(a, b, pts)
+    assert np.array_equal(got, st.reshape(-1))
+    ok = got == 1
+    assert np.abs(out[ok] - ref.reshape(-1, 2)[ok]).max() <= 5e-5
+
+
 def test_ransac_exact_consensus(golden):
     p, q = golden["ransac_p"], golden["ransac_q"]
     corners = np.array([[0, 0, 1], [320, 0, 1], [0, 180, 1], [320, 180, 1]], float).T

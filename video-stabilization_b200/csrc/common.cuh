@@ -26,12 +26,29 @@ VSTAB_HD int luma_q15(int b, int g, int r) {
     return (3735 * b + 19235 * g + 9798 * r + 16384) >> 15;
 }
 
-// A device-resident gray pyramid of one frame: level l is (w[l] x h[l]) u8, tight rows.
+// OpenCV pads every LK pyramid level by the window size; kLkPad >= 22 covers every tap the
+// tracker may touch (window origins in [-21, cols-1], taps up to origin + 22).
+constexpr int kLkPad = 24;
+
+// BORDER_REFLECT_101 for any i (cv::borderInterpolate loops for small images), n >= 2
+VSTAB_HD int reflect101_multi(int i, int n) {
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// A device-resident gray pyramid of one frame.  Level l exists three times inside the frame's
+// block: tight (w x h u8: pyrDown chain, corner detector, taps), padded by kLkPad with
+// BORDER_REFLECT_101 (u8, row pitch `pitch[l]`) and its Scharr derivative image, padded with
+// zeros (short2 {dx, dy}, same geometry) -- the two buffers cv::calcOpticalFlowPyrLK tracks on.
 struct PyrDesc {
     int w[kLkLevels];
     int h[kLkLevels];
-    size_t off[kLkLevels];   // byte offset of level l inside one frame's pyramid block
-    size_t frame_bytes;      // bytes of one frame's pyramid block (all levels)
+    int pitch[kLkLevels];    // padded row pitch in pixels (multiple of 4)
+    int nlev;                // levels OpenCV keeps: next level must be larger than the LK window in both dims
+    size_t off[kLkLevels];   // byte offset of the tight level l inside one frame's pyramid block
+    size_t poff[kLkLevels];  // byte offset of padded pixel (-kLkPad, -kLkPad) of level l
+    size_t doff[kLkLevels];  // byte offset of the padded derivative image (4 bytes per pixel)
+    size_t frame_bytes;      // bytes of one frame's pyramid block
 };
 
 template <typename T>

@@ -9,60 +9,55 @@
 // (exact 64-bit integer sums here) => <= 1e-3 px against the 0.05 px tolerance.
 //
 // The 21x21 template (I, Ix, Iy) of a level lives in registers: lane l owns pixels
-// k = l + 32 s (s = 0..13).  The 24x24 u8 footprint and the 22x22 Scharr field are staged
-// in shared memory per warp; the 2x2 system and the mismatch vector are shuffle-reduced.
+// k = l + 32 s (s = 0..13).  Intensities come from the padded u8 level (reflect-101 border)
+// and derivatives from the padded Scharr level (zero border) that K2 prepares, so no tap ever
+// needs border logic; both are tiny and L1/L2-resident.  The 2x2 system and the mismatch
+// vector are reduced exactly with redux.sync.
 #include "kernels.h"
 
 namespace vstabk {
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kFoot = kLkWin + 3;      // 24: intensity footprint incl. derivative halo
-constexpr int kDer = kLkWin + 1;       // 22: derivative sites
 constexpr int kPix = kLkWin * kLkWin;  // 441
 constexpr int kStrides = (kPix + 31) / 32;  // 14
 
-struct WarpSmem {
-    uint8_t foot[kFoot][kFoot];
-    short dx[kDer][kDer];
-    short dy[kDer][kDer];
-};
-
-VSTAB_D int clamp_reflect(int i, int n) {
-    i = min(max(i, -(n - 1)), 2 * n - 2);
-    return reflect101(i, n);
+// exact warp-wide sum of one int32 per lane (|v| < 2^31) as a 64-bit integer: two redux.sync
+VSTAB_D long long warp_sum_i32(int v) {
+    const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return ((long long)hi << 16) + (long long)lo;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
           size_t prev_stride, size_t next_stride, PyrDesc d,
           const float2* __restrict__ pts, const int* __restrict__ counts,
           float2* __restrict__ out_pts, uint8_t* __restrict__ status) {
-    __shared__ WarpSmem smem[kWarpsPerBlock];
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fi = blockIdx.x * kWarpsPerBlock + warp;
     if (fi >= counts[frame]) return;
-    WarpSmem& sm = smem[warp];
     const uint8_t* pI = prev_pyr + (size_t)frame * prev_stride;
     const uint8_t* pJ = next_pyr + (size_t)frame * next_stride;
     const float2 pt = pts[(size_t)frame * kMaxCorners + fi];
 
-    // pixel ownership: k = lane + 32 s  ->  (ky, kx)
     float outx = 0.f, outy = 0.f;
     int st = 1;
     const float half = (float)(kLkWin - 1) * 0.5f;
     const float kFltScale = 1.f / (float)(1 << 20);
 
 #pragma unroll 1
-    for (int L = kLkLevels - 1; L >= 0; --L) {
-        const int cols = d.w[L], rows = d.h[L];
-        const uint8_t* I = pI + d.off[L];
-        const uint8_t* J = pJ + d.off[L];
+    for (int L = d.nlev - 1; L >= 0; --L) {
+        const int cols = d.w[L], rows = d.h[L], P = d.pitch[L];
+        const size_t org = (size_t)kLkPad * P + kLkPad;          // padded offset of image pixel (0,0)
+        const uint8_t* I = pI + d.poff[L] + org;
+        const short* dI = reinterpret_cast<const short*>(pI + d.doff[L]) + org * 2;
+        const uint8_t* J = pJ + d.poff[L] + org;
         const float lscale = (float)(1. / (1 << L));
         float px = __fmul_rn(pt.x, lscale), py = __fmul_rn(pt.y, lscale);
         float nx, ny;
-        if (L == kLkLevels - 1) { nx = px; ny = py; }
+        if (L == d.nlev - 1) { nx = px; ny = py; }
         else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
         outx = nx; outy = ny;
         px = __fsub_rn(px, half); py = __fsub_rn(py, half);
@@ -80,58 +75,43 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
             w10 = __float2int_rn(__fmul_rn(__fmul_rn(ia, b), 16384.f));
             w11 = 16384 - w00 - w01 - w10;
         }
-        // ---- stage the 24x24 footprint (reflect-101) and the 22x22 Scharr field ----------
-        __syncwarp();
-        for (int i = lane; i < kFoot * kFoot; i += 32) {
-            const int r = i / kFoot, c = i - r * kFoot;
-            const int gy = clamp_reflect(iy - 1 + r, rows);
-            const int gx = clamp_reflect(ix - 1 + c, cols);
-            sm.foot[r][c] = I[(size_t)gy * cols + gx];
-        }
-        __syncwarp();
-        for (int i = lane; i < kDer * kDer; i += 32) {
-            const int r = i / kDer, c = i - r * kDer;
-            const int gy = iy + r, gx = ix + c;
-            int dx = 0, dy = 0;
-            if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-                const int a00 = sm.foot[r][c], a01 = sm.foot[r][c + 1], a02 = sm.foot[r][c + 2];
-                const int a10 = sm.foot[r + 1][c], a12 = sm.foot[r + 1][c + 2];
-                const int a20 = sm.foot[r + 2][c], a21 = sm.foot[r + 2][c + 1], a22 = sm.foot[r + 2][c + 2];
-                dx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
-                dy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
-            }
-            sm.dx[r][c] = (short)dx;
-            sm.dy[r][c] = (short)dy;
-        }
-        __syncwarp();
-        // ---- template patch into registers, 2x2 normal matrix -----------------------------
-        int Iw[kStrides], Ix[kStrides], Iy[kStrides];
-        long long sA11 = 0, sA12 = 0, sA22 = 0;
+        // offsets of the pixels this lane owns (k = lane + 32 s -> ky * P + kx), shared by the
+        // template and every iteration of this level
+        int koff[kStrides];
 #pragma unroll
         for (int s = 0; s < kStrides; ++s) {
             const int k = lane + 32 * s;
-            Iw[s] = 0; Ix[s] = 0; Iy[s] = 0;
-            if (k < kPix) {
-                const int ky = (k * 3121) >> 16;           // k / 21 for k < 441
-                const int kx = k - ky * kLkWin;
-                const int iv = sm.foot[ky + 1][kx + 1] * w00 + sm.foot[ky + 1][kx + 2] * w01 +
-                               sm.foot[ky + 2][kx + 1] * w10 + sm.foot[ky + 2][kx + 2] * w11;
-                const int xv = sm.dx[ky][kx] * w00 + sm.dx[ky][kx + 1] * w01 +
-                               sm.dx[ky + 1][kx] * w10 + sm.dx[ky + 1][kx + 1] * w11;
-                const int yv = sm.dy[ky][kx] * w00 + sm.dy[ky][kx + 1] * w01 +
-                               sm.dy[ky + 1][kx] * w10 + sm.dy[ky + 1][kx + 1] * w11;
-                Iw[s] = (iv + (1 << 8)) >> 9;
-                Ix[s] = (xv + (1 << 13)) >> 14;
-                Iy[s] = (yv + (1 << 13)) >> 14;
-                sA11 += Ix[s] * Ix[s];
-                sA12 += Ix[s] * Iy[s];
-                sA22 += Iy[s] * Iy[s];
+            const int ky = (k * 3121) >> 16;               // k / 21 for k < 448
+            koff[s] = ky * P + (k - ky * kLkWin);
+        }
+
+        // ---- template patch (I in Q5, Ix/Iy) into registers, 2x2 normal matrix ---------------
+        int Iw[kStrides], Ix[kStrides], Iy[kStrides];
+        int sA11 = 0, sA12 = 0, sA22 = 0;          // per lane <= 14 * 4080^2 < 2^31
+        {
+            const int o0 = iy * P + ix;
+#pragma unroll
+            for (int s = 0; s < kStrides; ++s) {
+                Iw[s] = 0; Ix[s] = 0; Iy[s] = 0;
+                if (lane + 32 * s < kPix) {
+                    const int o = o0 + koff[s];
+                    const uint8_t* q = I + o;
+                    const short* g = dI + 2 * o;
+                    const int iv = q[0] * w00 + q[1] * w01 + q[P] * w10 + q[P + 1] * w11;
+                    const int xv = g[0] * w00 + g[2] * w01 + g[2 * P] * w10 + g[2 * P + 2] * w11;
+                    const int yv = g[1] * w00 + g[3] * w01 + g[2 * P + 1] * w10 + g[2 * P + 3] * w11;
+                    Iw[s] = (iv + (1 << 8)) >> 9;
+                    Ix[s] = (xv + (1 << 13)) >> 14;
+                    Iy[s] = (yv + (1 << 13)) >> 14;
+                    sA11 += Ix[s] * Ix[s];
+                    sA12 += Ix[s] * Iy[s];
+                    sA22 += Iy[s] * Iy[s];
+                }
             }
         }
-        sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
-        const float A11 = __fmul_rn((float)sA11, kFltScale);
-        const float A12 = __fmul_rn((float)sA12, kFltScale);
-        const float A22 = __fmul_rn((float)sA22, kFltScale);
+        const float A11 = __fmul_rn((float)warp_sum_i32(sA11), kFltScale);
+        const float A12 = __fmul_rn((float)warp_sum_i32(sA12), kFltScale);
+        const float A22 = __fmul_rn((float)warp_sum_i32(sA22), kFltScale);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         {
             const float dd = __fsub_rn(A11, A22);
@@ -161,44 +141,20 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
                 v10 = __float2int_rn(__fmul_rn(__fmul_rn(ia, b), 16384.f));
                 v11 = 16384 - v00 - v01 - v10;
             }
-            int sb1 = 0, sb2 = 0;
-            const bool inside = jx >= 0 && jy >= 0 && jx + kLkWin < cols && jy + kLkWin < rows;
-            if (inside) {
-                const uint8_t* Jw = J + (size_t)jy * cols + jx;
+            int sb1 = 0, sb2 = 0;                   // per lane <= 14 * 8160 * 4080 < 2^31
+            const int o0 = jy * P + jx;
 #pragma unroll
-                for (int s = 0; s < kStrides; ++s) {
-                    const int k = lane + 32 * s;
-                    if (k < kPix) {
-                        const int ky = (k * 3121) >> 16;
-                        const int kx = k - ky * kLkWin;
-                        const uint8_t* q = Jw + ky * cols + kx;
-                        const int jv = (q[0] * v00 + q[1] * v01 + q[cols] * v10 + q[cols + 1] * v11 + (1 << 8)) >> 9;
-                        const int diff = jv - Iw[s];
-                        sb1 += diff * Ix[s];
-                        sb2 += diff * Iy[s];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int s = 0; s < kStrides; ++s) {
-                    const int k = lane + 32 * s;
-                    if (k < kPix) {
-                        const int ky = (k * 3121) >> 16;
-                        const int kx = k - ky * kLkWin;
-                        const int y0 = clamp_reflect(jy + ky, rows), y1 = clamp_reflect(jy + ky + 1, rows);
-                        const int x0 = clamp_reflect(jx + kx, cols), x1 = clamp_reflect(jx + kx + 1, cols);
-                        const int jv = (J[(size_t)y0 * cols + x0] * v00 + J[(size_t)y0 * cols + x1] * v01 +
-                                        J[(size_t)y1 * cols + x0] * v10 + J[(size_t)y1 * cols + x1] * v11 + (1 << 8)) >> 9;
-                        const int diff = jv - Iw[s];
-                        sb1 += diff * Ix[s];
-                        sb2 += diff * Iy[s];
-                    }
+            for (int s = 0; s < kStrides; ++s) {
+                if (lane + 32 * s < kPix) {
+                    const uint8_t* q = J + (o0 + koff[s]);
+                    const int jv = (q[0] * v00 + q[1] * v01 + q[P] * v10 + q[P + 1] * v11 + (1 << 8)) >> 9;
+                    const int diff = jv - Iw[s];
+                    sb1 += diff * Ix[s];
+                    sb2 += diff * Iy[s];
                 }
             }
-            const long long t1 = warp_sum_ll((long long)sb1);
-            const long long t2 = warp_sum_ll((long long)sb2);
-            const float b1 = __fmul_rn((float)t1, kFltScale);
-            const float b2 = __fmul_rn((float)t2, kFltScale);
+            const float b1 = __fmul_rn((float)warp_sum_i32(sb1), kFltScale);
+            const float b2 = __fmul_rn((float)warp_sum_i32(sb2), kFltScale);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
