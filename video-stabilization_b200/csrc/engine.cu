@@ -220,7 +220,7 @@ static vstab_status stream_process(vstab* s, uint8_t* d_out, size_t out_pitch) {
     launch_pyramid(g.pd, s->pyr(cur), 1, q);
     if (n == 0) {                                                                                      // :1178-1182
         launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                    s->corners(cur), ccount + cur, q);
+                    s->corners(cur), ccount + cur, s->gws.eig, q);
         CK(cudaGetLastError());
         s->last_presented = 0;
         return VSTAB_OK;
@@ -250,7 +250,7 @@ static vstab_status stream_process(vstab* s, uint8_t* d_out, size_t out_pitch) {
     launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
                 d_out, out_pitch, 0, q);                                                               // :1309-1313
     launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                s->corners(cur), ccount + cur, q);                                                     // :1318
+                s->corners(cur), ccount + cur, s->gws.eig, q);                                         // :1318
     CK(cudaGetLastError());
     s->last_presented = p;
     return VSTAB_OK;
@@ -575,7 +575,7 @@ extern "C" vstab_status vstab_offline_estimate(vstab_offline_t* o, const uint8_t
     if (npairs > 0) {
         o->timer.begin(ST_GFTT, q);
         launch_gftt(pyr + (size_t)s0 * g.pd.frame_bytes, g.pd.frame_bytes, g.ww, g.wh, npairs, 0.01, g.min_distance,
-                    kMaxCorners, o->gws, corners, ccount, q);
+                    kMaxCorners, o->gws, corners, ccount, nullptr, q);
         o->timer.end(ST_GFTT, q);
         o->timer.begin(ST_LK, q);
         launch_lk(pyr + (size_t)s0 * g.pd.frame_bytes, pyr + (size_t)(s0 + 1) * g.pd.frame_bytes, g.pd.frame_bytes,
@@ -779,7 +779,7 @@ extern "C" vstab_status vstab_k_gftt(int device, const uint8_t* gray, int rows, 
     gftt_bind_workspace(mem.p, &ws);
     CK(cudaMemcpy(img.p, gray, (size_t)rows * cols, cudaMemcpyHostToDevice));
     launch_gftt(img.as<uint8_t>(), 0, cols, rows, 1, quality, min_distance, max_corners, ws, pts.as<float2>(),
-                cnt.as<int>(), 0);
+                cnt.as<int>(), ws.eig, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(n_out, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(pts_out, pts.p, sizeof(float2) * (*n_out), cudaMemcpyDeviceToHost));

@@ -33,24 +33,25 @@ void launch_pyramid(const PyrDesc& d, uint8_t* pyr, int nframes, cudaStream_t st
 
 // ---------------------------------------------------------------- K3 GFTT
 struct GfttWorkspace {
-    float* eig;                    // [nframes][w*h]
+    float* eig;                    // [w*h]  one frame, written only when a parity tap asks for it
     unsigned int* maxbits;         // [nframes]
     unsigned long long* keys;      // [nframes][cap]
     unsigned long long* keys_alt;  // [nframes][cap]   (sort double buffer)
     int* seg_begin;                // [nframes]  = f*cap
     int* seg_end;                  // [nframes]  = f*cap + count (atomic counter)
-    unsigned int* grid;            // [nframes][ncells*4]
+    unsigned short* grid;          // [nframes][ncells*4] global fallback when the grid does not fit in smem
     void* cub_temp;
     size_t cub_temp_bytes;
     int cap;                       // candidate capacity per frame
     int ncells, grid_w, grid_h, cell;
+    int grid_in_smem;
     int max_frames;
 };
 size_t gftt_workspace_bytes(int w, int h, int min_distance, int max_frames, GfttWorkspace* layout);
 void gftt_bind_workspace(void* base, GfttWorkspace* ws);     // base: cudaMalloc'ed block
 void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, int nframes,
                  double quality, int min_distance, int max_corners, GfttWorkspace& ws,
-                 float2* pts, int* counts, cudaStream_t st);
+                 float2* pts, int* counts, float* eig_out /* [nframes][w*h] or null */, cudaStream_t st);
 
 // ---------------------------------------------------------------- K4 sparse pyramidal LK
 void launch_lk(const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_stride, size_t next_stride,
