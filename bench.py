@@ -43,6 +43,11 @@ LOCK_CALL = 46                   # setStabilizationMode(ACCUMULATED_FULL_LOCK) i
 METRIC = "stabilized_frames_per_sec_1080p_lk_full_lock"
 UNIT = "frames/s"
 WORKLOAD = "c2_lk_full_lock_1080p_wh360_window60_45"
+# Scripted camera path of SURVEY.md 8d (jitter sigma 0.004 world units ~ 8.6 px at 1080p, +-107 px
+# sinusoid, +-3 deg roll) WITHOUT its steady x drift: a full lock on a drifting camera leaves the
+# anchor frame after ~500 frames and the output (and the warp's source traffic) degenerates to the
+# border colour, which would flatter the warp stage.  Both arms use this same path.
+PATH_DRIFT = 0.0
 
 
 def working_width():
@@ -135,7 +140,7 @@ def _render_one(args):
     from vstab_b200 import synth
     i, n = args
     tex = synth.make_texture(2048)
-    return ce.render_frame(tex, synth.camera_path(n)[i], W, H, synth.focal_for_width(W))
+    return ce.render_frame(tex, synth.camera_path(n, drift=PATH_DRIFT)[i], W, H, synth.focal_for_width(W))
 
 
 def cpu_frames(n):
@@ -202,7 +207,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST, "future": FUTURE,
-                   "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL, "frames_per_step": per_step},
+                   "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL, "frames_per_step": per_step,
+                   "camera_path": "survey 8d jitter+sinusoid+roll, drift 0"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -245,7 +251,7 @@ def run_ours(args):
 
     # ---- synthetic clip, rendered on the device (K13), shard [first-1, last) ------------------------
     tex = torch.from_numpy(synth.make_texture(2048)).to(dev)
-    path = synth.camera_path(n_total)
+    path = synth.camera_path(n_total, drift=PATH_DRIFT)
     has_halo = first > 0
     buf = torch.empty((n_local + 1, H, W, 3), dtype=torch.uint8, device=dev)
     lo = first - 1 if has_halo else first
@@ -355,6 +361,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST,
                        "future": FUTURE, "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL,
                        "frames_per_gpu": n_local, "frames_total": n_total, "batch": args.batch,
+                       "camera_path": "survey 8d jitter+sinusoid+roll, drift 0",
                        "l2_policy": f"inputs_exceed_l2 ({n_local * 3 * W * H / 1e6:.0f} MB of frames per GPU per step vs 126 MB L2)",
                        "parallelism": f"frame-sharded x{world}, one all-gather of 72 B/frame" if world > 1 else "single GPU"},
             "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu, "e2e": e2e,
@@ -368,19 +375,48 @@ def run_ours(args):
 
 
 def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
-    """Host-buffer path: vstab_stabilize_frame (the reference-facing call, include/vstab.h) fed from
-    pinned host memory, output read back to pinned host memory, every call synchronous."""
-    n_host = min(args.e2e_distinct_frames, frames.shape[0])
+    """Host-buffer paths through the C ABI (include/vstab.h), pinned host memory, copies inside the
+    timed region:
+      * headline `value`: vstab_offline_run_host -- a whole clip of host frames in, stabilized host
+        frames out (the reference's --file mode), uploads / compute / downloads pipelined;
+      * `streaming`: vstab_stabilize_frame -- the reference's per-frame call, synchronous per frame."""
+    from vstab_b200 import offline
     nbytes = H * W * 3
+    n_clip = min(args.e2e_frames_per_step, frames.shape[0])
     lib.vstab_host_alloc.restype = C.c_void_p
-    hin = lib.vstab_host_alloc(n_host * nbytes)
-    hout = lib.vstab_host_alloc(nbytes)
+    hin = lib.vstab_host_alloc(n_clip * nbytes)
+    hout = lib.vstab_host_alloc(n_clip * nbytes)
     if not hin or not hout:
         raise SystemExit("pinned host allocation failed")
-    hin_np = np.ctypeslib.as_array((C.c_uint8 * (n_host * nbytes)).from_address(hin)).reshape(n_host, H, W, 3)
-    hin_np[:] = frames[:n_host].cpu().numpy()
+    hin_np = np.ctypeslib.as_array((C.c_uint8 * (n_clip * nbytes)).from_address(hin)).reshape(n_clip, H, W, 3)
+    hin_np[:] = frames[:n_clip].cpu().numpy()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(dt):
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return dt
+
+    # ---- whole clip, pipelined (each rank stabilizes its own clip: replicas, no collective) --------
+    off = offline.OfflineStabilizer(PAST, FUTURE, WH, H, W, args.e2e_batch, device=local)
+    for _ in range(2):
+        off.run_host(hin, nbytes, W * 3, n_clip, vs.ACCUMULATED_FULL_LOCK, LOCK_CALL, hout, nbytes, W * 3)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        off.run_host(hin, nbytes, W * 3, n_clip, vs.ACCUMULATED_FULL_LOCK, LOCK_CALL, hout, nbytes, W * 3)
+    dt_clip = max_over_ranks(time.perf_counter() - t0)
+    off.close()
+
+    # ---- streaming, one synchronous call per frame --------------------------------------------------
     st = vs.Stabilizer(PAST, FUTURE, WH, device=local)
-    per_step = args.e2e_frames_per_step
+    per_step = args.e2e_stream_frames
     i = 0
 
     def run(n):
@@ -388,29 +424,27 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
         for _ in range(n):
             if i == LOCK_CALL:
                 st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
-            st.stabilize_frame_ptr(hin + pingpong(i, n_host) * nbytes, H, W, W * 3, hout, W * 3)
+            st.stabilize_frame_ptr(hin + pingpong(i, n_clip) * nbytes, H, W, W * 3, hout, W * 3)
             i += 1
 
     run(max(per_step, LOCK_CALL + 4))     # warm-up incl. the mode switch
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         run(per_step)
     st.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt_stream = max_over_ranks(time.perf_counter() - t0)
     st.close()
     lib.vstab_host_free(C.c_void_p(hin))
     lib.vstab_host_free(C.c_void_p(hout))
-    return {"value": world * per_step * args.steps / dt, "unit": UNIT,
-            "h2d_bytes_per_step": per_step * nbytes, "d2h_bytes_per_step": per_step * nbytes,
-            "api": "vstab_stabilize_frame (streaming, synchronous per frame, pinned host buffers)",
-            "frames_per_step": per_step, "timer": "host wall clock around synchronous calls, max over ranks"}
+    return {"value": world * n_clip * args.steps / dt_clip, "unit": UNIT,
+            "h2d_bytes_per_step": n_clip * nbytes, "d2h_bytes_per_step": n_clip * nbytes,
+            "api": "vstab_offline_run_host (whole clip of pinned host frames in/out, pipelined H2D / compute / D2H)",
+            "frames_per_step": n_clip, "timer": "host wall clock around the synchronous call, max over ranks",
+            "streaming": {"value": world * per_step * args.steps / dt_stream, "unit": UNIT,
+                          "api": "vstab_stabilize_frame (the reference's per-frame call; synchronous, pinned host buffers)",
+                          "frames_per_step": per_step, "h2d_bytes_per_step": per_step * nbytes,
+                          "d2h_bytes_per_step": per_step * nbytes}}
 
 
 def main():
@@ -421,8 +455,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=512)
     ap.add_argument("--batch", type=int, default=128, help="frames per kernel launch (offline batch)")
-    ap.add_argument("--e2e-frames-per-step", type=int, default=128)
-    ap.add_argument("--e2e-distinct-frames", type=int, default=96)
+    ap.add_argument("--e2e-frames-per-step", type=int, default=256, help="frames of the host clip (one step = one clip)")
+    ap.add_argument("--e2e-batch", type=int, default=32, help="chunk size of the host-clip pipeline")
+    ap.add_argument("--e2e-stream-frames", type=int, default=128, help="streaming calls per step")
     ap.add_argument("--cpu-distinct-frames", type=int, default=48)
     ap.add_argument("--cpu-sample-frames", type=int, default=400)
     ap.add_argument("--cpu-frames-per-step", type=int, default=100)

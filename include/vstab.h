@@ -171,6 +171,15 @@ vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* d_frames, s
  * (src/stabilizer.cpp:317-338).  Must precede vstab_offline_render in that mode. */
 vstab_status vstab_offline_prepare(vstab_offline_t* o, const double* d_T_all, long n_total, int mode,
                                    long lock_call);
+/* Whole-clip stabilization with HOST buffers on one GPU (the reference's --file input,
+ * src/main_utils.cpp:397-417 feeding stabilizeFrame at :465): `frames` holds n_total BGR frames
+ * `frame_stride` bytes apart, `out` receives the outputs of stabilizeFrame calls 0..n_total-1.
+ * Uploads, estimation, warping and downloads are pipelined over chunks of max_batch frames on
+ * three streams; every frame crosses PCIe once per direction.  Use pinned buffers
+ * (vstab_host_alloc) for asynchronous copies.  Synchronous: returns when `out` is complete. */
+vstab_status vstab_offline_run_host(vstab_offline_t* o, const uint8_t* frames, size_t frame_stride,
+                                    size_t step, long n_total, int mode, long lock_call,
+                                    uint8_t* out, size_t out_frame_stride, size_t out_step);
 vstab_status vstab_offline_synchronize(vstab_offline_t* o);
 /* per-stage device time (CUDA events on the instance stream) accumulated since the last call:
  * ms[8]/counts[8] = ingest, pyramid, gftt, lk, fit, smooth, warp, acc-scan */

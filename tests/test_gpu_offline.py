@@ -112,3 +112,23 @@ def test_offline_equals_streaming(texture_small, lock_at, shards):
             continue
         assert np.array_equal(got_H[c], want_H[c]), c      # same kernels, same order: bit-identical H
         assert np.array_equal(got[c], want[c]), c
+
+
+@pytest.mark.parametrize("lock_at", [None, 9])
+def test_run_host_equals_streaming(texture_small, lock_at):
+    """vstab_offline_run_host (pipelined uploads / estimation / warps / downloads over host buffers)
+    returns exactly the frames the streaming calls return."""
+    W, H, wh, P, F = 480, 270, 135, 6, 4
+    frames, _ = _dev_clip(texture_small, W, H, 30)
+    f_np = np.ascontiguousarray(frames.cpu().numpy())
+    want, _ = _streaming(f_np, P, F, wh, lock_at)
+    mode = vs.GLOBAL_SMOOTHING if lock_at is None else vs.ACCUMULATED_FULL_LOCK
+    out = np.zeros_like(f_np)
+    off = offline.OfflineStabilizer(P, F, wh, H, W, 7)
+    for _ in range(2):                    # second run reuses the instance's device clip buffers
+        off.run_host(f_np.ctypes.data, f_np.strides[0], f_np.strides[1], 30, mode, lock_at or 0,
+                     out.ctypes.data, out.strides[0], out.strides[1])
+        for c in range(30):
+            assert np.array_equal(out[c], want[c]), c
+        out[:] = 0
+    off.close()

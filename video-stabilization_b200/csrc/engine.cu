@@ -149,7 +149,11 @@ bool device_ok(int device, std::string& err) {
 // =====================================================================================
 struct vstab {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // estimation stream: ingest -> pyramid -> LK -> fit -> corner detection
+    cudaStream_t out_stream = nullptr;   // output stream: smoothing / lock -> warp -> device-to-host copy
+    cudaEvent_t ev_in = nullptr;         // input frame is in the ring (caller may reuse its buffer)
+    cudaEvent_t ev_fit = nullptr;        // T[n] and the channel sums of frame n are final
+    cudaEvent_t ev_out = nullptr;        // output chain of the previous call has finished reading the ring
     size_t P = 15, F = 15;
     int working_height = 360;
     int mode = VSTAB_GLOBAL_SMOOTHING;
@@ -202,9 +206,16 @@ static vstab_status stream_init(vstab* s, int rows, int cols) {
     return VSTAB_OK;
 }
 
-// Enqueue the whole per-frame pipeline for frame index s->n whose pixels are already in
-// ring slot n % W.  `d_out`/`out_pitch`: where the warped presentation frame goes.
-static vstab_status stream_process(vstab* s, uint8_t* d_out, size_t out_pitch) {
+// A streaming call is two independent chains (with future >= 1 the output of
+// call n depends only on transforms up to n-1, because the reference's window average excludes the
+// newest transform, stabilizer.cpp:825-826, and ACCUMULATED lock uses T[n-F]):
+//   estimation (s->stream):  frame n -> ingest -> pyramid -> LK against frame n-1 -> fit T[n] -> corners
+//   output (s->out_stream):  [wait T[n-1]] -> lock / window average -> warp of frame n-F -> copy out
+// so the host only waits for the output chain and the upload; the estimation of frame n overlaps
+// the copy-out and the next call.  With future == 0 the output chain waits for T[n] of this call.
+
+// Estimation chain for frame index s->n whose pixels are (being) written to ring slot n % W on s->stream.
+static vstab_status stream_estimate(vstab* s) {
     auto set_err = [&](const std::string& e) { s->err = e; };
     Geometry& g = s->g;
     cudaStream_t q = s->stream;
@@ -214,24 +225,32 @@ static vstab_status stream_process(vstab* s, uint8_t* d_out, size_t out_pitch) {
     const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)slot * g.frame_bytes;
     unsigned long long* sums = s->sums.as<unsigned long long>() + slot * 3;
     int* ccount = s->ccount.as<int>();
-
     CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3, q));
     launch_ingest(g.plan, frame, g.pitch, g.frame_bytes, 1, s->pyr(cur), g.pd.frame_bytes, sums, q);   // :1169-1175
     launch_pyramid(g.pd, s->pyr(cur), 1, q);
-    if (n == 0) {                                                                                      // :1178-1182
-        launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                    s->corners(cur), ccount + cur, s->gws.eig, q);
-        CK(cudaGetLastError());
-        s->last_presented = 0;
-        return VSTAB_OK;
+    if (n > 0) {
+        // :1187 trackFeatures
+        launch_lk(s->pyr(prev), s->pyr(cur), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
+                  s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), q);
+        // :1203 estimateMotion, :1209 updateTransformations
+        launch_fit(s->corners(prev), s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), ccount + prev, 1, 3.0,
+                   g.ww / 2.0, g.wh / 2.0, s->T.as<double>() + (size_t)(n % s->t_mod) * 9, s->Mtap.as<double>(),
+                   s->fitc.as<int>(), nullptr, n, q);
     }
-    // :1187 trackFeatures
-    launch_lk(s->pyr(prev), s->pyr(cur), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
-              s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), q);
-    // :1203 estimateMotion, :1209 updateTransformations
-    launch_fit(s->corners(prev), s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), ccount + prev, 1, 3.0,
-               g.ww / 2.0, g.wh / 2.0, s->T.as<double>() + (size_t)(n % s->t_mod) * 9, s->Mtap.as<double>(),
-               s->fitc.as<int>(), nullptr, n, q);
+    CK(cudaEventRecord(s->ev_fit, q));
+    launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
+                s->corners(cur), ccount + cur, s->gws.eig, q);                                         // :1318 / :1179
+    CK(cudaGetLastError());
+    return VSTAB_OK;
+}
+
+// Output chain of call s->n (n >= 1) on s->out_stream; `d_out`/`out_pitch`: where the warped
+// presentation frame goes.  The caller has already made out_stream wait for the transforms it needs.
+static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    Geometry& g = s->g;
+    cudaStream_t q = s->out_stream;
+    const long n = s->n;
     const long p = n - (long)s->F > 0 ? n - (long)s->F : 0;                                            // :1226-1229
     if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) {                                                      // :317-338
         launch_acc_update(s->T.as<double>(), s->t_mod, p, s->acc_valid ? 0 : 1, s->acc.as<double>(), q);
@@ -249,10 +268,57 @@ static vstab_status stream_process(vstab* s, uint8_t* d_out, size_t out_pitch) {
     launch_smooth(a, n, 1, s->wp.as<WarpParams>(), q);                                                 // :1234-1296
     launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
                 d_out, out_pitch, 0, q);                                                               // :1309-1313
-    launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                s->corners(cur), ccount + cur, s->gws.eig, q);                                         // :1318
     CK(cudaGetLastError());
     s->last_presented = p;
+    return VSTAB_OK;
+}
+
+// One stabilizeFrame call; `kind` selects how frame pixels move (host<->device or device<->device).
+static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols, size_t step, uint8_t* out,
+                                size_t out_step, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind, bool host_wait) {
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    Geometry& g = s->g;
+    uint8_t* slot = s->ring.as<uint8_t>() + (size_t)(s->n % s->W) * g.frame_bytes;
+    const size_t row_bytes = (size_t)cols * 3;
+    const bool device_out = out_kind == cudaMemcpyDeviceToDevice;
+    uint8_t* warp_dst = device_out ? out : s->dout.as<uint8_t>();
+    const size_t warp_pitch = device_out ? out_step : g.pitch;
+    const bool out_first = s->n > 0 && s->F >= 1;      // output chain does not need this call's transform
+
+    if (out_first) {
+        CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));          // T[n-1], sums of frames <= n-1
+        vstab_status st = stream_output(s, warp_dst, warp_pitch);
+        if (st != VSTAB_OK) return st;
+        if (!device_out)
+            CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
+    }
+    // estimation chain.  The ring slot being overwritten held frame n-W; its readers (the warp and the
+    // channel sums of an earlier call's output chain) are ordered before this copy by ev_out.
+    if (s->n > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_out, 0));
+    CK(cudaMemcpy2DAsync(slot, g.pitch, in, step, row_bytes, rows, in_kind, s->stream));
+    CK(cudaEventRecord(s->ev_in, s->stream));
+    vstab_status st = stream_estimate(s);
+    if (st != VSTAB_OK) return st;
+    if (!out_first) {
+        if (s->n == 0) {
+            // call 0 returns the input frame itself (:1181)
+            CK(cudaStreamWaitEvent(s->out_stream, s->ev_in, 0));
+            CK(cudaMemcpy2DAsync(out, out_step, slot, g.pitch, row_bytes, rows, out_kind, s->out_stream));
+            s->last_presented = 0;
+        } else {
+            CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));      // future == 0: needs T[n] of this call
+            st = stream_output(s, warp_dst, warp_pitch);
+            if (st != VSTAB_OK) return st;
+            if (!device_out)
+                CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
+        }
+    }
+    CK(cudaEventRecord(s->ev_out, s->out_stream));
+    if (host_wait) {
+        CK(cudaEventSynchronize(s->ev_in));                            // caller may reuse `in` (the reference clones, :160)
+        CK(cudaStreamSynchronize(s->out_stream));                      // `out` is complete
+    }
+    s->n += 1;
     return VSTAB_OK;
 }
 
@@ -308,8 +374,12 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
     vstab* s = new (std::nothrow) vstab();
     if (!s) return VSTAB_ERR_CUDA;
     s->device = device; s->P = past_frames; s->F = future_frames; s->working_height = working_height;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        g_err = "cudaStreamCreate failed"; delete s; return VSTAB_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->out_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        g_err = "cudaStreamCreate failed"; vstab_destroy(s); return VSTAB_ERR_CUDA;
     }
     *out = s;
     return VSTAB_OK;
@@ -319,6 +389,10 @@ void vstab_destroy(vstab_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    if (s->out_stream) { cudaStreamSynchronize(s->out_stream); cudaStreamDestroy(s->out_stream); }
+    if (s->ev_in) cudaEventDestroy(s->ev_in);
+    if (s->ev_fit) cudaEventDestroy(s->ev_fit);
+    if (s->ev_out) cudaEventDestroy(s->ev_out);
     delete s;
 }
 
@@ -346,6 +420,7 @@ vstab_status vstab_synchronize(vstab_t* s) {
     auto set_err = [&](const std::string& e) { s->err = e; };
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
+    CK(cudaStreamSynchronize(s->out_stream));
     return VSTAB_OK;
 }
 
@@ -356,20 +431,7 @@ vstab_status vstab_stabilize_frame(vstab_t* s, const uint8_t* bgr, int rows, int
     auto set_err = [&](const std::string& e) { s->err = e; };
     CK(cudaSetDevice(s->device));
     if (!s->inited) { st = stream_init(s, rows, cols); if (st != VSTAB_OK) return st; }
-    Geometry& g = s->g;
-    uint8_t* slot = s->ring.as<uint8_t>() + (size_t)(s->n % s->W) * g.frame_bytes;
-    CK(cudaMemcpy2DAsync(slot, g.pitch, bgr, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice, s->stream));
-    st = stream_process(s, s->dout.as<uint8_t>(), g.pitch);
-    if (st != VSTAB_OK) return st;
-    if (s->n == 0) {
-        // call 0 returns the input frame itself (:1181)
-        CK(cudaMemcpy2DAsync(out_bgr, out_step, slot, g.pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost, s->stream));
-    } else {
-        CK(cudaMemcpy2DAsync(out_bgr, out_step, s->dout.p, g.pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost, s->stream));
-    }
-    CK(cudaStreamSynchronize(s->stream));
-    s->n += 1;
-    return VSTAB_OK;
+    return stream_call(s, bgr, rows, cols, step, out_bgr, out_step, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, true);
 }
 
 vstab_status vstab_stabilize_frame_device(vstab_t* s, const uint8_t* d_bgr, int rows, int cols, size_t step,
@@ -379,15 +441,8 @@ vstab_status vstab_stabilize_frame_device(vstab_t* s, const uint8_t* d_bgr, int 
     auto set_err = [&](const std::string& e) { s->err = e; };
     CK(cudaSetDevice(s->device));
     if (!s->inited) { st = stream_init(s, rows, cols); if (st != VSTAB_OK) return st; }
-    Geometry& g = s->g;
-    uint8_t* slot = s->ring.as<uint8_t>() + (size_t)(s->n % s->W) * g.frame_bytes;
-    CK(cudaMemcpy2DAsync(slot, g.pitch, d_bgr, step, (size_t)cols * 3, rows, cudaMemcpyDeviceToDevice, s->stream));
-    st = stream_process(s, d_out_bgr, out_step);
-    if (st != VSTAB_OK) return st;
-    if (s->n == 0)
-        CK(cudaMemcpy2DAsync(d_out_bgr, out_step, slot, g.pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToDevice, s->stream));
-    s->n += 1;
-    return VSTAB_OK;
+    return stream_call(s, d_bgr, rows, cols, step, d_out_bgr, out_step, cudaMemcpyDeviceToDevice,
+                       cudaMemcpyDeviceToDevice, false);
 }
 
 int vstab_decompose_homography(const double H[9], double cx, double cy, vstab_hparams* out) {
@@ -424,6 +479,7 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
     if (!s || !s->inited || !dst || s->n == 0) return -1;
     if (cudaSetDevice(s->device) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s->out_stream) != cudaSuccess) return -1;
     Geometry& g = s->g;
     const long last = s->n - 1;                 // index of the most recent frame
     const int cur = (int)(last & 1), prev = cur ^ 1;
@@ -475,6 +531,10 @@ struct vstab_offline {
     const double* acc_T = nullptr;
     int last_ncalls = 0;
     StageTimer timer;
+    // host-clip runner (vstab_offline_run_host): device-resident clip, double-buffered output chunks
+    DevBuf clip, outbuf, clipT, clipSums;
+    size_t clip_frames = 0;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::string err;
     void set_err(const std::string& e) { err = e; }
 };
@@ -519,6 +579,8 @@ void vstab_offline_destroy(vstab_offline_t* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->stream) { cudaStreamSynchronize(o->stream); cudaStreamDestroy(o->stream); }
+    if (o->copy_in) { cudaStreamSynchronize(o->copy_in); cudaStreamDestroy(o->copy_in); }
+    if (o->copy_out) { cudaStreamSynchronize(o->copy_out); cudaStreamDestroy(o->copy_out); }
     delete o;
 }
 
@@ -661,6 +723,87 @@ extern "C" vstab_status vstab_offline_prepare(vstab_offline_t* o, const double* 
     CK(cudaGetLastError());
     o->acc_T = d_T_all; o->acc_n_total = n_total; o->acc_anchor = anchor;
     return VSTAB_OK;
+}
+
+// Whole-clip stabilization with HOST buffers on one GPU (the reference's --file mode: decoded
+// frames in host memory in, stabilized frames out).  Produces the outputs of stabilizeFrame calls
+// 0..n_total-1 (call c presents frame max(0, c - future)).  Two pipelined phases over chunks of
+// max_batch frames:
+//   1. upload chunk k+1 (copy-in stream)  ||  estimate chunk k (instance stream)
+//   2. smooth + warp chunk k (instance stream)  ||  download chunk k-1 (copy-out stream)
+// Every frame crosses PCIe exactly once in each direction; the clip stays resident in HBM between
+// the phases (6.2 MB per 1080p frame: ~29 k frames fit in 180 GB).
+extern "C" vstab_status vstab_offline_run_host(vstab_offline_t* o, const uint8_t* frames, size_t frame_stride, size_t step,
+                                                long n_total, int mode, long lock_call, uint8_t* out,
+                                                size_t out_frame_stride, size_t out_step) {
+    if (!o || !frames || !out || n_total < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    Geometry& g = o->g;
+    const size_t row_bytes = (size_t)g.cols * 3;
+    if (step < row_bytes || out_step < row_bytes) { o->err = "row step smaller than 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    CK(cudaSetDevice(o->device));
+    if (!o->copy_in) CK(cudaStreamCreateWithFlags(&o->copy_in, cudaStreamNonBlocking));
+    if (!o->copy_out) CK(cudaStreamCreateWithFlags(&o->copy_out, cudaStreamNonBlocking));
+    const int B = o->max_batch;
+    if (o->clip_frames < (size_t)n_total) {
+        CK(o->clip.alloc(g.frame_bytes * (size_t)n_total + 64));
+        CK(o->outbuf.alloc(g.frame_bytes * (size_t)B * 2 + 64));
+        CK(o->clipT.alloc(sizeof(double) * 9 * (size_t)n_total));
+        CK(o->clipSums.alloc(sizeof(unsigned long long) * 3 * (size_t)n_total));
+        o->clip_frames = (size_t)n_total;
+    }
+    uint8_t* clip = o->clip.as<uint8_t>();
+    double* T = o->clipT.as<double>();
+    unsigned long long* sums = o->clipSums.as<unsigned long long>();
+    const long nchunks = (n_total + B - 1) / B;
+    std::vector<cudaEvent_t> ev((size_t)nchunks * 3, nullptr);
+    auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); };
+    for (auto& e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cleanup(); o->err = "cudaEventCreate failed"; return VSTAB_ERR_CUDA; }
+    cudaEvent_t* ev_up = ev.data();                 // chunk k uploaded
+    cudaEvent_t* ev_rd = ev.data() + nchunks;       // chunk k rendered
+    cudaEvent_t* ev_dn = ev.data() + 2 * nchunks;   // chunk k downloaded
+    vstab_status st = VSTAB_OK;
+    // ---- phase 1: upload + estimate -----------------------------------------------------------
+    for (long k = 0; k < nchunks && st == VSTAB_OK; ++k) {
+        const long f0 = k * B, n = (n_total - f0 < B) ? n_total - f0 : B;
+        // one 2-D copy per chunk: rows of all frames of the chunk are `step` apart only inside a frame,
+        // so copy frame by frame (fewer, larger copies than per row; no batched-memcpy API)
+        for (long i = 0; i < n; ++i)
+            if (cudaMemcpy2DAsync(clip + (size_t)(f0 + i) * g.frame_bytes, g.pitch, frames + (size_t)(f0 + i) * frame_stride,
+                                  step, row_bytes, g.rows, cudaMemcpyHostToDevice, o->copy_in) != cudaSuccess) {
+                o->err = "upload failed"; st = VSTAB_ERR_CUDA; break;
+            }
+        if (st != VSTAB_OK) break;
+        cudaEventRecord(ev_up[k], o->copy_in);
+        cudaStreamWaitEvent(o->stream, ev_up[k], 0);
+        st = vstab_offline_estimate(o, clip + (size_t)f0 * g.frame_bytes, g.frame_bytes, g.pitch, (int)n, f0,
+                                    f0 > 0 ? clip + (size_t)(f0 - 1) * g.frame_bytes : nullptr, T + (size_t)f0 * 9,
+                                    sums + (size_t)f0 * 3);
+    }
+    // ---- phase 2: smooth + warp + download ------------------------------------------------------
+    if (st == VSTAB_OK) st = vstab_offline_prepare(o, T, n_total, mode, lock_call);
+    for (long k = 0; k < nchunks && st == VSTAB_OK; ++k) {
+        const long c0 = k * B, n = (n_total - c0 < B) ? n_total - c0 : B;
+        uint8_t* ob = o->outbuf.as<uint8_t>() + (size_t)(k & 1) * B * g.frame_bytes;
+        if (k >= 2) cudaStreamWaitEvent(o->stream, ev_dn[k - 2], 0);      // output half is free again
+        st = vstab_offline_render(o, clip, g.frame_bytes, g.pitch, 0, (int)n, c0, T, n_total, mode, lock_call, sums, ob,
+                                  g.frame_bytes, g.pitch);
+        if (st != VSTAB_OK) break;
+        cudaEventRecord(ev_rd[k], o->stream);
+        cudaStreamWaitEvent(o->copy_out, ev_rd[k], 0);
+        for (long i = 0; i < n; ++i)
+            if (cudaMemcpy2DAsync(out + (size_t)(c0 + i) * out_frame_stride, out_step, ob + (size_t)i * g.frame_bytes, g.pitch,
+                                  row_bytes, g.rows, cudaMemcpyDeviceToHost, o->copy_out) != cudaSuccess) {
+                o->err = "download failed"; st = VSTAB_ERR_CUDA; break;
+            }
+        cudaEventRecord(ev_dn[k], o->copy_out);
+    }
+    cudaStreamSynchronize(o->copy_in);
+    cudaStreamSynchronize(o->stream);
+    cudaStreamSynchronize(o->copy_out);
+    cleanup();
+    if (st == VSTAB_OK && cudaGetLastError() != cudaSuccess) { o->err = "CUDA failure in vstab_offline_run_host"; st = VSTAB_ERR_CUDA; }
+    return st;
 }
 
 extern "C" void vstab_offline_set_timing(vstab_offline_t* o, int enable) { if (o) o->timer.enabled = enable != 0; }

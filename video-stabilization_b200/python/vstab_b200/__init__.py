@@ -67,6 +67,8 @@ SYMBOLS = {
     "vstab_offline_estimate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, C.c_long, _vp, _vp, _vp]),
     "vstab_offline_render": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_long, C.c_int, C.c_long, _vp, C.c_long,
                                        C.c_int, C.c_long, _vp, _vp, C.c_size_t, C.c_size_t]),
+    "vstab_offline_run_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_long, C.c_int, C.c_long, _vp, C.c_size_t,
+                                       C.c_size_t]),
     "vstab_offline_synchronize": (C.c_int, [_vp]),
     "vstab_offline_prepare": (C.c_int, [_vp, _vp, C.c_long, C.c_int, C.c_long]),
     "vstab_offline_set_timing": (None, [_vp, C.c_int]),

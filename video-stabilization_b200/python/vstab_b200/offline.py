@@ -118,6 +118,13 @@ class OfflineStabilizer:
                 _vp(out[done].data_ptr()), out.stride(0), out.stride(1)), self._h)
             done += m
 
+    def run_host(self, frames_ptr: int, frame_stride: int, step: int, n_total: int, mode: int, lock_call: int,
+                 out_ptr: int, out_frame_stride: int, out_step: int):
+        """Whole clip through host buffers (pointers to n_total frames in / out), pipelined uploads,
+        estimation, warps and downloads; returns when the output buffer is complete."""
+        _check(self._lib.vstab_offline_run_host(self._h, _vp(frames_ptr), frame_stride, step, n_total, mode, lock_call,
+                                                _vp(out_ptr), out_frame_stride, out_step), self._h)
+
     def read_h(self, ncalls: int):
         import numpy as np
         buf = np.zeros((ncalls, 9))

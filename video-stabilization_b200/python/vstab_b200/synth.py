@@ -108,12 +108,17 @@ def make_texture(size: int = 2048, seed: int = TEXTURE_SEED,
     return img
 
 
-def camera_path(n_frames: int, seed: int = PATH_SEED) -> np.ndarray:
+def camera_path(n_frames: int, seed: int = PATH_SEED, drift: float = 0.0015) -> np.ndarray:
     """Scripted pose per frame: columns (x, y, z, pan, tilt, roll) in the units
     of CameraParams (/root/reference/include/camera_engine.hpp:44-74).
 
     SURVEY.md §8d: x = 0.5+0.0015 i+N(0,0.004), y = -0.3+0.05 sin(i/40)+N(0,0.004),
     roll = 180+3 sin(i/55)+N(0,0.35 deg), z = 0.7, pan 0, tilt 180.
+
+    `drift` is the x velocity in world units per frame (0.0015 ~ 2.1 px/frame at 720p).  The
+    full-lock benchmark uses drift = 0 (a hand-held camera over a fixed scene): with a steady
+    drift a locked view leaves the anchor frame after a few hundred frames and the output
+    degenerates to the border colour.
     """
     rng = np.random.default_rng(seed)
     i = np.arange(n_frames, dtype=np.float64)
@@ -121,7 +126,7 @@ def camera_path(n_frames: int, seed: int = PATH_SEED) -> np.ndarray:
     jy = rng.normal(0.0, 0.004, n_frames)
     jr = rng.normal(0.0, 0.35, n_frames)
     out = np.empty((n_frames, 6), dtype=np.float64)
-    out[:, 0] = 0.5 + 0.0015 * i + jx
+    out[:, 0] = 0.5 + drift * i + jx
     out[:, 1] = -0.3 + 0.05 * np.sin(i / 40.0) + jy
     out[:, 2] = 0.7
     out[:, 3] = 0.0
