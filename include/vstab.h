@@ -216,6 +216,16 @@ vstab_status vstab_k_fit(int device, const float* prev_pts, const float* next_pt
 vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, int cols, size_t step,
                           const double H[9], const uint8_t border[3], uint8_t* out, size_t out_step);
 
+/* ORB / SIFT registration path (src/stabilizer.cpp:448-477 preprocessing, :483-491 + :605-606 ORB
+ * detectAndCompute, :647-673 Hamming 2-NN + ratio test).  kps_out: 6 floats per keypoint
+ * {x, y, size, angle, response, octave}, level-major then row-major; desc_out: 32 bytes each. */
+vstab_status vstab_k_featprep(int device, const uint8_t* bgr, int rows, int cols, size_t step,
+                              int working_height, uint8_t* gray_out);
+vstab_status vstab_k_orb(int device, const uint8_t* gray, int rows, int cols, double size_ratio,
+                         float* kps_out, uint8_t* desc_out, int* n_out, int max_out);
+vstab_status vstab_k_hamming(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur,
+                             float ratio, int* best_idx, int* best_d, int* second_d, uint8_t* good);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,95 @@
+"""K8-K10: the ORB registration path kernels against cv2 4.13.0 (bit-exact integer work):
+preprocessing chain, ORB keypoint set / angles / descriptors over all pyramid levels, Hamming
+2-NN match indices and the ratio test."""
+import cv2
+import numpy as np
+import pytest
+
+import vstab_b200 as vs
+from conftest import render_clip
+from oracle import stabilizer_ref as sr
+
+pytestmark = pytest.mark.gpu
+
+
+def _cv_prep(frame, wh):
+    o = sr.StabilizerRef(15, 15, wh)
+    o._initialize_frame(frame)
+    return o._preprocess_for_features(frame)
+
+
+@pytest.mark.parametrize("W,H,wh", [(1280, 720, 360), (1920, 1080, 1080), (1920, 1080, 360), (640, 360, 100), (333, 250, 97)])
+def test_featprep_bit_exact(texture, W, H, wh):
+    frame = render_clip(texture, W, H, 1, start=4)[0]
+    got = vs.k_featprep(frame, wh)
+    want = _cv_prep(frame, wh)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_featprep_noise_and_flat():
+    rng = np.random.default_rng(5)
+    for img in (rng.integers(0, 256, (360, 640, 3), dtype=np.uint8), np.full((360, 640, 3), 77, np.uint8),
+                np.zeros((360, 640, 3), np.uint8)):
+        assert np.array_equal(vs.k_featprep(img, 180), _cv_prep(img, 180))
+
+
+def _cv_orb(gray):
+    det = cv2.ORB_create(2500, 1.2, 12, 31, 0, 2, cv2.ORB_FAST_SCORE, 31, 20)
+    kps, desc = det.detectAndCompute(gray, None)
+    return kps, desc
+
+
+def _as_dict(kps, desc):
+    """keypoints keyed by (octave, rounded level coordinates): order independent comparison"""
+    return {(int(k[5]), round(float(k[0]), 3), round(float(k[1]), 3)): (float(k[2]), float(k[3]), float(k[4]), bytes(d))
+            for k, d in zip(kps, desc)}
+
+
+@pytest.mark.parametrize("W,H,wh", [(1280, 720, 360), (1920, 1080, 1080)])
+def test_orb_identical_keypoints_and_descriptors(texture, W, H, wh):
+    frame = render_clip(texture, W, H, 1, start=7)[0]
+    gray = _cv_prep(frame, wh)
+    kps, desc = vs.k_orb(gray)
+    ckps, cdesc = _cv_orb(gray)
+    want = {(k.octave, round(k.pt[0], 3), round(k.pt[1], 3)): (k.size, k.angle, k.response, bytes(d)) for k, d in zip(ckps, cdesc)}
+    got = _as_dict(kps, desc)
+    assert len(got) == len(kps)
+    assert set(got) == set(want)                               # identical FAST corner sets on every level
+    for key, (size, angle, resp, d) in want.items():
+        g = got[key]
+        assert g[0] == np.float32(size) and g[2] == resp
+        assert g[1] == np.float32(angle), (key, g[1], angle)   # fastAtan2 polynomial, bit-identical
+        assert g[3] == d, key                                  # 256-bit rBRIEF descriptor
+    # level-major, row-major order
+    order = [(int(k[5]), float(k[1]), float(k[0])) for k in kps]
+    assert order == sorted(order)
+
+
+def test_orb_size_filter_and_empty(texture):
+    frame = render_clip(texture, 1280, 720, 1, start=7)[0]
+    gray = _cv_prep(frame, 360)
+    kps, desc = vs.k_orb(gray, size_ratio=0.10)
+    ckps, cdesc = _cv_orb(gray)
+    ckps, cdesc = sr.filter_keypoints_by_relative_size(gray.shape[0], list(ckps), cdesc, 0.10)
+    assert len(kps) == len(ckps) and len(kps) > 100
+    assert set(map(bytes, desc)) == set(map(bytes, cdesc))
+    flat = np.full((360, 640), 90, np.uint8)
+    kps, desc = vs.k_orb(flat)
+    assert len(kps) == 0
+
+
+def test_hamming_knn_and_ratio(texture):
+    f0, f1 = render_clip(texture, 1280, 720, 2, start=9)
+    d0 = _cv_orb(_cv_prep(f0, 360))[1]
+    d1 = _cv_orb(_cv_prep(f1, 360))[1]
+    bi, bd, sd, good = vs.k_hamming(d0, d1, 0.6)
+    knn = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d0, d1, 2)
+    assert len(knn) == len(d0)
+    for q, pair in enumerate(knn):
+        assert pair[0].trainIdx == bi[q] and int(pair[0].distance) == bd[q] and int(pair[1].distance) == sd[q]
+        assert bool(good[q]) == bool(pair[0].distance < np.float32(0.6) * np.float32(pair[1].distance))
+    assert good.sum() > 50
+    # degenerate train sets
+    bi, bd, sd, good = vs.k_hamming(d0[:5], d1[:1], 0.6)
+    assert (good == 0).all() and (bi == 0).all()

@@ -996,3 +996,90 @@ extern "C" vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, i
     CK(cudaMemcpy2D(out, out_step, dst.p, pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost));
     return VSTAB_OK;
 }
+
+// ---- ORB / SIFT registration path: single-kernel entry points (host buffers) ------------------
+extern "C" vstab_status vstab_k_featprep(int device, const uint8_t* bgr, int rows, int cols, size_t step,
+                                         int working_height, uint8_t* gray_out) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!bgr || !gray_out) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    Geometry g;
+    vstab_status st = g.init(rows, cols, working_height, g_err);
+    if (st != VSTAB_OK) return st;
+    std::vector<int> xo(g.ww), yo(g.wh);
+    build_nn_table(cols, g.ww, xo.data());
+    build_nn_table(rows, g.wh, yo.data());
+    DevBuf frame, ws, out, dx, dy;
+    CK(frame.alloc(g.frame_bytes + 64));
+    CK(ws.alloc(featprep_workspace_bytes(g.ww, g.wh)));
+    CK(out.alloc((size_t)g.ww * g.wh));
+    CK(dx.alloc(sizeof(int) * g.ww)); CK(dy.alloc(sizeof(int) * g.wh));
+    CK(cudaMemcpy2D(frame.p, g.pitch, bgr, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dx.p, xo.data(), sizeof(int) * g.ww, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy.p, yo.data(), sizeof(int) * g.wh, cudaMemcpyHostToDevice));
+    launch_featprep(frame.as<uint8_t>(), g.pitch, dx.as<int>(), dy.as<int>(), g.ww, g.wh, ws.p, out.as<uint8_t>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(gray_out, out.p, (size_t)g.ww * g.wh, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_orb(int device, const uint8_t* gray, int rows, int cols, double size_ratio,
+                                    float* kps_out, uint8_t* desc_out, int* n_out, int max_out) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!gray || !kps_out || !desc_out || !n_out || max_out < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    OrbPlan* P = orb_plan_create(cols, rows, size_ratio, kOrbMaxKp, &g_err);
+    if (!P) return VSTAB_ERR_CUDA;
+    DevBuf img, kps, desc, cnt;
+    vstab_status st = VSTAB_OK;
+    auto fail = [&](const char* m) { g_err = m; st = VSTAB_ERR_CUDA; };
+    if (img.alloc((size_t)rows * cols) != cudaSuccess || kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp) != cudaSuccess ||
+        desc.alloc(32 * kOrbMaxKp) != cudaSuccess || cnt.alloc(sizeof(int)) != cudaSuccess) fail("cudaMalloc failed");
+    if (st == VSTAB_OK) {
+        cudaMemcpy(img.p, gray, (size_t)rows * cols, cudaMemcpyHostToDevice);
+        launch_orb(P, img.as<uint8_t>(), kps.as<OrbKeypoint>(), desc.as<uint8_t>(), cnt.as<int>(), 0);
+        int n = 0;
+        if (cudaMemcpy(&n, cnt.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) fail(cudaGetErrorString(cudaGetLastError()));
+        if (st == VSTAB_OK) {
+            if (n > kOrbMaxKp) n = kOrbMaxKp;
+            if (n > max_out) n = max_out;
+            *n_out = n;
+            std::vector<OrbKeypoint> h(n);
+            cudaMemcpy(h.data(), kps.p, sizeof(OrbKeypoint) * n, cudaMemcpyDeviceToHost);
+            cudaMemcpy(desc_out, desc.p, (size_t)32 * n, cudaMemcpyDeviceToHost);
+            for (int i = 0; i < n; ++i) {
+                float* o = kps_out + (size_t)i * 6;
+                o[0] = h[i].x; o[1] = h[i].y; o[2] = h[i].size; o[3] = h[i].angle; o[4] = h[i].response; o[5] = (float)h[i].octave;
+            }
+            if (cudaGetLastError() != cudaSuccess) fail("CUDA failure in vstab_k_orb");
+        }
+    }
+    orb_plan_destroy(P);
+    return st;
+}
+
+extern "C" vstab_status vstab_k_hamming(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur, float ratio,
+                                        int* best_idx, int* best_d, int* second_d, uint8_t* good) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!ref || !cur || !best_idx || !best_d || !second_d || !good || nref < 0 || ncur < 0 || nref > kOrbMaxKp || ncur > kOrbMaxKp)
+        return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    DevBuf a, b, na, nb, bi, bd, sd, gd, ka, kb, rp, cp, stt, nm;
+    CK(a.alloc(32 * kOrbMaxKp)); CK(b.alloc(32 * kOrbMaxKp)); CK(na.alloc(4)); CK(nb.alloc(4));
+    CK(bi.alloc(4 * kOrbMaxKp)); CK(bd.alloc(4 * kOrbMaxKp)); CK(sd.alloc(4 * kOrbMaxKp)); CK(gd.alloc(kOrbMaxKp));
+    CK(ka.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(kb.alloc(sizeof(OrbKeypoint) * kOrbMaxKp));
+    CK(rp.alloc(sizeof(float2) * kOrbMaxKp)); CK(cp.alloc(sizeof(float2) * kOrbMaxKp)); CK(stt.alloc(kOrbMaxKp)); CK(nm.alloc(4));
+    CK(cudaMemset(ka.p, 0, sizeof(OrbKeypoint) * kOrbMaxKp)); CK(cudaMemset(kb.p, 0, sizeof(OrbKeypoint) * kOrbMaxKp));
+    CK(cudaMemcpy(a.p, ref, (size_t)32 * nref, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.p, cur, (size_t)32 * ncur, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(na.p, &nref, 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(nb.p, &ncur, 4, cudaMemcpyHostToDevice));
+    launch_hamming_match(a.as<uint8_t>(), na.as<int>(), ka.as<OrbKeypoint>(), b.as<uint8_t>(), nb.as<int>(), kb.as<OrbKeypoint>(),
+                         kOrbMaxKp, ratio, bi.as<int>(), bd.as<int>(), sd.as<int>(), gd.as<uint8_t>(), rp.as<float2>(),
+                         cp.as<float2>(), stt.as<uint8_t>(), nm.as<int>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(best_idx, bi.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(best_d, bd.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(second_d, sd.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(good, gd.p, (size_t)nref, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}

@@ -35,12 +35,14 @@ VSTAB_D T block_sum(T v, T* scratch /* >= 8 */) {
     return t;
 }
 
+template <int CAP>
 __global__ void __launch_bounds__(kFitThreads)
 fit_kernel(const float2* __restrict__ prev_pts, const float2* __restrict__ next_pts,
            const uint8_t* __restrict__ status, const int* __restrict__ counts,
            double thresh, double cx, double cy, double* __restrict__ T, double* __restrict__ M,
            int* __restrict__ fit_counts, long frame_id0) {
-    __shared__ float spx[kMaxCorners], spy[kMaxCorners], sqx[kMaxCorners], sqy[kMaxCorners];
+    extern __shared__ float fit_smem[];
+    float* spx = fit_smem; float* spy = spx + CAP; float* sqx = spy + CAP; float* sqy = sqx + CAP;
     __shared__ int wcount[kFitThreads / 32];
     __shared__ int wcount2[2][kFitThreads / 32];
     __shared__ double dscratch[kFitThreads / 32];
@@ -48,13 +50,13 @@ fit_kernel(const float2* __restrict__ prev_pts, const float2* __restrict__ next_
 
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n = min(counts[frame], kMaxCorners);
-    const float2* P = prev_pts + (size_t)frame * kMaxCorners;
-    const float2* Q = next_pts + (size_t)frame * kMaxCorners;
-    const uint8_t* S = status + (size_t)frame * kMaxCorners;
+    const int n = min(counts[frame], CAP);
+    const float2* P = prev_pts + (size_t)frame * CAP;
+    const float2* Q = next_pts + (size_t)frame * CAP;
+    const uint8_t* S = status + (size_t)frame * CAP;
 
     // ---- stable compaction of the tracked pairs -----------------------------------------
-    constexpr int kPer = (kMaxCorners + kFitThreads - 1) / kFitThreads;   // 6 consecutive items per thread
+    constexpr int kPer = (CAP + kFitThreads - 1) / kFitThreads;           // consecutive items per thread
     const int i0 = tid * kPer;
     int mine = 0;
 #pragma unroll
@@ -109,7 +111,7 @@ fit_kernel(const float2* __restrict__ prev_pts, const float2* __restrict__ next_
         rng = (unsigned long long)(unsigned)rng * 4164903690ull + (unsigned)(rng >> 32);
         return (int)((unsigned)rng % n_);
     };
-    constexpr int kOwn = (kMaxCorners + kFitThreads - 1) / kFitThreads;   // 6 points per thread
+    constexpr int kOwn = (CAP + kFitThreads - 1) / kFitThreads;           // points per thread (mask bits)
     unsigned best_bits = 0;
     int max_good = 0;
     int niters = 2000;
@@ -212,18 +214,22 @@ fit_kernel(const float2* __restrict__ prev_pts, const float2* __restrict__ next_
             double* Mo = M + (size_t)frame * 6;
             Mo[0] = la; Mo[1] = -lb; Mo[2] = ltx; Mo[3] = lb; Mo[4] = la; Mo[5] = lty;
         }
+        bool valid = false;
         if (ok) {
             HParams hp;
             if (decompose_h(H, cx, cy, &hp)) {           // :261-266
                 hp.s = 1.0;
                 compose_h(&hp, cx, cy, Tout);
+                valid = true;
             } else {
                 eye3(Tout);                              // :268-272
             }
         } else {
             eye3(Tout);
         }
-        if (fit_counts) { fit_counts[frame * 2] = m; fit_counts[frame * 2 + 1] = (int)s1; }
+        // second count: inliers of the consensus set, 0 when no valid transform came out (the ORB /
+        // SIFT registration then keeps its previous matrix, :738-749)
+        if (fit_counts) { fit_counts[frame * 2] = m; fit_counts[frame * 2 + 1] = valid ? (int)s1 : 0; }
     }
 }
 
@@ -235,8 +241,20 @@ void launch_fit(const float2* prev_pts, const float2* next_pts, const uint8_t* s
                 cudaStream_t st) {
     if (nframes <= 0) return;
     count_launch(1);
-    fit_kernel<<<nframes, kFitThreads, 0, st>>>(prev_pts, next_pts, status, counts, thresh, cx, cy, T, M,
-                                                fit_counts, frame_id0);
+    fit_kernel<kMaxCorners><<<nframes, kFitThreads, sizeof(float) * 4 * kMaxCorners, st>>>(
+        prev_pts, next_pts, status, counts, thresh, cx, cy, T, M, fit_counts, frame_id0);
+}
+
+void launch_fit_large(const float2* ref_pts, const float2* cur_pts, const uint8_t* status, const int* count,
+                      double thresh, double cx, double cy, double* T, double* M, int* fit_counts, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fit_kernel<kOrbMaxKp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 4 * kOrbMaxKp));
+        attr = true;
+    }
+    count_launch(1);
+    fit_kernel<kOrbMaxKp><<<1, kFitThreads, sizeof(float) * 4 * kOrbMaxKp, st>>>(ref_pts, cur_pts, status, count, thresh, cx,
+                                                                                 cy, T, M, fit_counts, 0);
 }
 
 }  // namespace vstabk

@@ -5,6 +5,8 @@
 //   * corners / LK points: float2 [frame][kMaxCorners]; counts int [frame].
 //   * transforms: double [frame][9] row-major.
 #pragma once
+#include <string>
+#include <vector>
 #include "common.cuh"
 
 namespace vstabk {
@@ -64,6 +66,9 @@ void launch_fit(const float2* prev_pts, const float2* next_pts, const uint8_t* s
                 double* T /* [nframes][9] */, double* M /* [nframes][6] or null */,
                 int* fit_counts /* [nframes][2] or null */, const long* frame_ids /* or null */,
                 long frame_id0, cudaStream_t st);
+// same estimator for up to kOrbMaxKp point pairs of ONE pair set (ORB / SIFT registration, thr 5.0, :734-736)
+void launch_fit_large(const float2* ref_pts, const float2* cur_pts, const uint8_t* status, const int* count,
+                      double thresh, double cx, double cy, double* T, double* M, int* fit_counts, cudaStream_t st);
 
 // ---------------------------------------------------------------- K6 window smoothing / lock, warp params
 struct WarpParams {          // consumed by K7
@@ -97,6 +102,40 @@ void launch_acc_scan(const double* T, long n_total, long anchor, double* acc, cu
 void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long slot_mod,
                  const WarpParams* wp, int nout, int w, int h,
                  uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st);
+
+// ---------------------------------------------------------------- K8 feature-path preprocessing
+void build_nn_table(int src, int dst, int* host_tab);                       // cv::resize INTER_NEAREST offsets
+size_t featprep_workspace_bytes(int w, int h);
+// frame: device BGR (full resolution) -> out: device u8 w x h (tight), the conditioned working image
+void launch_featprep(const uint8_t* frame, size_t pitch, const int* xofs, const int* yofs, int w, int h,
+                     void* workspace, uint8_t* out, cudaStream_t st);
+
+// ---------------------------------------------------------------- K9 ORB, K10 Hamming matcher
+constexpr int kOrbLevels = 12;             // ORB::create nlevels, src/stabilizer.cpp:485
+constexpr int kOrbMaxKp = 4096;            // 2500 requested + retainBest ties, rounded up
+struct OrbKeypoint { float x, y, size, angle, response; int octave; };     // cv::KeyPoint fields the path uses
+struct OrbPlan {
+    int w = 0, h = 0, max_kp = 0, cap = 0, ntiles = 0;
+    size_t pyr_bytes = 0, cub_bytes = 0;
+    void* levels = nullptr;                // OrbLevels (orb.cu)
+    void* mem = nullptr;
+    int2* tabs = nullptr;
+    std::vector<size_t> tab_off;
+    uint8_t *pyr = nullptr, *blur = nullptr, *score = nullptr;
+    unsigned long long *cand = nullptr, *cand_sorted = nullptr;
+    unsigned int* hist = nullptr;
+    int* counters = nullptr;
+    void* cub_temp = nullptr;
+};
+// size_ratio: the reference's filterKeypointByRelativeSize ratio (0.10 for ORB; <= 0 keeps every level)
+OrbPlan* orb_plan_create(int w, int h, double size_ratio, int max_keypoints, std::string* err);
+void orb_plan_destroy(OrbPlan* P);
+int orb_levels_used(const OrbPlan* P);
+void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, cudaStream_t st);
+void launch_hamming_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,
+                          const int* ncur, const OrbKeypoint* cur_kps, int max_kp, float ratio, int* best_idx, int* best_d,
+                          int* second_d, uint8_t* good, float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch,
+                          cudaStream_t st);
 
 // ---------------------------------------------------------------- K13 simulator render
 struct RenderPose { double R[9]; double cam[3]; };

@@ -85,6 +85,9 @@ SYMBOLS = {
     "vstab_k_fit": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, _f64p, _f64p,
                               C.POINTER(C.c_int)]),
     "vstab_k_warp": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, _f64p, _vp, _vp, C.c_size_t]),
+    "vstab_k_featprep": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, C.c_int, _vp]),
+    "vstab_k_orb": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
+    "vstab_k_hamming": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -314,3 +317,37 @@ def k_warp(bgr: np.ndarray, H: np.ndarray, border, device: int = 0):
     _check(lib.vstab_k_warp(device, _ptr(bgr), bgr.shape[0], bgr.shape[1], bgr.strides[0], H.ctypes.data_as(_f64p),
                             _ptr(b), _ptr(out), out.strides[0]))
     return out
+
+
+def k_featprep(bgr: np.ndarray, working_height: int, device: int = 0) -> np.ndarray:
+    """ORB/SIFT preprocessing chain of the reference (src/stabilizer.cpp:448-477) on the GPU."""
+    lib = load_library()
+    rows, cols = bgr.shape[:2]
+    ww = int(cols * (float(working_height) / rows))
+    out = np.empty((working_height, ww), np.uint8)
+    bgr = np.ascontiguousarray(bgr)
+    _check(lib.vstab_k_featprep(device, _ptr(bgr), rows, cols, bgr.strides[0], working_height, _ptr(out)))
+    return out
+
+
+def k_orb(gray: np.ndarray, size_ratio: float = 0.0, device: int = 0):
+    """ORB(2500, 1.2, 12, 31, 0, 2, FAST_SCORE, 31, 20).detectAndCompute -> (kps [n,6], desc [n,32])."""
+    lib = load_library()
+    gray = np.ascontiguousarray(gray)
+    kps = np.zeros((4096, 6), np.float32)
+    desc = np.zeros((4096, 32), np.uint8)
+    n = C.c_int(0)
+    _check(lib.vstab_k_orb(device, _ptr(gray), gray.shape[0], gray.shape[1], float(size_ratio), _ptr(kps), _ptr(desc),
+                           C.byref(n), 4096))
+    return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+def k_hamming(ref: np.ndarray, cur: np.ndarray, ratio: float = 0.6, device: int = 0):
+    """BFMatcher(NORM_HAMMING).knnMatch(ref, cur, 2) + ratio test -> (best_idx, best_d, second_d, good)."""
+    lib = load_library()
+    ref = np.ascontiguousarray(ref, np.uint8)
+    cur = np.ascontiguousarray(cur, np.uint8)
+    n = len(ref)
+    bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); sd = np.zeros(n, np.int32); good = np.zeros(n, np.uint8)
+    _check(lib.vstab_k_hamming(device, _ptr(ref), n, _ptr(cur), len(cur), ratio, _ptr(bi), _ptr(bd), _ptr(sd), _ptr(good)))
+    return bi, bd, sd, good
