@@ -126,7 +126,10 @@ typedef enum vstab_tap {
     VSTAB_TAP_BORDER = 12,     /* u8  3     border colour after saturate_cast (:1309)             */
     VSTAB_TAP_EIG = 13,        /* f32 working_h*working_w  min-eigenvalue map of the current gray  */
     VSTAB_TAP_INLIERS = 14,    /* i32 2     {n tracked, n RANSAC inliers}                         */
-    VSTAB_TAP_CHANNEL_SUMS = 15/* u64 3     per-channel byte sums of the presentation frame       */
+    VSTAB_TAP_CHANNEL_SUMS = 15,/* u64 3    per-channel byte sums of the presentation frame       */
+    VSTAB_TAP_LOCK_H = 16,     /* f64 9     ORB registration: matrix returned by calculateFullLockStabilization (:784-787) */
+    VSTAB_TAP_ORB_COUNTS = 17, /* i32 5     {keypoints current, reference, matches after ratio test, inliers, updated} */
+    VSTAB_TAP_FEAT_GRAY = 18   /* u8  working_h*working_w  conditioned image of the presentation frame (:448-477) */
 } vstab_tap;
 long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes);
 int vstab_working_width(const vstab_t* s);
@@ -218,11 +221,12 @@ vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, int cols, si
 
 /* ORB / SIFT registration path (src/stabilizer.cpp:448-477 preprocessing, :483-491 + :605-606 ORB
  * detectAndCompute, :647-673 Hamming 2-NN + ratio test).  kps_out: 6 floats per keypoint
- * {x, y, size, angle, response, octave}, level-major then row-major; desc_out: 32 bytes each. */
+ * {x, y, size, angle, response, octave}, level-major then row-major -- or, with reference_order,
+ * in the exact order cv::ORB returns them (retainBest's nth_element permutation); desc_out: 32 bytes each. */
 vstab_status vstab_k_featprep(int device, const uint8_t* bgr, int rows, int cols, size_t step,
                               int working_height, uint8_t* gray_out);
 vstab_status vstab_k_orb(int device, const uint8_t* gray, int rows, int cols, double size_ratio,
-                         float* kps_out, uint8_t* desc_out, int* n_out, int max_out);
+                         int reference_order, float* kps_out, uint8_t* desc_out, int* n_out, int max_out);
 vstab_status vstab_k_hamming(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur,
                              float ratio, int* best_idx, int* best_d, int* second_d, uint8_t* good);
 

@@ -66,6 +66,20 @@ def test_orb_identical_keypoints_and_descriptors(texture, W, H, wh):
     assert order == sorted(order)
 
 
+@pytest.mark.parametrize("W,H,wh", [(1280, 720, 360), (1920, 1080, 1080), (1920, 1080, 720)])
+def test_orb_reference_order_equals_opencv(texture, W, H, wh):
+    """reference_order replays retainBest's std::nth_element + std::partition permutation: keypoints and
+    descriptors come out in exactly cv::ORB's order (which fixes the RANSAC sample sequence downstream)."""
+    frame = render_clip(texture, W, H, 1, start=11)[0]
+    gray = _cv_prep(frame, wh)
+    kps, desc = vs.k_orb(gray, reference_order=True)
+    ckps, cdesc = _cv_orb(gray)
+    assert len(kps) == len(ckps)
+    want = np.array([[k.pt[0], k.pt[1], k.octave] for k in ckps], np.float32)
+    assert np.array_equal(kps[:, [0, 1, 5]], want)
+    assert np.array_equal(desc, cdesc)
+
+
 def test_orb_size_filter_and_empty(texture):
     frame = render_clip(texture, 1280, 720, 1, start=7)[0]
     gray = _cv_prep(frame, 360)

@@ -132,7 +132,7 @@ def test_api_errors(golden):
     with pytest.raises(AssertionError):
         st.stabilize_frame(clip[2])
     with pytest.raises(NotImplementedError):
-        st.set_stabilization_mode(vs.ORB_FULL_LOCK)
+        st.set_stabilization_mode(vs.SIFT_FULL_LOCK)
     with pytest.raises(ValueError):
         st.set_stabilization_mode(7)
     st.close()
@@ -165,3 +165,63 @@ def test_two_instances_are_independent(golden):
         assert np.array_equal(oa, solo.stabilize_frame(fr))
     for s in (a, b, solo):
         s.close()
+
+
+@pytest.mark.parametrize("W,H,wh,n", [(1280, 720, 360, 22), (1920, 1080, 1080, 14)])
+def test_orb_full_lock_matches_oracle(texture, W, H, wh, n):
+    """BASELINE config 3 (shortened): ORB registration to the reference frame.  Integer stages are
+    bit-exact (conditioned image, keypoint counts, match counts) and the reference keypoints are kept in
+    cv::ORB's own order, so the similarity fit sees the same match list as OpenCV's RANSAC:
+    homography <= 0.1 px at the frame corners (north-star tolerance; observed ~1e-9)."""
+    frames = render_clip(texture, W, H, n)
+    P, F, switch = 6, 4, 8
+    ref = sr.StabilizerRef(P, F, wh)
+    st = vs.Stabilizer(P, F, wh)
+    worst_h, worst_frac = 0.0, 0.0
+    for i, f in enumerate(frames):
+        if i == switch:
+            ref.set_stabilization_mode(sr.ORB_FULL_LOCK)
+            st.set_stabilization_mode(vs.ORB_FULL_LOCK)
+        want = ref.stabilize_frame(f)
+        got = st.stabilize_frame(f)
+        if i < switch:
+            continue
+        assert st.presentation_index() == ref.taps.presentation_idx
+        cnt = st.tap(vs.TAP_ORB_COUNTS)
+        if i == switch:
+            assert np.array_equal(st.tap(vs.TAP_LOCK_H), np.eye(3))        # reference capture returns identity
+            assert cnt[1] == len(ref.ref_kps) and cnt[1] > 100
+            assert np.array_equal(st.tap(vs.TAP_FEAT_GRAY), ref.reference_gray)
+        else:
+            assert cnt[1] == len(ref.ref_kps)
+            assert cnt[2] == ref.taps.n_matches                            # ratio-test survivors: identical set
+            assert cnt[4] == 1
+        worst_h = max(worst_h, _corner_diff(st.tap(vs.TAP_H_SCALED), ref.taps.H_scaled, W, H))
+        worst_frac = max(worst_frac, float((np.abs(got.astype(int) - want) > PIX_TOL).mean()))
+    st.close()
+    assert worst_h <= H_TOL_PX
+    assert worst_frac <= 0.05
+
+
+def test_orb_lock_keeps_previous_h_on_failure(texture):
+    """Too few keypoints in the current frame: calculateFullLockStabilization returns the previously
+    returned matrix (src/stabilizer.cpp:640-643)."""
+    frames = render_clip(texture, 640, 360, 12)
+    st = vs.Stabilizer(3, 2, 360)
+    for i, f in enumerate(frames[:8]):
+        if i == 4:
+            st.set_stabilization_mode(vs.ORB_FULL_LOCK)
+        st.stabilize_frame(f)
+    assert st.tap(vs.TAP_ORB_COUNTS)[4] == 1
+    flat = np.full_like(frames[0], 128)
+    for _ in range(2):                                  # these calls still present textured frames 6 and 7
+        st.stabilize_frame(flat)
+        assert st.tap(vs.TAP_ORB_COUNTS)[4] == 1
+    h_before = st.tap(vs.TAP_LOCK_H)
+    assert not np.array_equal(h_before, np.eye(3))
+    for _ in range(3):                                  # now the flat frames are presented: no keypoints
+        out = st.stabilize_frame(flat)
+        cnt = st.tap(vs.TAP_ORB_COUNTS)
+        assert cnt[0] < 10 and cnt[4] == 0
+        assert np.array_equal(st.tap(vs.TAP_LOCK_H), h_before)
+    st.close()

@@ -168,6 +168,12 @@ struct vstab {
     DevBuf ring, sums, pyr0, pyr1, corners0, corners1, ccount, lkpts, lkstat, T, Mtap, fitc, acc, wp, gmem, dout;
     long t_mod = 0;
     GfttWorkspace gws{};
+    // ORB registration state (reference: referenceGray_/Keypoints_/Descriptors_, hpp:447-456, and the
+    // function-static previouslyReturnedH, cpp:446 -- per instance here)
+    OrbPlan* orb = nullptr;
+    bool has_reference = false;
+    DevBuf feat_ws, feat_gray, nn_x, nn_y, ref_kps, ref_desc, cur_kps, cur_desc, orb_counts, m_idx, m_d0, m_d1, m_good,
+        m_ref, m_cur, m_status, lock_fit, lock_h, lock_tap;
     std::string err;
 
     void set_err(const std::string& e) { err = e; }
@@ -244,6 +250,59 @@ static vstab_status stream_estimate(vstab* s) {
     return VSTAB_OK;
 }
 
+// calculateFullLockStabilization, ORB branch (stabilizer.cpp:440-787) for presentation frame p, on
+// the output stream: condition the full-resolution frame, detect + describe, and either capture the
+// reference (first call after setStabilizationMode) or match against it and fit.
+static vstab_status stream_orb_lock(vstab* s, long p) {
+    auto set_err = [&](const std::string& e) { s->err = e; };
+    Geometry& g = s->g;
+    cudaStream_t q = s->out_stream;
+    if (!s->orb) {
+        s->orb = orb_plan_create(g.ww, g.wh, 0.10, kOrbMaxKp, &s->err);      // MAX_KEYPOINT_RELATIVE_SIZE_ORB, :493
+        if (!s->orb) return VSTAB_ERR_CUDA;
+        std::vector<int> xo(g.ww), yo(g.wh);
+        build_nn_table(g.cols, g.ww, xo.data());
+        build_nn_table(g.rows, g.wh, yo.data());
+        CK(s->feat_ws.alloc(featprep_workspace_bytes(g.ww, g.wh)));
+        CK(s->feat_gray.alloc((size_t)g.ww * g.wh));
+        CK(s->nn_x.alloc(sizeof(int) * g.ww)); CK(s->nn_y.alloc(sizeof(int) * g.wh));
+        CK(cudaMemcpy(s->nn_x.p, xo.data(), sizeof(int) * g.ww, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->nn_y.p, yo.data(), sizeof(int) * g.wh, cudaMemcpyHostToDevice));
+        CK(s->ref_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(s->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp));
+        CK(s->ref_desc.alloc(32 * kOrbMaxKp)); CK(s->cur_desc.alloc(32 * kOrbMaxKp));
+        CK(s->orb_counts.alloc(sizeof(int) * 4));                            // {nref, ncur, nmatch}
+        CK(s->m_idx.alloc(4 * kOrbMaxKp)); CK(s->m_d0.alloc(4 * kOrbMaxKp)); CK(s->m_d1.alloc(4 * kOrbMaxKp));
+        CK(s->m_good.alloc(kOrbMaxKp)); CK(s->m_status.alloc(kOrbMaxKp));
+        CK(s->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(s->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
+        CK(s->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));        // T[9], M[6], counts[2]
+        CK(s->lock_h.alloc(sizeof(double) * 9));
+        CK(s->lock_tap.alloc(sizeof(int) * 8));
+        CK(cudaMemsetAsync(s->orb_counts.p, 0, sizeof(int) * 4, q));
+    }
+    const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)(p % s->W) * g.frame_bytes;           // :444
+    launch_featprep(frame, g.pitch, s->nn_x.as<int>(), s->nn_y.as<int>(), g.ww, g.wh, s->feat_ws.p,
+                    s->feat_gray.as<uint8_t>(), q);                                                // :448-477
+    int* counts = s->orb_counts.as<int>();
+    double* Tfit = s->lock_fit.as<double>();
+    int* fitc = reinterpret_cast<int*>(Tfit + 16);
+    if (!s->has_reference) {                                                                     // :520-589
+        launch_orb(s->orb, s->feat_gray.as<uint8_t>(), s->ref_kps.as<OrbKeypoint>(), s->ref_desc.as<uint8_t>(), counts + 0, true, q);
+        launch_lock_update(Tfit, fitc, counts + 0, counts + 0, counts + 0, 1, s->lock_h.as<double>(), s->lock_tap.as<int>(), q);
+        s->has_reference = true;
+    } else {
+        launch_orb(s->orb, s->feat_gray.as<uint8_t>(), s->cur_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(), counts + 1, false, q);  // :604-612
+        launch_hamming_match(s->ref_desc.as<uint8_t>(), counts + 0, s->ref_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(),
+                             counts + 1, s->cur_kps.as<OrbKeypoint>(), kOrbMaxKp, 0.6f, s->m_idx.as<int>(), s->m_d0.as<int>(),
+                             s->m_d1.as<int>(), s->m_good.as<uint8_t>(), s->m_ref.as<float2>(), s->m_cur.as<float2>(),
+                             s->m_status.as<uint8_t>(), counts + 2, q);                            // :647-673, :711-716
+        launch_fit_large(s->m_ref.as<float2>(), s->m_cur.as<float2>(), s->m_status.as<uint8_t>(), counts + 2, 5.0,
+                         g.ww / 2.0, g.wh / 2.0, Tfit, Tfit + 9, fitc, q);                         // :734-758
+        launch_lock_update(Tfit, fitc, counts + 0, counts + 1, counts + 2, 0, s->lock_h.as<double>(), s->lock_tap.as<int>(), q);  // :784-787
+    }
+    CK(cudaGetLastError());
+    return VSTAB_OK;
+}
+
 // Output chain of call s->n (n >= 1) on s->out_stream; `d_out`/`out_pitch`: where the warped
 // presentation frame goes.  The caller has already made out_stream wait for the transforms it needs.
 static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
@@ -257,11 +316,16 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
         s->acc_valid = true;
         s->acc_to = p;
     }
+    if (s->mode == VSTAB_ORB_FULL_LOCK) {
+        vstab_status st = stream_orb_lock(s, p);
+        if (st != VSTAB_OK) return st;
+    }
     SmoothArgs a{};
     a.T = s->T.as<double>(); a.t_mod = s->t_mod;
     a.P = (int)s->P; a.F = (int)s->F;
     a.mode = s->mode; a.lock_call = s->lock_call;
     a.acc = s->acc.as<double>(); a.acc_mod = 0;
+    a.lock_h = s->mode == VSTAB_ORB_FULL_LOCK ? s->lock_h.as<double>() : nullptr;
     a.scale = g.scale;
     a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
     a.npix = (double)g.rows * (double)g.cols;
@@ -393,17 +457,19 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_in) cudaEventDestroy(s->ev_in);
     if (s->ev_fit) cudaEventDestroy(s->ev_fit);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
+    if (s->orb) orb_plan_destroy(s->orb);
     delete s;
 }
 
 vstab_status vstab_set_mode(vstab_t* s, int mode) {
     if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
     if (mode < 0 || mode > 5) { s->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
-    if (mode == VSTAB_ORB_FULL_LOCK || mode == VSTAB_SIFT_FULL_LOCK) {
-        s->err = "ORB/SIFT registration modes are not built yet (DESIGN.md, SURVEY 8a rows a11-a16)";
+    if (mode == VSTAB_SIFT_FULL_LOCK) {
+        s->err = "SIFT registration mode is not built yet (DESIGN.md, SURVEY 8a rows a14-a15)";
         return VSTAB_ERR_UNSUPPORTED;
     }
     // stabilizer.cpp:55-70: reset reference + accumulator, keep window / prevGray_ / prevPoints_
+    s->has_reference = false;
     s->acc_valid = false;
     s->acc_to = -1;
     s->mode = mode;
@@ -507,6 +573,9 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
         case VSTAB_TAP_BORDER: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, border), 3, 3);
         case VSTAB_TAP_EIG: return copy(s->gws.eig, sizeof(float) * g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_INLIERS: if (last == 0) return 0; return copy(s->fitc.p, sizeof(int) * 2, 2);
+        case VSTAB_TAP_LOCK_H: if (!s->lock_h.p) return 0; return copy(s->lock_h.p, sizeof(double) * 9, 9);
+        case VSTAB_TAP_ORB_COUNTS: if (!s->lock_tap.p) return 0; return copy(s->lock_tap.p, sizeof(int) * 5, 5);
+        case VSTAB_TAP_FEAT_GRAY: if (!s->feat_gray.p) return 0; return copy(s->feat_gray.p, (size_t)g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_CHANNEL_SUMS:
             return copy(s->sums.as<unsigned long long>() + (s->last_presented % s->W) * 3, sizeof(unsigned long long) * 3, 3);
     }
@@ -1024,7 +1093,7 @@ extern "C" vstab_status vstab_k_featprep(int device, const uint8_t* bgr, int row
 }
 
 extern "C" vstab_status vstab_k_orb(int device, const uint8_t* gray, int rows, int cols, double size_ratio,
-                                    float* kps_out, uint8_t* desc_out, int* n_out, int max_out) {
+                                    int reference_order, float* kps_out, uint8_t* desc_out, int* n_out, int max_out) {
     auto set_err = [&](const std::string& e) { g_err = e; };
     if (!gray || !kps_out || !desc_out || !n_out || max_out < 1) return VSTAB_ERR_INVALID_ARGUMENT;
     if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
@@ -1037,7 +1106,7 @@ extern "C" vstab_status vstab_k_orb(int device, const uint8_t* gray, int rows, i
         desc.alloc(32 * kOrbMaxKp) != cudaSuccess || cnt.alloc(sizeof(int)) != cudaSuccess) fail("cudaMalloc failed");
     if (st == VSTAB_OK) {
         cudaMemcpy(img.p, gray, (size_t)rows * cols, cudaMemcpyHostToDevice);
-        launch_orb(P, img.as<uint8_t>(), kps.as<OrbKeypoint>(), desc.as<uint8_t>(), cnt.as<int>(), 0);
+        launch_orb(P, img.as<uint8_t>(), kps.as<OrbKeypoint>(), desc.as<uint8_t>(), cnt.as<int>(), reference_order != 0, 0);
         int n = 0;
         if (cudaMemcpy(&n, cnt.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) fail(cudaGetErrorString(cudaGetLastError()));
         if (st == VSTAB_OK) {

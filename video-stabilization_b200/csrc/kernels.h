@@ -86,6 +86,7 @@ struct SmoothArgs {
     long lock_call;              // call index at which the lock mode was set (ACCUMULATED)
     const double* acc;           // optional precomputed accumulated products by abs frame idx (offline), mod acc_mod
     long acc_mod;
+    const double* lock_h;        // ORB / SIFT registration matrix (9 doubles, device) or null
     double scale;                // workingHeight / rows
     const unsigned long long* sums;   // [slot][3] channel sums by frame slot
     long sums_mod;               // slot = abs frame % sums_mod   (ring) or abs - frame_base (offline: see frame_base)
@@ -93,6 +94,9 @@ struct SmoothArgs {
     double npix;                 // rows*cols
 };
 void launch_smooth(const SmoothArgs& a, long call_first, int ncalls, WarpParams* out, cudaStream_t st);
+// ORB / SIFT registration: fold one fit result into the "previously returned H" state (:724-787)
+void launch_lock_update(const double* Tfit, const int* fit_counts, const int* nref, const int* ncur, const int* nmatch,
+                        int reset, double* lock_h, int* tap, cudaStream_t st);
 // streaming ACCUMULATED_FULL_LOCK state update: acc <- T[p] * acc (src/stabilizer.cpp:334)
 void launch_acc_update(const double* T, long t_mod, long p, int reset, double* acc_state, cudaStream_t st);
 // offline: acc[k] for k in [a, a+n): acc[a] = I, acc[k] = T[k] * acc[k-1]
@@ -131,7 +135,8 @@ struct OrbPlan {
 OrbPlan* orb_plan_create(int w, int h, double size_ratio, int max_keypoints, std::string* err);
 void orb_plan_destroy(OrbPlan* P);
 int orb_levels_used(const OrbPlan* P);
-void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, cudaStream_t st);
+void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, bool reference_order,
+                cudaStream_t st);
 void launch_hamming_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,
                           const int* ncur, const OrbKeypoint* cur_kps, int max_kp, float ratio, int* best_idx, int* best_d,
                           int* second_d, uint8_t* good, float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch,

@@ -190,21 +190,170 @@ orb_threshold_kernel(const unsigned int* __restrict__ hist, OrbLevels L, int* __
     thr[l] = t;
 }
 
+// keys beyond the candidate count sort to the end
 __global__ void __launch_bounds__(256)
-orb_mark_kernel(unsigned long long* __restrict__ cand, const int* __restrict__ ncand, int cap, const int* __restrict__ thr,
-                int* __restrict__ nkept) {
+orb_tail_kernel(unsigned long long* __restrict__ cand, const int* __restrict__ ncand, int cap) {
     const int n = min(*ncand, cap);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
-    if (i < n) {
-        const unsigned long long k = cand[i];
-        keep = (int)(k & 0xffffu) >= thr[(int)(k >> 56)];
-        if (!keep) cand[i] = ~0ull;
-    } else if (i < cap) {
-        cand[i] = ~0ull;
+    if (i >= n && i < cap) cand[i] = ~0ull;
+}
+
+// Stable compaction of the sorted candidate list (level-major, row-major) to the keypoints that
+// survive retainBest: score >= threshold of their level.  Single CTA.
+__global__ void __launch_bounds__(1024)
+orb_compact_kernel(const unsigned long long* __restrict__ sorted, const int* __restrict__ ncand, int cap,
+                   const int* __restrict__ thr, unsigned long long* __restrict__ kept, int* __restrict__ nkept, int max_kp) {
+    __shared__ int wsum[32];
+    __shared__ int s_base;
+    const int n = min(*ncand, cap);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        unsigned long long k = 0;
+        bool keep = false;
+        if (i < n) { k = sorted[i]; keep = (int)(k & 0xffffu) >= thr[(int)(k >> 56)]; }
+        const unsigned ball = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[wid] = __popc(ball);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < wid; ++w) off += wsum[w];
+        if (keep) {
+            const int pos = off + __popc(ball & ((1u << lane) - 1u));
+            if (pos < max_kp) kept[pos] = k;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += wsum[w]; s_base += t; }
+        __syncthreads();
     }
-    const unsigned ball = __ballot_sync(0xffffffffu, keep);
-    if ((threadIdx.x & 31) == 0 && ball) atomicAdd(nkept, __popc(ball));
+    if (threadIdx.x == 0) *nkept = s_base;
+}
+
+// ---- OpenCV's keypoint ORDER inside a level (reference capture only) -----------------------------
+// KeyPointsFilter::retainBest leaves the survivors in the permutation produced by
+//   std::nth_element(begin, begin + quota - 1, end, response >)  followed by
+//   std::partition(begin + quota, end, response >= response[quota - 1])
+// (libstdc++: introselect with median-of-3 to *first, unguarded partition, final insertion sort).
+// The order of the REFERENCE keypoints fixes the order of the match list and hence the RANSAC
+// sample sequence of estimateAffinePartial2D, so the reference set is put into exactly that order:
+// one thread per level replays the algorithm on (score, row-major rank) words in shared memory.
+// The current frame's keypoints never need it (their order does not reach the estimator).
+struct Sel {
+    unsigned* a;
+    __device__ bool gt(int i, int j) const { return (a[i] >> 24) > (a[j] >> 24); }          // KeypointResponseGreater
+    __device__ void swp(int i, int j) { const unsigned t = a[i]; a[i] = a[j]; a[j] = t; }
+};
+
+__device__ void sel_move_median_to_first(Sel& S, int result, int a, int b, int c) {
+    if (S.gt(a, b)) {
+        if (S.gt(b, c)) S.swp(result, b);
+        else if (S.gt(a, c)) S.swp(result, c);
+        else S.swp(result, a);
+    } else if (S.gt(a, c)) S.swp(result, a);
+    else if (S.gt(b, c)) S.swp(result, c);
+    else S.swp(result, b);
+}
+
+__device__ int sel_unguarded_partition(Sel& S, int first, int last, int pivot) {
+    while (true) {
+        while (S.gt(first, pivot)) ++first;
+        --last;
+        while (S.gt(pivot, last)) --last;
+        if (!(first < last)) return first;
+        S.swp(first, last);
+        ++first;
+    }
+}
+
+__device__ void sel_insertion_sort(Sel& S, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        const unsigned val = S.a[i];
+        if ((val >> 24) > (S.a[first] >> 24)) {
+            for (int j = i; j > first; --j) S.a[j] = S.a[j - 1];        // move_backward
+            S.a[first] = val;
+        } else {
+            int j = i;                                                   // unguarded linear insert
+            while ((val >> 24) > (S.a[j - 1] >> 24)) { S.a[j] = S.a[j - 1]; --j; }
+            S.a[j] = val;
+        }
+    }
+}
+
+// returns false when introselect would have fallen back to heap_select (depth limit): not replayed
+__device__ bool sel_nth_element(Sel& S, int first, int nth, int last) {
+    if (first == last || nth == last) return true;
+    int depth = 0;
+    for (int n = last - first; n > 1; n >>= 1) ++depth;                  // __lg(n)
+    depth *= 2;
+    while (last - first > 3) {
+        if (depth == 0) return false;
+        --depth;
+        const int mid = first + (last - first) / 2;
+        sel_move_median_to_first(S, first, first + 1, mid, last - 1);
+        const int cut = sel_unguarded_partition(S, first + 1, last, first);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    sel_insertion_sort(S, first, last);
+    return true;
+}
+
+__global__ void __launch_bounds__(32)
+orb_reference_order_kernel(const unsigned long long* __restrict__ sorted, const int* __restrict__ ncand, int cap,
+                           const unsigned int* __restrict__ hist, OrbLevels L, int smem_words,
+                           unsigned long long* __restrict__ kept, const int* __restrict__ nkept, int max_kp,
+                           int* __restrict__ replay_ok) {
+    extern __shared__ unsigned sel_buf[];
+    const int l = blockIdx.x;
+    if (l >= L.nlevels_used) return;
+    // segment of level l in the sorted list and in the kept list
+    int seg0 = 0, kept0 = 0, cnt = 0, kcnt = 0;
+    for (int k = 0; k <= l; ++k) {
+        int c = 0;
+        for (int s2 = threadIdx.x; s2 < 256; s2 += 32) c += (int)hist[k * 256 + s2];
+        c = __reduce_add_sync(0xffffffffu, c);
+        int thr_k = 1, acc = 0;
+        if (L.quota[k] <= 0) thr_k = 256;
+        else for (int s2 = 255; s2 >= 1; --s2) { acc += (int)hist[k * 256 + s2]; if (acc >= L.quota[k]) { thr_k = s2; break; } }
+        int kc = 0;
+        for (int s2 = thr_k; s2 < 256; ++s2) kc += (int)hist[k * 256 + s2];
+        if (k < l) { seg0 += c; kept0 += kc; } else { cnt = c; kcnt = kc; }
+    }
+    const int quota = L.quota[l];
+    if (cnt <= quota || quota <= 0) return;             // retainBest leaves the (row-major) order untouched
+    if (seg0 + cnt > min(*ncand, cap) || cnt > smem_words || kept0 + kcnt > max_kp) {
+        if (threadIdx.x == 0) atomicExch(replay_ok, 0);
+        return;
+    }
+    for (int i = threadIdx.x; i < cnt; i += 32) sel_buf[i] = ((unsigned)(sorted[seg0 + i] & 0xffu) << 24) | (unsigned)i;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        Sel S{sel_buf};
+        bool ok = sel_nth_element(S, 0, quota - 1, cnt);
+        int new_end = quota;
+        if (ok) {
+            const unsigned amb = S.a[quota - 1] >> 24;
+            // std::partition(begin + quota, end, response >= ambiguous)   (bidirectional version)
+            int first = quota, last = cnt;
+            while (true) {
+                while (true) { if (first == last) goto done; else if ((S.a[first] >> 24) >= amb) ++first; else break; }
+                --last;
+                while (true) { if (first == last) goto done; else if (!((S.a[last] >> 24) >= amb)) --last; else break; }
+                S.swp(first, last);
+                ++first;
+            }
+        done:
+            new_end = first;
+            if (new_end != kcnt) ok = false;
+        }
+        if (!ok) atomicExch(replay_ok, 0);
+        sel_buf[smem_words] = ok ? 1u : 0u;
+    }
+    __syncwarp();
+    if (sel_buf[smem_words]) {
+        for (int i = threadIdx.x; i < kcnt; i += 32) kept[kept0 + i] = sorted[seg0 + (sel_buf[i] & 0xffffffu)];
+    }
 }
 
 // ---------------------------------------------------------------- 7x7 sigma-2 Gaussian blur (float, separable)
@@ -506,10 +655,12 @@ void orb_plan_destroy(OrbPlan* P) {
 
 int orb_levels_used(const OrbPlan* P) { return ((const OrbLevels*)P->levels)->nlevels_used; }
 
-// gray: device u8 w x h (tight).  Outputs: kps[max_kp], desc[max_kp][32], *count (device int) = number of keypoints
-void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, cudaStream_t st) {
+// gray: device u8 w x h (tight).  Outputs: kps[max_kp], desc[max_kp][32], *count (device int) = number of keypoints.
+// reference_order: additionally put the keypoints of every level into OpenCV's retainBest order.
+void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, bool reference_order,
+                cudaStream_t st) {
     OrbLevels& L = *(OrbLevels*)P->levels;
-    count_launch(7 + (L.nlevels_used - 1));
+    count_launch(8 + (L.nlevels_used - 1) + (reference_order ? 1 : 0));
     cudaMemcpyAsync(P->pyr, gray, (size_t)P->w * P->h, cudaMemcpyDeviceToDevice, st);
     for (int l = 1; l < L.nlevels_used; ++l)
         orb_resize_kernel<<<dim3((L.w[l] + 255) / 256, L.h[l]), 256, 0, st>>>(
@@ -518,14 +669,30 @@ void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc
     cudaMemsetAsync(P->hist, 0, kOrbLevels * 256 * 4, st);
     cudaMemsetAsync(P->counters, 0, 256, st);
     cudaMemsetAsync(count, 0, sizeof(int), st);
-    fast_score_kernel<<<P->ntiles, dim3(FTX, FTY), 0, st>>>(P->pyr, P->score, L);
-    orb_blur_kernel<<<P->ntiles, dim3(FTX, FTY), 0, st>>>(P->pyr, P->blur, L);
-    fast_nms_kernel<<<dim3(148, L.nlevels_used), 256, 0, st>>>(P->score, L, P->hist, P->cand, P->counters, P->cap);
+    if (P->ntiles > 0) {
+        fast_score_kernel<<<P->ntiles, dim3(FTX, FTY), 0, st>>>(P->pyr, P->score, L);
+        orb_blur_kernel<<<P->ntiles, dim3(FTX, FTY), 0, st>>>(P->pyr, P->blur, L);
+        fast_nms_kernel<<<dim3(148, L.nlevels_used), 256, 0, st>>>(P->score, L, P->hist, P->cand, P->counters, P->cap);
+    }
     orb_threshold_kernel<<<1, 32, 0, st>>>(P->hist, L, P->counters + 4);
-    orb_mark_kernel<<<(P->cap + 255) / 256, 256, 0, st>>>(P->cand, P->counters, P->cap, P->counters + 4, count);
+    orb_tail_kernel<<<(P->cap + 255) / 256, 256, 0, st>>>(P->cand, P->counters, P->cap);
     size_t temp = P->cub_bytes;
     cub::DeviceRadixSort::SortKeys(P->cub_temp, temp, (const unsigned long long*)P->cand, P->cand_sorted, P->cap, 0, 64, st);
-    orb_describe_kernel<<<(P->max_kp + 3) / 4, 128, 0, st>>>(P->cand_sorted, count, P->max_kp, P->pyr, P->blur, L, kps, desc);
+    // the kept keys reuse the (now free) unsorted candidate buffer
+    orb_compact_kernel<<<1, 1024, 0, st>>>(P->cand_sorted, P->counters, P->cap, P->counters + 4, P->cand, count, P->max_kp);
+    if (reference_order && L.nlevels_used > 0) {
+        static bool attr = false;
+        const int words = 50 * 1024;
+        if (!attr) {
+            cudaFuncSetAttribute(orb_reference_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (words + 1) * 4);
+            attr = true;
+        }
+        int one = 1;
+        cudaMemcpyAsync(P->counters + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st);
+        orb_reference_order_kernel<<<L.nlevels_used, 32, (words + 1) * 4, st>>>(P->cand_sorted, P->counters, P->cap, P->hist, L,
+                                                                                words, P->cand, count, P->max_kp, P->counters + 2);
+    }
+    orb_describe_kernel<<<(P->max_kp + 3) / 4, 128, 0, st>>>(P->cand, count, P->max_kp, P->pyr, P->blur, L, kps, desc);
 }
 
 void launch_hamming_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,

@@ -79,9 +79,14 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
         HParams hp;
         if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
     }
+    if ((mode == 1 || mode == 2) && a.lock_h) {           // ORB / SIFT registration (:440-787)
+        for (int i = 0; i < 9; ++i) Hl[i] = a.lock_h[i];
+        HParams hp;
+        if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
+    }
     double H[9];
     if (mode == 5) { for (int i = 0; i < 9; ++i) H[i] = Hs[i]; }
-    else if (mode == 0) { for (int i = 0; i < 9; ++i) H[i] = Hl[i]; }
+    else if (mode == 0 || mode == 1 || mode == 2) { for (int i = 0; i < 9; ++i) H[i] = Hl[i]; }
     else { eye3(H); }                                     // T/R lock: identity
 
     WarpParams wp;
@@ -102,6 +107,28 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
     }
     wp.border[3] = 0;
     out[ci] = wp;
+}
+
+// ORB / SIFT registration result -> the matrix calculateFullLockStabilization returns (:724-787):
+// a valid fit of >= 10 matches between >= 10 keypoints on either side replaces the previously
+// returned matrix by inverse(H with scale forced to 1); anything else keeps it.  reset: reference
+// capture (:520-589) returns identity and resets the fallback (:528).
+__global__ void lock_update_kernel(const double* __restrict__ Tfit, const int* __restrict__ fit_counts,
+                                   const int* __restrict__ nref, const int* __restrict__ ncur,
+                                   const int* __restrict__ nmatch, int reset, double* __restrict__ lock_h,
+                                   int* __restrict__ tap /* {ncur, nref, nmatch, inliers, updated} or null */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (reset) {
+        eye3(lock_h);
+        if (tap) { tap[0] = *nref; tap[1] = *nref; tap[2] = 0; tap[3] = 0; tap[4] = 0; }
+        return;
+    }
+    bool ok = *ncur >= kMinPointsForMotion && *nref >= kMinPointsForMotion && *nmatch >= kMinPointsForMotion &&
+              fit_counts[1] > 0;
+    double inv[9];
+    if (ok) ok = invert3(Tfit, inv) && finite9(inv);
+    if (ok) for (int i = 0; i < 9; ++i) lock_h[i] = inv[i];
+    if (tap) { tap[0] = *ncur; tap[1] = *nref; tap[2] = *nmatch; tap[3] = fit_counts[1]; tap[4] = ok ? 1 : 0; }
 }
 
 // acc <- T[p] * acc   (or identity on the first call after setStabilizationMode)
@@ -168,6 +195,12 @@ void launch_smooth(const SmoothArgs& a, long call_first, int ncalls, WarpParams*
     if (ncalls <= 0) return;
     count_launch(1);
     smooth_kernel<<<ncalls, 32, 0, st>>>(a, call_first, ncalls, out);
+}
+
+void launch_lock_update(const double* Tfit, const int* fit_counts, const int* nref, const int* ncur, const int* nmatch,
+                        int reset, double* lock_h, int* tap, cudaStream_t st) {
+    count_launch(1);
+    lock_update_kernel<<<1, 32, 0, st>>>(Tfit, fit_counts, nref, ncur, nmatch, reset, lock_h, tap);
 }
 
 void launch_acc_update(const double* T, long t_mod, long p, int reset, double* acc_state, cudaStream_t st) {

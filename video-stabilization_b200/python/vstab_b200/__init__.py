@@ -20,7 +20,8 @@ ACCUMULATED_FULL_LOCK, ORB_FULL_LOCK, SIFT_FULL_LOCK, TRANSLATION_LOCK, ROTATION
 OK, ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = range(6)
 
 TAP_GRAY, TAP_PYR1, TAP_PYR2, TAP_PYR3, TAP_PREV_PTS, TAP_LK_PTS, TAP_LK_STATUS, TAP_NEW_PTS, TAP_T, TAP_M, \
-    TAP_H_STABILIZE, TAP_H_SCALED, TAP_BORDER, TAP_EIG, TAP_INLIERS, TAP_CHANNEL_SUMS = range(16)
+    TAP_H_STABILIZE, TAP_H_SCALED, TAP_BORDER, TAP_EIG, TAP_INLIERS, TAP_CHANNEL_SUMS, TAP_LOCK_H, TAP_ORB_COUNTS, \
+    TAP_FEAT_GRAY = range(19)
 
 _PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libvstab.so")
@@ -86,7 +87,7 @@ SYMBOLS = {
                               C.POINTER(C.c_int)]),
     "vstab_k_warp": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, _f64p, _vp, _vp, C.c_size_t]),
     "vstab_k_featprep": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, C.c_int, _vp]),
-    "vstab_k_orb": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
+    "vstab_k_orb": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
     "vstab_k_hamming": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp]),
 }
 
@@ -202,7 +203,8 @@ class Stabilizer:
             TAP_LK_STATUS: (np.uint8, 1300), TAP_NEW_PTS: (np.float32, 2600), TAP_T: (np.float64, 9),
             TAP_M: (np.float64, 6), TAP_H_STABILIZE: (np.float64, 9), TAP_H_SCALED: (np.float64, 9),
             TAP_BORDER: (np.uint8, 3), TAP_EIG: (np.float32, ww * wh), TAP_INLIERS: (np.int32, 2),
-            TAP_CHANNEL_SUMS: (np.uint64, 3),
+            TAP_CHANNEL_SUMS: (np.uint64, 3), TAP_LOCK_H: (np.float64, 9), TAP_ORB_COUNTS: (np.int32, 5),
+            TAP_FEAT_GRAY: (np.uint8, ww * wh),
         }[which]
         buf = np.zeros(spec[1], spec[0])
         n = self._lib.vstab_read_tap(self._h, which, _ptr(buf), buf.nbytes)
@@ -210,7 +212,7 @@ class Stabilizer:
             raise VstabError(f"tap {which} failed ({n})")
         if which in (TAP_PREV_PTS, TAP_LK_PTS, TAP_NEW_PTS):
             return buf[:2 * n].reshape(-1, 2)
-        if which == TAP_GRAY or which == TAP_EIG:
+        if which in (TAP_GRAY, TAP_EIG, TAP_FEAT_GRAY):
             return buf[:n].reshape(wh, ww)
         if which in (TAP_PYR1, TAP_PYR2, TAP_PYR3):
             l = which - TAP_PYR1 + 1
@@ -218,7 +220,7 @@ class Stabilizer:
             for _ in range(l):
                 w_, h_ = (w_ + 1) // 2, (h_ + 1) // 2
             return buf[:n].reshape(h_, w_)
-        if which in (TAP_T, TAP_H_STABILIZE, TAP_H_SCALED):
+        if which in (TAP_T, TAP_H_STABILIZE, TAP_H_SCALED, TAP_LOCK_H):
             return buf[:n].reshape(3, 3)
         if which == TAP_M:
             return buf[:n].reshape(2, 3)
@@ -330,14 +332,14 @@ def k_featprep(bgr: np.ndarray, working_height: int, device: int = 0) -> np.ndar
     return out
 
 
-def k_orb(gray: np.ndarray, size_ratio: float = 0.0, device: int = 0):
+def k_orb(gray: np.ndarray, size_ratio: float = 0.0, reference_order: bool = False, device: int = 0):
     """ORB(2500, 1.2, 12, 31, 0, 2, FAST_SCORE, 31, 20).detectAndCompute -> (kps [n,6], desc [n,32])."""
     lib = load_library()
     gray = np.ascontiguousarray(gray)
     kps = np.zeros((4096, 6), np.float32)
     desc = np.zeros((4096, 32), np.uint8)
     n = C.c_int(0)
-    _check(lib.vstab_k_orb(device, _ptr(gray), gray.shape[0], gray.shape[1], float(size_ratio), _ptr(kps), _ptr(desc),
+    _check(lib.vstab_k_orb(device, _ptr(gray), gray.shape[0], gray.shape[1], float(size_ratio), int(reference_order), _ptr(kps), _ptr(desc),
                            C.byref(n), 4096))
     return kps[:n.value].copy(), desc[:n.value].copy()
 
