@@ -107,3 +107,30 @@ def test_hamming_knn_and_ratio(texture):
     # degenerate train sets
     bi, bd, sd, good = vs.k_hamming(d0[:5], d1[:1], 0.6)
     assert (good == 0).all() and (bi == 0).all()
+
+
+def test_l2_match_tcgen05_equals_bfmatcher(texture):
+    """K12: exact L2 nearest neighbour of real SIFT descriptors on the tensor cores == cv2.BFMatcher(NORM_L2)
+    (indices and distances), plus the reference's distance filter d <= max(0.5 * mean(d), 0.02)."""
+    f0, f1 = render_clip(texture, 1280, 720, 2, start=9)
+    sift = cv2.SIFT_create(2500, 3, 0.04, 5, 1.2)
+    d0 = sift.detectAndCompute(_cv_prep(f0, 720), None)[1]
+    d1 = sift.detectAndCompute(_cv_prep(f1, 720), None)[1]
+    assert len(d0) > 2000 and len(d1) > 2000
+    bi, bd2, good = vs.k_l2match(d0, d1)
+    ms = cv2.BFMatcher(cv2.NORM_L2).match(d0, d1)
+    assert len(ms) == len(d0)
+    want_idx = np.array([m.trainIdx for m in ms])
+    want_d = np.array([m.distance for m in ms], np.float32)
+    # exact squared distances from the integer descriptors (numpy int64)
+    d2 = ((d0.astype(np.int64)[:, None, :] - d1.astype(np.int64)[None, :, :]) ** 2).sum(-1)
+    assert np.array_equal(bd2, d2.min(1))
+    assert np.array_equal(bi, d2.argmin(1))                      # ties -> lowest index
+    assert np.array_equal(bi, want_idx)
+    assert np.array_equal(np.sqrt(bd2.astype(np.float32)), want_d)
+    avg = float(np.sum(want_d.astype(np.float64))) / len(d0)
+    assert np.array_equal(good.astype(bool), want_d.astype(np.float64) <= max(avg * 0.5, 0.02))
+    # ragged sizes: a non-multiple of the 128-row tiles on both sides, and a single train row
+    for nr, nc in ((300, 77), (129, 1), (5, 2500)):
+        bi, bd2, _ = vs.k_l2match(d0[:nr], d1[:nc])
+        assert np.array_equal(bi, d2[:nr, :nc].argmin(1)) and np.array_equal(bd2, d2[:nr, :nc].min(1))

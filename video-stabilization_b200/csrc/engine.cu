@@ -1152,3 +1152,29 @@ extern "C" vstab_status vstab_k_hamming(int device, const uint8_t* ref, int nref
     CK(cudaMemcpy(good, gd.p, (size_t)nref, cudaMemcpyDeviceToHost));
     return VSTAB_OK;
 }
+
+extern "C" vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur,
+                                        int* best_idx, int* best_d2, uint8_t* good) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!ref || !cur || !best_idx || !best_d2 || !good || nref < 0 || ncur < 0 || nref > kOrbMaxKp || ncur > kOrbMaxKp)
+        return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    DevBuf a, b, na, nb, bi, bd, gd, ka, kb, rp, cp, stt, nm;
+    CK(a.alloc(128 * kOrbMaxKp)); CK(b.alloc(128 * kOrbMaxKp)); CK(na.alloc(4)); CK(nb.alloc(4));
+    CK(bi.alloc(4 * kOrbMaxKp)); CK(bd.alloc(4 * kOrbMaxKp)); CK(gd.alloc(kOrbMaxKp));
+    CK(ka.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(kb.alloc(sizeof(OrbKeypoint) * kOrbMaxKp));
+    CK(rp.alloc(sizeof(float2) * kOrbMaxKp)); CK(cp.alloc(sizeof(float2) * kOrbMaxKp)); CK(stt.alloc(kOrbMaxKp)); CK(nm.alloc(4));
+    CK(cudaMemset(ka.p, 0, sizeof(OrbKeypoint) * kOrbMaxKp)); CK(cudaMemset(kb.p, 0, sizeof(OrbKeypoint) * kOrbMaxKp));
+    CK(cudaMemcpy(a.p, ref, (size_t)128 * nref, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.p, cur, (size_t)128 * ncur, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(na.p, &nref, 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(nb.p, &ncur, 4, cudaMemcpyHostToDevice));
+    launch_l2_match(a.as<uint8_t>(), na.as<int>(), ka.as<OrbKeypoint>(), b.as<uint8_t>(), nb.as<int>(), kb.as<OrbKeypoint>(),
+                    kOrbMaxKp, bi.as<int>(), bd.as<int>(), gd.as<uint8_t>(), rp.as<float2>(), cp.as<float2>(),
+                    stt.as<uint8_t>(), nm.as<int>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(best_idx, bi.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(best_d2, bd.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(good, gd.p, (size_t)nref, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}

@@ -142,6 +142,12 @@ void launch_hamming_match(const uint8_t* ref_desc, const int* nref, const OrbKey
                           int* second_d, uint8_t* good, float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch,
                           cudaStream_t st);
 
+// ---------------------------------------------------------------- K12 exact L2 matcher (tcgen05)
+// descriptors: u8 [n][128] (SIFT descriptors are integers 0..255).  best_d2 = exact squared distances.
+void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,
+                     const int* ncur, const OrbKeypoint* cur_kps, int max_kp, int* best_idx, int* best_d2, uint8_t* good,
+                     float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch, cudaStream_t st);
+
 // ---------------------------------------------------------------- K13 simulator render
 struct RenderPose { double R[9]; double cam[3]; };
 void launch_render(const uint8_t* tex, int tex_rows, int tex_cols, const RenderPose* poses_dev, int n,

@@ -1,0 +1,246 @@
+// K12: exact L2 nearest-neighbour matching of SIFT descriptors on the 5th-generation tensor cores
+//   reference: cv::FlannBasedMatcher().match(refDesc, curDesc) + distance filter
+//              d <= max(0.5 * mean(d), 0.02)             /root/reference/src/stabilizer.cpp:675-708
+// FLANN's randomised KD-trees are approximate and not reproducible call to call; this
+// kernel returns the exact nearest neighbour, which equals cv::BFMatcher(NORM_L2).match 100 %:
+//   ||a_i - b_j||^2 = ||a_i||^2 + ||b_j||^2 - 2 a_i . b_j
+// SIFT descriptors are integers 0..255, exact in fp16; products <= 65025 and the
+// 128-term sums <= 8.4e6 < 2^24, so the fp32 accumulation in TMEM is exact and the squared
+// distances are exact integers.
+//
+// One CTA owns 128 reference rows.  A (128 x 128 fp16) is staged once, B tiles of 128 current rows
+// stream through shared memory, both K-major in the 128-byte swizzle the UMMA descriptors name.  One
+// elected thread issues 8 x tcgen05.mma (M128 N128 K16, kind::f16) per tile into a 128-column TMEM
+// accumulator, commits to an mbarrier; the four warps then read their 32-lane TMEM quarter with
+// tcgen05.ld and fold the tile into a running row-wise arg-min -- the distance matrix never
+// leaves the SM.
+#include <cuda_fp16.h>
+#include "kernels.h"
+
+namespace vstabk {
+namespace {
+
+constexpr int TM = 128, TN = 128, TK = 128;          // tile: reference rows, current rows, descriptor length
+constexpr int KB = 64;                                // fp16 elements per 128-byte swizzle row
+constexpr int kTileBytes = TM * KB * 2;               // one K-block of one operand tile: 16 KB
+
+VSTAB_D unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4, leading byte offset 0 (one swizzle atom along K), stride byte offset 1024 B (8 rows x 128 B)
+// >> 4, version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+VSTAB_D unsigned long long umma_desc(unsigned saddr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr >> 4) & 0x3fffu);
+    d |= (unsigned long long)((1024u >> 4) & 0x3fffu) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+
+// byte offset of element (row, k) inside one K-block tile [rows][64 fp16] with the 128-B swizzle:
+// 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
+VSTAB_D int swz_off(int row, int k) {
+    const int chunk = k >> 3;
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4) + (k & 7) * 2;
+}
+
+// Stage 128 descriptors (u8, 128 bytes each; rows >= n are zero) as fp16 into two swizzled K-block
+// tiles and return the squared norm of row `tid`.
+VSTAB_D int stage_tile(const uint8_t* __restrict__ desc, int row0, int n, unsigned char* smem_tile, int tid) {
+    // thread t converts row t: 128 bytes = 8 x uint4
+    const int row = row0 + tid;
+    int norm = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                      // 16 descriptor bytes -> 2 chunks of 8 fp16
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < n) v = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)row * TK) + c);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b0 = w[i] & 0xff, b1 = (w[i] >> 8) & 0xff, b2 = (w[i] >> 16) & 0xff, b3 = w[i] >> 24;
+            norm += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+            h[2 * i] = __halves2half2(__int2half_rn(b0), __int2half_rn(b1));
+            h[2 * i + 1] = __halves2half2(__int2half_rn(b2), __int2half_rn(b3));
+        }
+        const int k = c * 16;                          // first of the 16 elements
+        unsigned char* blk = smem_tile + (k / KB) * kTileBytes;
+        *reinterpret_cast<uint4*>(blk + swz_off(tid, k % KB)) = *reinterpret_cast<uint4*>(&h[0]);
+        *reinterpret_cast<uint4*>(blk + swz_off(tid, (k % KB) + 8)) = *reinterpret_cast<uint4*>(&h[4]);
+    }
+    return norm;
+}
+
+__global__ void __launch_bounds__(128, 1)
+l2_nn_kernel(const uint8_t* __restrict__ ref, const int* __restrict__ nref_p, int nref_max,
+             const uint8_t* __restrict__ cur, const int* __restrict__ ncur_p, int ncur_max,
+             int* __restrict__ best_idx, int* __restrict__ best_d2) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment (the launch reserves 1 KB of slack)
+    unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sA = smem;                         // 2 K-blocks x 16 KB
+    unsigned char* sB = smem + 2 * kTileBytes;        // 2 K-blocks x 16 KB
+    __shared__ int nb[TN];
+    __shared__ unsigned long long mbar;
+    __shared__ unsigned tmem_base_smem;
+    const int nref = min(*nref_p, nref_max), ncur = min(*ncur_p, ncur_max);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row0 = blockIdx.x * TM;
+    if (row0 >= nref) return;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"(TN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int na = stage_tile(ref, row0, nref, sA, tid);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_base_smem;
+
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N, M
+    const unsigned idesc = (1u << 4) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
+    int bd = 0x7fffffff, bi = -1;
+    unsigned phase = 0;
+    for (int j0 = 0; j0 < ncur; j0 += TN) {
+        nb[tid] = stage_tile(cur, j0, ncur, sB, tid);
+        // generic-proxy writes to shared memory must be visible to the tensor core (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < TK / 16; ++k) {                     // UMMA_K = 16 fp16 = 32 bytes
+                const unsigned koff = (unsigned)((k / 4) * kTileBytes + (k % 4) * 32);
+                const unsigned long long da = umma_desc(smem_addr(sA) + koff), db = umma_desc(smem_addr(sB) + koff);
+                const unsigned acc = k > 0 ? 1u : 0u;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                    "}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mbar)) : "memory");
+        }
+        // wait for the accumulator
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(smem_addr(&mbar)), "r"(phase) : "memory");
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: thread `tid` owns TMEM lane (= reference row) tid; warp w may touch lanes 32w..32w+31
+        const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+            unsigned r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr + (unsigned)c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int j = j0 + c0 + c;
+                const int dot = __float2int_rn(__uint_as_float(r[c]));          // exact integer
+                const int d2 = na + nb[c0 + c] - 2 * dot;
+                if (j < ncur && d2 < bd) { bd = d2; bi = j; }                   // ascending j, strict <: lowest index wins ties
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                  // TMEM and sB are free for the next tile
+    }
+    if (row0 + tid < nref) { best_idx[row0 + tid] = bi; best_d2[row0 + tid] = bd; }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TN) : "memory");
+}
+
+// distance filter of the reference (:680-697): d = sqrt(d2) as float (BFMatcher NORM_L2), mean over the
+// reference rows in double, keep d <= max(0.5 * mean, 0.02); then gather the point pairs in
+// reference order for the similarity fit.  Single CTA.
+__global__ void __launch_bounds__(256)
+l2_filter_kernel(const int* __restrict__ best_idx, const int* __restrict__ best_d2, const int* __restrict__ nref_p,
+                 int nref_max, const int* __restrict__ ncur_p, const OrbKeypoint* __restrict__ ref_kps,
+                 const OrbKeypoint* __restrict__ cur_kps, uint8_t* __restrict__ good, float2* __restrict__ ref_pts,
+                 float2* __restrict__ cur_pts, uint8_t* __restrict__ status, int* __restrict__ nmatch) {
+    __shared__ double wsum_d[8];
+    __shared__ int wsum[8];
+    __shared__ int s_base;
+    __shared__ double s_thr;
+    const int nref = min(*nref_p, nref_max);
+    const int ncur = *ncur_p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double acc = 0.0;
+    if (ncur > 0)
+        for (int i = threadIdx.x; i < nref; i += 256) acc += (double)__fsqrt_rn((float)best_d2[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) wsum_d[wid] = acc;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += wsum_d[k];
+        const double avg = nref > 0 ? t / (double)nref : 0.0;
+        s_thr = fmax(avg * 0.5, 0.02);
+    }
+    __syncthreads();
+    const double thr = s_thr;
+    for (int base = 0; base < nref; base += 256) {
+        const int i = base + threadIdx.x;
+        const bool g = i < nref && ncur > 0 && (double)__fsqrt_rn((float)best_d2[i]) <= thr;
+        if (i < nref && good) good[i] = g ? 1 : 0;
+        const unsigned ball = __ballot_sync(0xffffffffu, g);
+        if (lane == 0) wsum[wid] = __popc(ball);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < wid; ++k) off += wsum[k];
+        if (g && ref_pts) {
+            const int pos = off + __popc(ball & ((1u << lane) - 1u));
+            const OrbKeypoint a = ref_kps[i], b = cur_kps[best_idx[i]];
+            ref_pts[pos] = make_float2(a.x, a.y);
+            cur_pts[pos] = make_float2(b.x, b.y);
+            status[pos] = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += wsum[k]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && nmatch) *nmatch = s_base;
+}
+
+}  // namespace
+
+void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,
+                     const int* ncur, const OrbKeypoint* cur_kps, int max_kp, int* best_idx, int* best_d2, uint8_t* good,
+                     float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch, cudaStream_t st) {
+    static bool attr = false;
+    const int smem = 4 * kTileBytes + 1024;
+    if (!attr) {
+        cudaFuncSetAttribute(l2_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = true;
+    }
+    count_launch(2);
+    l2_nn_kernel<<<(max_kp + TM - 1) / TM, 128, smem, st>>>(ref_desc, nref, max_kp, cur_desc, ncur, max_kp, best_idx, best_d2);
+    l2_filter_kernel<<<1, 256, 0, st>>>(best_idx, best_d2, nref, max_kp, ncur, ref_kps, cur_kps, good, ref_pts, cur_pts, status,
+                                        nmatch);
+}
+
+}  // namespace vstabk

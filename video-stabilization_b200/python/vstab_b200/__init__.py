@@ -89,6 +89,7 @@ SYMBOLS = {
     "vstab_k_featprep": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_size_t, C.c_int, _vp]),
     "vstab_k_orb": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
     "vstab_k_hamming": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp]),
+    "vstab_k_l2match": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -353,3 +354,17 @@ def k_hamming(ref: np.ndarray, cur: np.ndarray, ratio: float = 0.6, device: int 
     bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); sd = np.zeros(n, np.int32); good = np.zeros(n, np.uint8)
     _check(lib.vstab_k_hamming(device, _ptr(ref), n, _ptr(cur), len(cur), ratio, _ptr(bi), _ptr(bd), _ptr(sd), _ptr(good)))
     return bi, bd, sd, good
+
+
+def k_l2match(ref: np.ndarray, cur: np.ndarray, device: int = 0):
+    """BFMatcher(NORM_L2).match(ref, cur) on tcgen05 + the reference's distance filter
+    -> (best_idx, best_d2 (exact squared distance), good).  Descriptors: integer valued [n,128]."""
+    lib = load_library()
+    ref8 = np.ascontiguousarray(ref).astype(np.uint8)
+    cur8 = np.ascontiguousarray(cur).astype(np.uint8)
+    if not (np.array_equal(ref8, ref) and np.array_equal(cur8, cur)):
+        raise ValueError("descriptors must be integers in 0..255")
+    n = len(ref8)
+    bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); good = np.zeros(n, np.uint8)
+    _check(lib.vstab_k_l2match(device, _ptr(ref8), n, _ptr(cur8), len(cur8), _ptr(bi), _ptr(bd), _ptr(good)))
+    return bi, bd, good
