@@ -230,6 +230,11 @@ vstab_status vstab_k_orb(int device, const uint8_t* gray, int rows, int cols, do
 vstab_status vstab_k_hamming(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur,
                              float ratio, int* best_idx, int* best_d, int* second_d, uint8_t* good);
 
+/* SIFT(2500, 3, 0.04, 5, 1.2).detectAndCompute (src/stabilizer.cpp:496-506, :614-615): kps_out 6 floats per
+ * keypoint {x, y, size, angle, response, packed octave (cv::KeyPoint::octave)}, sorted by (x, y); desc_out
+ * 128 bytes each (OpenCV stores the same integers as float). */
+vstab_status vstab_k_sift(int device, const uint8_t* gray, int rows, int cols, double size_ratio,
+                          float* kps_out, uint8_t* desc_out, int* n_out, int max_out);
 /* Exact L2 1-NN of SIFT descriptors (u8 [n][128]) on the tensor cores + the reference's distance filter
  * d <= max(0.5 * mean(d), 0.02) (src/stabilizer.cpp:675-697).  best_d2: exact squared distances. */
 vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur,

@@ -134,3 +134,41 @@ def test_l2_match_tcgen05_equals_bfmatcher(texture):
     for nr, nc in ((300, 77), (129, 1), (5, 2500)):
         bi, bd2, _ = vs.k_l2match(d0[:nr], d1[:nc])
         assert np.array_equal(bi, d2[:nr, :nc].argmin(1)) and np.array_equal(bd2, d2[:nr, :nc].min(1))
+
+
+def _sift_overlap(gray):
+    kps, desc = vs.k_sift(gray)
+    ckps, cdesc = cv2.SIFT_create(2500, 3, 0.04, 5, 1.2).detectAndCompute(gray, None)
+    mine = {}
+    for i, k in enumerate(kps):
+        mine.setdefault((int(k[5]) & 0xffff, round(float(k[0]), 1), round(float(k[1]), 1)), []).append(i)
+    hit, pos_err, ang_err, dsc_err = 0, [], [], []
+    for k, d in zip(ckps, cdesc):
+        best = None
+        for dx in (-0.1, 0.0, 0.1):
+            for dy in (-0.1, 0.0, 0.1):
+                for i in mine.get((k.octave & 0xffff, round(k.pt[0] + dx, 1), round(k.pt[1] + dy, 1)), []):
+                    e = max(abs(kps[i][0] - k.pt[0]), abs(kps[i][1] - k.pt[1]))
+                    a = abs((kps[i][3] - k.angle + 180.0) % 360.0 - 180.0)
+                    if e <= 0.05 and a <= 2.0 and (best is None or e + a < best[0]):
+                        best = (e + a, e, a, i)
+        if best is not None:
+            hit += 1
+            pos_err.append(best[1]); ang_err.append(best[2])
+            dsc_err.append(np.abs(desc[best[3]].astype(float) - d).mean())
+    return len(kps), len(ckps), hit, np.array(pos_err), np.array(ang_err), np.array(dsc_err)
+
+
+@pytest.mark.parametrize("W,H,wh", [(1280, 720, 360), (1920, 1080, 1080)])
+def test_sift_overlaps_opencv(texture, W, H, wh):
+    """K11 is a float pipeline and not bit-pinned: the keypoint set must overlap cv2's
+    (same octave/layer, position <= 0.05 px, orientation <= 2 deg) and matched descriptors must agree."""
+    frame = render_clip(texture, W, H, 1, start=7)[0]
+    gray = _cv_prep(frame, wh)
+    n, nc, hit, pe, ae, de = _sift_overlap(gray)
+    print(f"SIFT {W}x{H} wh{wh}: ours {n}, cv2 {nc}, matched {hit}, pos p99 {np.percentile(pe, 99):.4f}px, "
+          f"angle p99 {np.percentile(ae, 99):.3f}deg, mean |desc diff| {de.mean():.3f}")
+    assert abs(n - nc) <= 0.03 * nc
+    assert hit >= 0.95 * nc
+    assert np.percentile(pe, 99) <= 0.02 and np.percentile(ae, 99) <= 0.5
+    assert de.mean() <= 1.0                     # descriptor entries are 0..255

@@ -1178,3 +1178,38 @@ extern "C" vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref
     CK(cudaMemcpy(good, gd.p, (size_t)nref, cudaMemcpyDeviceToHost));
     return VSTAB_OK;
 }
+
+extern "C" vstab_status vstab_k_sift(int device, const uint8_t* gray, int rows, int cols, double size_ratio,
+                                     float* kps_out, uint8_t* desc_out, int* n_out, int max_out) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!gray || !kps_out || !desc_out || !n_out || max_out < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    SiftPlan* P = sift_plan_create(cols, rows, size_ratio, kOrbMaxKp, &g_err);
+    if (!P) return VSTAB_ERR_CUDA;
+    DevBuf img, kps, desc, cnt;
+    vstab_status st = VSTAB_OK;
+    auto fail = [&](const char* m) { g_err = m; st = VSTAB_ERR_CUDA; };
+    if (img.alloc((size_t)rows * cols) != cudaSuccess || kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp) != cudaSuccess ||
+        desc.alloc(128 * kOrbMaxKp) != cudaSuccess || cnt.alloc(sizeof(int)) != cudaSuccess) fail("cudaMalloc failed");
+    if (st == VSTAB_OK) {
+        cudaMemcpy(img.p, gray, (size_t)rows * cols, cudaMemcpyHostToDevice);
+        launch_sift(P, img.as<uint8_t>(), kps.as<OrbKeypoint>(), desc.as<uint8_t>(), cnt.as<int>(), 0);
+        int n = 0;
+        if (cudaMemcpy(&n, cnt.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) fail(cudaGetErrorString(cudaGetLastError()));
+        if (st == VSTAB_OK) {
+            if (n > kOrbMaxKp) n = kOrbMaxKp;
+            if (n > max_out) n = max_out;
+            *n_out = n;
+            std::vector<OrbKeypoint> h(n);
+            cudaMemcpy(h.data(), kps.p, sizeof(OrbKeypoint) * n, cudaMemcpyDeviceToHost);
+            cudaMemcpy(desc_out, desc.p, (size_t)128 * n, cudaMemcpyDeviceToHost);
+            for (int i = 0; i < n; ++i) {
+                float* o = kps_out + (size_t)i * 6;
+                o[0] = h[i].x; o[1] = h[i].y; o[2] = h[i].size; o[3] = h[i].angle; o[4] = h[i].response; o[5] = (float)h[i].octave;
+            }
+            if (cudaGetLastError() != cudaSuccess) fail("CUDA failure in vstab_k_sift");
+        }
+    }
+    sift_plan_destroy(P);
+    return st;
+}

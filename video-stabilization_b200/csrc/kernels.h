@@ -142,6 +142,28 @@ void launch_hamming_match(const uint8_t* ref_desc, const int* nref, const OrbKey
                           int* second_d, uint8_t* good, float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch,
                           cudaStream_t st);
 
+// ---------------------------------------------------------------- K11 SIFT
+constexpr int kSiftMaxOctaves = 12;
+struct SiftPlan {
+    int w = 0, h = 0, max_kp = 0, cand_cap = 0, kp_cap = 0;
+    float max_size = 0.f;                  // relative-size filter of the reference (0.05 * rows), 0 = off
+    size_t pyr_floats = 0, cub_bytes = 0;
+    int radii[8] = {};
+    void* octaves = nullptr;               // SiftOctaves (sift.cu)
+    void* mem = nullptr;
+    float* pyr = nullptr;
+    unsigned long long *cand = nullptr, *keys = nullptr, *keys_sorted = nullptr;
+    void* kps = nullptr;
+    int *idx = nullptr, *idx_sorted = nullptr, *counters = nullptr;
+    unsigned int *rkeys = nullptr, *rkeys_sorted = nullptr;
+    uint8_t* alive = nullptr;
+    void* cub_temp = nullptr;
+};
+SiftPlan* sift_plan_create(int w, int h, double size_ratio, int max_keypoints, std::string* err);
+void sift_plan_destroy(SiftPlan* P);
+// gray: device u8 w x h.  kps_out[max_kp] {x, y, size, angle, response, packed octave}, desc[max_kp][128] u8
+void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t* desc, int* count, cudaStream_t st);
+
 // ---------------------------------------------------------------- K12 exact L2 matcher (tcgen05)
 // descriptors: u8 [n][128] (SIFT descriptors are integers 0..255).  best_d2 = exact squared distances.
 void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,

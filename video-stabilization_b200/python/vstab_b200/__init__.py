@@ -90,6 +90,7 @@ SYMBOLS = {
     "vstab_k_orb": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
     "vstab_k_hamming": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp]),
     "vstab_k_l2match": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "vstab_k_sift": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
 }
 
 _lib = None
@@ -368,3 +369,15 @@ def k_l2match(ref: np.ndarray, cur: np.ndarray, device: int = 0):
     bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); good = np.zeros(n, np.uint8)
     _check(lib.vstab_k_l2match(device, _ptr(ref8), n, _ptr(cur8), len(cur8), _ptr(bi), _ptr(bd), _ptr(good)))
     return bi, bd, good
+
+
+def k_sift(gray: np.ndarray, size_ratio: float = 0.0, device: int = 0):
+    """SIFT(2500, 3, 0.04, 5, 1.2).detectAndCompute -> (kps [n,6] {x,y,size,angle,response,octave}, desc u8 [n,128])."""
+    lib = load_library()
+    gray = np.ascontiguousarray(gray)
+    kps = np.zeros((4096, 6), np.float32)
+    desc = np.zeros((4096, 128), np.uint8)
+    n = C.c_int(0)
+    _check(lib.vstab_k_sift(device, _ptr(gray), gray.shape[0], gray.shape[1], float(size_ratio), _ptr(kps), _ptr(desc),
+                            C.byref(n), 4096))
+    return kps[:n.value].copy(), desc[:n.value].copy()
