@@ -131,8 +131,6 @@ def test_api_errors(golden):
     st.stabilize_frame(clip[1])
     with pytest.raises(AssertionError):
         st.stabilize_frame(clip[2])
-    with pytest.raises(NotImplementedError):
-        st.set_stabilization_mode(vs.SIFT_FULL_LOCK)
     with pytest.raises(ValueError):
         st.set_stabilization_mode(7)
     st.close()
@@ -225,3 +223,32 @@ def test_orb_lock_keeps_previous_h_on_failure(texture):
         assert cnt[0] < 10 and cnt[4] == 0
         assert np.array_equal(st.tap(vs.TAP_LOCK_H), h_before)
     st.close()
+
+
+@pytest.mark.parametrize("W,H,wh,n", [(1280, 720, 360, 18), (1920, 1080, 1080, 13)])
+def test_sift_full_lock_matches_oracle(texture, W, H, wh, n):
+    """BASELINE config 4 (shortened, 1080p): SIFT registration to the reference frame.  The oracle runs the
+    reference's control flow with the exact L2 matcher (FLANN is approximate and not reproducible call to
+    call); parity is at the homography level: <= 0.1 px at the frame corners."""
+    frames = render_clip(texture, W, H, n)
+    P, F, switch = 6, 4, 8
+    ref = sr.StabilizerRef(P, F, wh, exact_sift_matcher=True)
+    st = vs.Stabilizer(P, F, wh)
+    worst_h = 0.0
+    for i, f in enumerate(frames):
+        if i == switch:
+            ref.set_stabilization_mode(sr.SIFT_FULL_LOCK)
+            st.set_stabilization_mode(vs.SIFT_FULL_LOCK)
+        ref.stabilize_frame(f)
+        st.stabilize_frame(f)
+        if i < switch:
+            continue
+        cnt = st.tap(vs.TAP_ORB_COUNTS)
+        assert abs(int(cnt[1]) - len(ref.ref_kps)) <= 0.03 * len(ref.ref_kps) and cnt[1] > 300
+        if i > switch:
+            assert cnt[4] == 1
+            assert abs(int(cnt[2]) - ref.taps.n_matches) <= 0.05 * ref.taps.n_matches + 5
+        worst_h = max(worst_h, _corner_diff(st.tap(vs.TAP_H_SCALED), ref.taps.H_scaled, W, H))
+    st.close()
+    print(f"SIFT lock {W}x{H} wh{wh}: worst corner difference {worst_h:.4f} px")
+    assert worst_h <= H_TOL_PX

@@ -171,6 +171,7 @@ struct vstab {
     // ORB registration state (reference: referenceGray_/Keypoints_/Descriptors_, hpp:447-456, and the
     // function-static previouslyReturnedH, cpp:446 -- per instance here)
     OrbPlan* orb = nullptr;
+    SiftPlan* sift = nullptr;
     bool has_reference = false;
     DevBuf feat_ws, feat_gray, nn_x, nn_y, ref_kps, ref_desc, cur_kps, cur_desc, orb_counts, m_idx, m_d0, m_d1, m_good,
         m_ref, m_cur, m_status, lock_fit, lock_h, lock_tap;
@@ -250,16 +251,15 @@ static vstab_status stream_estimate(vstab* s) {
     return VSTAB_OK;
 }
 
-// calculateFullLockStabilization, ORB branch (stabilizer.cpp:440-787) for presentation frame p, on
+// calculateFullLockStabilization, ORB / SIFT branch (stabilizer.cpp:440-787) for presentation frame p, on
 // the output stream: condition the full-resolution frame, detect + describe, and either capture the
 // reference (first call after setStabilizationMode) or match against it and fit.
-static vstab_status stream_orb_lock(vstab* s, long p) {
+static vstab_status stream_feature_lock(vstab* s, long p) {
     auto set_err = [&](const std::string& e) { s->err = e; };
     Geometry& g = s->g;
     cudaStream_t q = s->out_stream;
-    if (!s->orb) {
-        s->orb = orb_plan_create(g.ww, g.wh, 0.10, kOrbMaxKp, &s->err);      // MAX_KEYPOINT_RELATIVE_SIZE_ORB, :493
-        if (!s->orb) return VSTAB_ERR_CUDA;
+    const bool is_orb = s->mode == VSTAB_ORB_FULL_LOCK;
+    if (!s->feat_ws.p) {
         std::vector<int> xo(g.ww), yo(g.wh);
         build_nn_table(g.cols, g.ww, xo.data());
         build_nn_table(g.rows, g.wh, yo.data());
@@ -269,7 +269,7 @@ static vstab_status stream_orb_lock(vstab* s, long p) {
         CK(cudaMemcpy(s->nn_x.p, xo.data(), sizeof(int) * g.ww, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s->nn_y.p, yo.data(), sizeof(int) * g.wh, cudaMemcpyHostToDevice));
         CK(s->ref_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(s->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp));
-        CK(s->ref_desc.alloc(32 * kOrbMaxKp)); CK(s->cur_desc.alloc(32 * kOrbMaxKp));
+        CK(s->ref_desc.alloc(128 * kOrbMaxKp)); CK(s->cur_desc.alloc(128 * kOrbMaxKp));   // 32 B (ORB) or 128 B (SIFT) per row
         CK(s->orb_counts.alloc(sizeof(int) * 4));                            // {nref, ncur, nmatch}
         CK(s->m_idx.alloc(4 * kOrbMaxKp)); CK(s->m_d0.alloc(4 * kOrbMaxKp)); CK(s->m_d1.alloc(4 * kOrbMaxKp));
         CK(s->m_good.alloc(kOrbMaxKp)); CK(s->m_status.alloc(kOrbMaxKp));
@@ -279,22 +279,40 @@ static vstab_status stream_orb_lock(vstab* s, long p) {
         CK(s->lock_tap.alloc(sizeof(int) * 8));
         CK(cudaMemsetAsync(s->orb_counts.p, 0, sizeof(int) * 4, q));
     }
+    if (is_orb && !s->orb) {
+        s->orb = orb_plan_create(g.ww, g.wh, 0.10, kOrbMaxKp, &s->err);      // MAX_KEYPOINT_RELATIVE_SIZE_ORB, :493
+        if (!s->orb) return VSTAB_ERR_CUDA;
+    }
+    if (!is_orb && !s->sift) {
+        s->sift = sift_plan_create(g.ww, g.wh, 0.05, kOrbMaxKp, &s->err);    // MAX_KEYPOINT_RELATIVE_SIZE_SIFT, :507
+        if (!s->sift) return VSTAB_ERR_CUDA;
+    }
     const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)(p % s->W) * g.frame_bytes;           // :444
     launch_featprep(frame, g.pitch, s->nn_x.as<int>(), s->nn_y.as<int>(), g.ww, g.wh, s->feat_ws.p,
                     s->feat_gray.as<uint8_t>(), q);                                                // :448-477
     int* counts = s->orb_counts.as<int>();
     double* Tfit = s->lock_fit.as<double>();
     int* fitc = reinterpret_cast<int*>(Tfit + 16);
-    if (!s->has_reference) {                                                                     // :520-589
-        launch_orb(s->orb, s->feat_gray.as<uint8_t>(), s->ref_kps.as<OrbKeypoint>(), s->ref_desc.as<uint8_t>(), counts + 0, true, q);
+    const bool capture = !s->has_reference;                                                      // :520-589
+    OrbKeypoint* kps = capture ? s->ref_kps.as<OrbKeypoint>() : s->cur_kps.as<OrbKeypoint>();
+    uint8_t* desc = capture ? s->ref_desc.as<uint8_t>() : s->cur_desc.as<uint8_t>();
+    int* cnt = counts + (capture ? 0 : 1);
+    if (is_orb) launch_orb(s->orb, s->feat_gray.as<uint8_t>(), kps, desc, cnt, capture, q);      // :557-559 / :604-612
+    else launch_sift(s->sift, s->feat_gray.as<uint8_t>(), kps, desc, cnt, q);                    // :572-574 / :614-621
+    if (capture) {
         launch_lock_update(Tfit, fitc, counts + 0, counts + 0, counts + 0, 1, s->lock_h.as<double>(), s->lock_tap.as<int>(), q);
         s->has_reference = true;
     } else {
-        launch_orb(s->orb, s->feat_gray.as<uint8_t>(), s->cur_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(), counts + 1, false, q);  // :604-612
-        launch_hamming_match(s->ref_desc.as<uint8_t>(), counts + 0, s->ref_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(),
-                             counts + 1, s->cur_kps.as<OrbKeypoint>(), kOrbMaxKp, 0.6f, s->m_idx.as<int>(), s->m_d0.as<int>(),
-                             s->m_d1.as<int>(), s->m_good.as<uint8_t>(), s->m_ref.as<float2>(), s->m_cur.as<float2>(),
-                             s->m_status.as<uint8_t>(), counts + 2, q);                            // :647-673, :711-716
+        if (is_orb)
+            launch_hamming_match(s->ref_desc.as<uint8_t>(), counts + 0, s->ref_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(),
+                                 counts + 1, s->cur_kps.as<OrbKeypoint>(), kOrbMaxKp, 0.6f, s->m_idx.as<int>(), s->m_d0.as<int>(),
+                                 s->m_d1.as<int>(), s->m_good.as<uint8_t>(), s->m_ref.as<float2>(), s->m_cur.as<float2>(),
+                                 s->m_status.as<uint8_t>(), counts + 2, q);                        // :647-673, :711-716
+        else
+            launch_l2_match(s->ref_desc.as<uint8_t>(), counts + 0, s->ref_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(),
+                            counts + 1, s->cur_kps.as<OrbKeypoint>(), kOrbMaxKp, s->m_idx.as<int>(), s->m_d0.as<int>(),
+                            s->m_good.as<uint8_t>(), s->m_ref.as<float2>(), s->m_cur.as<float2>(), s->m_status.as<uint8_t>(),
+                            counts + 2, q);                                                        // :675-708, :711-716
         launch_fit_large(s->m_ref.as<float2>(), s->m_cur.as<float2>(), s->m_status.as<uint8_t>(), counts + 2, 5.0,
                          g.ww / 2.0, g.wh / 2.0, Tfit, Tfit + 9, fitc, q);                         // :734-758
         launch_lock_update(Tfit, fitc, counts + 0, counts + 1, counts + 2, 0, s->lock_h.as<double>(), s->lock_tap.as<int>(), q);  // :784-787
@@ -316,8 +334,9 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
         s->acc_valid = true;
         s->acc_to = p;
     }
-    if (s->mode == VSTAB_ORB_FULL_LOCK) {
-        vstab_status st = stream_orb_lock(s, p);
+    const bool feature_lock = s->mode == VSTAB_ORB_FULL_LOCK || s->mode == VSTAB_SIFT_FULL_LOCK;
+    if (feature_lock) {
+        vstab_status st = stream_feature_lock(s, p);
         if (st != VSTAB_OK) return st;
     }
     SmoothArgs a{};
@@ -325,7 +344,7 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
     a.P = (int)s->P; a.F = (int)s->F;
     a.mode = s->mode; a.lock_call = s->lock_call;
     a.acc = s->acc.as<double>(); a.acc_mod = 0;
-    a.lock_h = s->mode == VSTAB_ORB_FULL_LOCK ? s->lock_h.as<double>() : nullptr;
+    a.lock_h = feature_lock ? s->lock_h.as<double>() : nullptr;
     a.scale = g.scale;
     a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
     a.npix = (double)g.rows * (double)g.cols;
@@ -458,16 +477,13 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_fit) cudaEventDestroy(s->ev_fit);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
     if (s->orb) orb_plan_destroy(s->orb);
+    if (s->sift) sift_plan_destroy(s->sift);
     delete s;
 }
 
 vstab_status vstab_set_mode(vstab_t* s, int mode) {
     if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
     if (mode < 0 || mode > 5) { s->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
-    if (mode == VSTAB_SIFT_FULL_LOCK) {
-        s->err = "SIFT registration mode is not built yet (DESIGN.md, SURVEY 8a rows a14-a15)";
-        return VSTAB_ERR_UNSUPPORTED;
-    }
     // stabilizer.cpp:55-70: reset reference + accumulator, keep window / prevGray_ / prevPoints_
     s->has_reference = false;
     s->acc_valid = false;
