@@ -183,6 +183,19 @@ vstab_status vstab_offline_prepare(vstab_offline_t* o, const double* d_T_all, lo
 vstab_status vstab_offline_run_host(vstab_offline_t* o, const uint8_t* frames, size_t frame_stride,
                                     size_t step, long n_total, int mode, long lock_call,
                                     uint8_t* out, size_t out_frame_stride, size_t out_step);
+/* ORB_FULL_LOCK / SIFT_FULL_LOCK offline: the owner of the anchor frame (the presentation frame
+ * of the call at which the mode was set, src/stabilizer.cpp:520-589) captures the reference set and exports
+ * it as one packed device buffer of vstab_offline_reference_bytes() bytes; the caller broadcasts it and
+ * the other ranks import it.  Every rank then registers its own frames (independent units) into
+ * d_reg[n][10] = {matrix[9], valid}; after the all-gather of those, vstab_offline_set_registrations +
+ * vstab_offline_render apply the reference's "previously returned H" carry (:446) as a backward scan. */
+size_t vstab_offline_reference_bytes(void);
+vstab_status vstab_offline_reference_capture(vstab_offline_t* o, const uint8_t* d_frame, size_t step, int mode);
+vstab_status vstab_offline_reference_export(vstab_offline_t* o, void* d_pack);
+vstab_status vstab_offline_reference_import(vstab_offline_t* o, const void* d_pack, int mode);
+vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride, size_t step,
+                                    int n, double* d_reg);
+vstab_status vstab_offline_set_registrations(vstab_offline_t* o, const double* d_reg_all, long n_total);
 vstab_status vstab_offline_synchronize(vstab_offline_t* o);
 /* per-stage device time (CUDA events on the instance stream) accumulated since the last call:
  * ms[8]/counts[8] = ingest, pyramid, gftt, lk, fit, smooth, warp, acc-scan */

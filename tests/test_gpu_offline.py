@@ -132,3 +132,56 @@ def test_run_host_equals_streaming(texture_small, lock_at):
             assert np.array_equal(out[c], want[c]), c
         out[:] = 0
     off.close()
+
+
+@pytest.mark.parametrize("mode", [vs.ORB_FULL_LOCK, vs.SIFT_FULL_LOCK])
+@pytest.mark.parametrize("shards", [[(0, 20)], [(0, 9), (9, 20)]])
+def test_offline_feature_lock_equals_streaming(texture_small, mode, shards):
+    """ORB / SIFT registration offline (reference broadcast + independent per-frame registration + gathered
+    {H, valid} + carry scan) == the streaming calls, bit for bit, across a shard boundary."""
+    W, H, wh, P, F, lock_at, n_total = 640, 360, 360, 5, 3, 6, 20
+    frames, _ = _dev_clip(texture_small, W, H, n_total)
+    f_np = frames.cpu().numpy()
+    st = vs.Stabilizer(P, F, wh)
+    want, want_H = [], []
+    for i, f in enumerate(f_np):
+        if i == lock_at:
+            st.set_stabilization_mode(mode)
+        want.append(st.stabilize_frame(f))
+        want_H.append(st.tap(vs.TAP_H_SCALED) if i else np.eye(3))
+    st.close()
+    anchor = max(0, lock_at - F)
+    runners, T_parts, sums_parts, reg_parts = [], [], [], []
+    pack = None
+    for (first, last) in shards:
+        off = offline.OfflineStabilizer(P, F, wh, H, W, 32)
+        T = torch.zeros((last - first, 9), dtype=torch.float64, device="cuda")
+        sums = torch.zeros((last - first, 3), dtype=torch.int64, device="cuda")
+        off.estimate(frames[first:last], first, frames[first - 1] if first else None, T, sums)
+        if first <= anchor < last:
+            off.capture_reference(frames[anchor], mode)
+            pack = off.export_reference()
+        runners.append(off); T_parts.append(T); sums_parts.append(sums)
+    for (first, last), off in zip(shards, runners):
+        if not (first <= anchor < last):
+            off.import_reference(pack, mode)                  # the "broadcast"
+        reg = torch.zeros((last - first, 10), dtype=torch.float64, device="cuda")
+        off.register(frames[first:last], reg)
+        off.synchronize()
+        reg_parts.append(reg)
+    T_all, reg_all = torch.cat(T_parts, 0), torch.cat(reg_parts, 0)     # the "all-gather"
+    assert float(reg_all[anchor + 1:, 9].min()) == 1.0
+    for (first, last), sums, off in zip(shards, sums_parts, runners):
+        c0, c1 = offline.calls_of_shard(first, last, n_total, F)
+        out = torch.empty((c1 - c0, H, W, 3), dtype=torch.uint8, device="cuda")
+        off.set_registrations(reg_all)
+        off.prepare(T_all, mode, lock_at)
+        off.render(frames[first:last], first, c0, c1 - c0, T_all, mode, lock_at, sums, out)
+        hs = off.read_h(c1 - c0)
+        o = out.cpu().numpy()
+        for j in range(c1 - c0):
+            c = c0 + j
+            if c:
+                assert np.array_equal(hs[j], want_H[c]), c
+            assert np.array_equal(o[j], want[c]), c
+        off.close()

@@ -620,11 +620,142 @@ struct vstab_offline {
     DevBuf clip, outbuf, clipT, clipSums;
     size_t clip_frames = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // ORB / SIFT registration (offline): reference set, per-launch scratch, gathered registrations
+    OrbPlan* orb = nullptr;
+    SiftPlan* sift = nullptr;
+    int ref_mode = -1;
+    DevBuf feat_ws, feat_gray, nn_x, nn_y, ref_pack, cur_kps, cur_desc, f_counts, m_idx, m_d0, m_d1, m_good, m_ref, m_cur,
+        m_status, lock_fit;
+    const double* reg_all = nullptr;
+    long reg_n = 0;
     std::string err;
     void set_err(const std::string& e) { err = e; }
 };
 
+// packed reference set: {int count, pad to 16 B} {OrbKeypoint[kOrbMaxKp]} {u8 desc[kOrbMaxKp][128]}
+static constexpr size_t kRefPackKps = 16;
+static constexpr size_t kRefPackDesc = kRefPackKps + sizeof(OrbKeypoint) * kOrbMaxKp;
+static constexpr size_t kRefPackBytes = kRefPackDesc + (size_t)128 * kOrbMaxKp;
+
+static vstab_status offline_feature_setup(vstab_offline* o, int mode) {
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    Geometry& g = o->g;
+    if (mode != VSTAB_ORB_FULL_LOCK && mode != VSTAB_SIFT_FULL_LOCK) { o->err = "mode must be ORB_FULL_LOCK or SIFT_FULL_LOCK"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (!o->feat_ws.p) {
+        std::vector<int> xo(g.ww), yo(g.wh);
+        build_nn_table(g.cols, g.ww, xo.data());
+        build_nn_table(g.rows, g.wh, yo.data());
+        CK(o->feat_ws.alloc(featprep_workspace_bytes(g.ww, g.wh)));
+        CK(o->feat_gray.alloc((size_t)g.ww * g.wh));
+        CK(o->nn_x.alloc(sizeof(int) * g.ww)); CK(o->nn_y.alloc(sizeof(int) * g.wh));
+        CK(cudaMemcpy(o->nn_x.p, xo.data(), sizeof(int) * g.ww, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(o->nn_y.p, yo.data(), sizeof(int) * g.wh, cudaMemcpyHostToDevice));
+        CK(o->ref_pack.alloc(kRefPackBytes));
+        CK(o->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(o->cur_desc.alloc(128 * kOrbMaxKp));
+        CK(o->f_counts.alloc(sizeof(int) * 4));
+        CK(o->m_idx.alloc(4 * kOrbMaxKp)); CK(o->m_d0.alloc(4 * kOrbMaxKp)); CK(o->m_d1.alloc(4 * kOrbMaxKp));
+        CK(o->m_good.alloc(kOrbMaxKp)); CK(o->m_status.alloc(kOrbMaxKp));
+        CK(o->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(o->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
+        CK(o->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));
+        CK(cudaMemset(o->ref_pack.p, 0, kRefPackBytes));
+    }
+    if (mode == VSTAB_ORB_FULL_LOCK && !o->orb) { o->orb = orb_plan_create(g.ww, g.wh, 0.10, kOrbMaxKp, &o->err); if (!o->orb) return VSTAB_ERR_CUDA; }
+    if (mode == VSTAB_SIFT_FULL_LOCK && !o->sift) { o->sift = sift_plan_create(g.ww, g.wh, 0.05, kOrbMaxKp, &o->err); if (!o->sift) return VSTAB_ERR_CUDA; }
+    return VSTAB_OK;
+}
+
 extern "C" {
+
+size_t vstab_offline_reference_bytes(void) { return kRefPackBytes; }
+
+// Reference capture (stabilizer.cpp:520-589) from the anchor frame (the presentation frame of the call at
+// which the mode was set); the owner of that frame calls this, exports the packed set, and the other
+// ranks import it after the broadcast.
+vstab_status vstab_offline_reference_capture(vstab_offline_t* o, const uint8_t* d_frame, size_t step, int mode) {
+    if (!o || !d_frame) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    CK(cudaSetDevice(o->device));
+    vstab_status st = offline_feature_setup(o, mode);
+    if (st != VSTAB_OK) return st;
+    Geometry& g = o->g;
+    cudaStream_t q = o->stream;
+    char* pack = o->ref_pack.as<char>();
+    launch_featprep(d_frame, step, o->nn_x.as<int>(), o->nn_y.as<int>(), g.ww, g.wh, o->feat_ws.p, o->feat_gray.as<uint8_t>(), q);
+    if (mode == VSTAB_ORB_FULL_LOCK)
+        launch_orb(o->orb, o->feat_gray.as<uint8_t>(), (OrbKeypoint*)(pack + kRefPackKps), (uint8_t*)(pack + kRefPackDesc), (int*)pack, true, q);
+    else
+        launch_sift(o->sift, o->feat_gray.as<uint8_t>(), (OrbKeypoint*)(pack + kRefPackKps), (uint8_t*)(pack + kRefPackDesc), (int*)pack, q);
+    CK(cudaGetLastError());
+    o->ref_mode = mode;
+    return VSTAB_OK;
+}
+
+vstab_status vstab_offline_reference_export(vstab_offline_t* o, void* d_pack) {
+    if (!o || !d_pack || !o->ref_pack.p) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    CK(cudaSetDevice(o->device));
+    CK(cudaMemcpyAsync(d_pack, o->ref_pack.p, kRefPackBytes, cudaMemcpyDeviceToDevice, o->stream));
+    return VSTAB_OK;
+}
+
+vstab_status vstab_offline_reference_import(vstab_offline_t* o, const void* d_pack, int mode) {
+    if (!o || !d_pack) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    CK(cudaSetDevice(o->device));
+    vstab_status st = offline_feature_setup(o, mode);
+    if (st != VSTAB_OK) return st;
+    CK(cudaMemcpyAsync(o->ref_pack.p, d_pack, kRefPackBytes, cudaMemcpyDeviceToDevice, o->stream));
+    o->ref_mode = mode;
+    return VSTAB_OK;
+}
+
+// Register frames d_frames[0..n) against the reference set (stabilizer.cpp:604-787 without the carry):
+// d_reg[i] = {inverse(H with scale forced to 1) [9], valid} -- identity / 0 when the reference would have
+// returned its previous matrix.
+vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride, size_t step, int n,
+                                    double* d_reg) {
+    if (!o || !d_frames || !d_reg || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    if (o->ref_mode != VSTAB_ORB_FULL_LOCK && o->ref_mode != VSTAB_SIFT_FULL_LOCK) { o->err = "no reference set: call vstab_offline_reference_capture / _import first"; return VSTAB_ERR_STATE; }
+    CK(cudaSetDevice(o->device));
+    Geometry& g = o->g;
+    cudaStream_t q = o->stream;
+    char* pack = o->ref_pack.as<char>();
+    const int* nref = (const int*)pack;
+    const OrbKeypoint* ref_kps = (const OrbKeypoint*)(pack + kRefPackKps);
+    const uint8_t* ref_desc = (const uint8_t*)(pack + kRefPackDesc);
+    int* counts = o->f_counts.as<int>();
+    double* Tfit = o->lock_fit.as<double>();
+    int* fitc = reinterpret_cast<int*>(Tfit + 16);
+    for (int i = 0; i < n; ++i) {
+        const uint8_t* frame = d_frames + (size_t)i * frame_stride;
+        launch_featprep(frame, step, o->nn_x.as<int>(), o->nn_y.as<int>(), g.ww, g.wh, o->feat_ws.p, o->feat_gray.as<uint8_t>(), q);
+        if (o->ref_mode == VSTAB_ORB_FULL_LOCK) {
+            launch_orb(o->orb, o->feat_gray.as<uint8_t>(), o->cur_kps.as<OrbKeypoint>(), o->cur_desc.as<uint8_t>(), counts + 1, false, q);
+            launch_hamming_match(ref_desc, nref, ref_kps, o->cur_desc.as<uint8_t>(), counts + 1, o->cur_kps.as<OrbKeypoint>(), kOrbMaxKp,
+                                 0.6f, o->m_idx.as<int>(), o->m_d0.as<int>(), o->m_d1.as<int>(), o->m_good.as<uint8_t>(),
+                                 o->m_ref.as<float2>(), o->m_cur.as<float2>(), o->m_status.as<uint8_t>(), counts + 2, q);
+        } else {
+            launch_sift(o->sift, o->feat_gray.as<uint8_t>(), o->cur_kps.as<OrbKeypoint>(), o->cur_desc.as<uint8_t>(), counts + 1, q);
+            launch_l2_match(ref_desc, nref, ref_kps, o->cur_desc.as<uint8_t>(), counts + 1, o->cur_kps.as<OrbKeypoint>(), kOrbMaxKp,
+                            o->m_idx.as<int>(), o->m_d0.as<int>(), o->m_good.as<uint8_t>(), o->m_ref.as<float2>(),
+                            o->m_cur.as<float2>(), o->m_status.as<uint8_t>(), counts + 2, q);
+        }
+        launch_fit_large(o->m_ref.as<float2>(), o->m_cur.as<float2>(), o->m_status.as<uint8_t>(), counts + 2, 5.0, g.ww / 2.0,
+                         g.wh / 2.0, Tfit, Tfit + 9, fitc, q);
+        launch_reg_store(Tfit, fitc, nref, counts + 1, counts + 2, d_reg + (size_t)i * 10, q);
+    }
+    CK(cudaGetLastError());
+    return VSTAB_OK;
+}
+
+// All registrations of the clip ({H[9], valid} per frame, e.g. after the all-gather) for vstab_offline_render
+// in ORB_FULL_LOCK / SIFT_FULL_LOCK.
+vstab_status vstab_offline_set_registrations(vstab_offline_t* o, const double* d_reg_all, long n_total) {
+    if (!o) return VSTAB_ERR_INVALID_ARGUMENT;
+    o->reg_all = d_reg_all; o->reg_n = n_total;
+    return VSTAB_OK;
+}
 
 vstab_status vstab_offline_create(size_t past_frames, size_t future_frames, int working_height, int rows, int cols,
                                   int max_batch, int device, vstab_offline_t** out) {
@@ -666,6 +797,8 @@ void vstab_offline_destroy(vstab_offline_t* o) {
     if (o->stream) { cudaStreamSynchronize(o->stream); cudaStreamDestroy(o->stream); }
     if (o->copy_in) { cudaStreamSynchronize(o->copy_in); cudaStreamDestroy(o->copy_in); }
     if (o->copy_out) { cudaStreamSynchronize(o->copy_out); cudaStreamDestroy(o->copy_out); }
+    if (o->orb) orb_plan_destroy(o->orb);
+    if (o->sift) sift_plan_destroy(o->sift);
     delete o;
 }
 
@@ -752,8 +885,12 @@ extern "C" vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* 
     if (!o || !d_frames || !d_T_all || !d_out || !d_sums || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
     auto set_err = [&](const std::string& e) { o->err = e; };
     if (n > o->max_batch + 1) { o->err = "n exceeds max_batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
-    if (mode != VSTAB_GLOBAL_SMOOTHING && mode != VSTAB_ACCUMULATED_FULL_LOCK && mode != VSTAB_TRANSLATION_LOCK &&
-        mode != VSTAB_ROTATION_LOCK) { o->err = "mode not supported offline"; return VSTAB_ERR_UNSUPPORTED; }
+    if (mode < 0 || mode > 5) { o->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    const bool feature_lock = mode == VSTAB_ORB_FULL_LOCK || mode == VSTAB_SIFT_FULL_LOCK;
+    if (feature_lock && (!o->reg_all || o->reg_n != n_total)) {
+        o->err = "call vstab_offline_set_registrations(d_reg_all, n_total) before rendering in ORB / SIFT lock";
+        return VSTAB_ERR_STATE;
+    }
     if (mode == VSTAB_ACCUMULATED_FULL_LOCK && lock_call < (long)o->F) {
         o->err = "ACCUMULATED_FULL_LOCK must be set at a call index >= future (SURVEY B.6)"; return VSTAB_ERR_STATE;
     }
@@ -772,6 +909,8 @@ extern "C" vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* 
     a.P = (int)o->P; a.F = (int)o->F;
     a.mode = mode; a.lock_call = lock_call;
     a.acc = o->acc.as<double>(); a.acc_mod = n_total;
+    a.reg = feature_lock ? o->reg_all : nullptr;
+    a.reg_lo = lock_call + 1 - (long)o->F > 0 ? lock_call + 1 - (long)o->F : 0;
     a.scale = g.scale;
     a.sums = d_sums; a.sums_mod = 0; a.frame_base = frame_base;
     a.npix = (double)g.rows * (double)g.cols;

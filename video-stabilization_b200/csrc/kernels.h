@@ -87,6 +87,8 @@ struct SmoothArgs {
     const double* acc;           // optional precomputed accumulated products by abs frame idx (offline), mod acc_mod
     long acc_mod;
     const double* lock_h;        // ORB / SIFT registration matrix (9 doubles, device) or null
+    const double* reg;           // offline ORB / SIFT: per frame {H[9], valid} by absolute frame index, or null
+    long reg_lo;                 // first frame a call after lock_call can present (lower end of the carry scan)
     double scale;                // workingHeight / rows
     const unsigned long long* sums;   // [slot][3] channel sums by frame slot
     long sums_mod;               // slot = abs frame % sums_mod   (ring) or abs - frame_base (offline: see frame_base)
@@ -97,6 +99,9 @@ void launch_smooth(const SmoothArgs& a, long call_first, int ncalls, WarpParams*
 // ORB / SIFT registration: fold one fit result into the "previously returned H" state (:724-787)
 void launch_lock_update(const double* Tfit, const int* fit_counts, const int* nref, const int* ncur, const int* nmatch,
                         int reset, double* lock_h, int* tap, cudaStream_t st);
+// offline ORB / SIFT: fold one fit result into reg[10] = {inverse(T), valid} (no carry: the carry is a scan at render time)
+void launch_reg_store(const double* Tfit, const int* fit_counts, const int* nref, const int* ncur, const int* nmatch,
+                      double* reg, cudaStream_t st);
 // streaming ACCUMULATED_FULL_LOCK state update: acc <- T[p] * acc (src/stabilizer.cpp:334)
 void launch_acc_update(const double* T, long t_mod, long p, int reset, double* acc_state, cudaStream_t st);
 // offline: acc[k] for k in [a, a+n): acc[a] = I, acc[k] = T[k] * acc[k-1]

@@ -70,7 +70,7 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
 
     // ---- full-lock transform -------------------------------------------------------------
     int mode = a.mode;
-    if (mode == 0 /*ACCUMULATED_FULL_LOCK*/ && c < a.lock_call) mode = 5;   // lock not yet set at this call
+    if ((mode == 0 || mode == 1 || mode == 2) && c < a.lock_call) mode = 5;   // lock not yet set at this call
     double Hl[9];
     eye3(Hl);
     if (mode == 0) {
@@ -79,7 +79,15 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
         HParams hp;
         if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
     }
-    if ((mode == 1 || mode == 2) && a.lock_h) {           // ORB / SIFT registration (:440-787)
+    if ((mode == 1 || mode == 2) && a.reg) {
+        // offline: the matrix returned at call c is the registration of the latest presented frame that
+        // produced one (the reference's "previously returned H" carry, :446), identity at the capture call
+        if (c > a.lock_call)
+            for (long q = p; q >= a.reg_lo; --q)
+                if (a.reg[(size_t)q * 10 + 9] != 0.0) { for (int i = 0; i < 9; ++i) Hl[i] = a.reg[(size_t)q * 10 + i]; break; }
+        HParams hp;
+        if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
+    } else if ((mode == 1 || mode == 2) && a.lock_h) {    // ORB / SIFT registration (:440-787)
         for (int i = 0; i < 9; ++i) Hl[i] = a.lock_h[i];
         HParams hp;
         if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
@@ -129,6 +137,19 @@ __global__ void lock_update_kernel(const double* __restrict__ Tfit, const int* _
     if (ok) ok = invert3(Tfit, inv) && finite9(inv);
     if (ok) for (int i = 0; i < 9; ++i) lock_h[i] = inv[i];
     if (tap) { tap[0] = *ncur; tap[1] = *nref; tap[2] = *nmatch; tap[3] = fit_counts[1]; tap[4] = ok ? 1 : 0; }
+}
+
+__global__ void reg_store_kernel(const double* __restrict__ Tfit, const int* __restrict__ fit_counts,
+                                 const int* __restrict__ nref, const int* __restrict__ ncur,
+                                 const int* __restrict__ nmatch, double* __restrict__ reg) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool ok = *ncur >= kMinPointsForMotion && *nref >= kMinPointsForMotion && *nmatch >= kMinPointsForMotion &&
+              fit_counts[1] > 0;
+    double inv[9];
+    if (ok) ok = invert3(Tfit, inv) && finite9(inv);
+    if (!ok) eye3(inv);
+    for (int i = 0; i < 9; ++i) reg[i] = inv[i];
+    reg[9] = ok ? 1.0 : 0.0;
 }
 
 // acc <- T[p] * acc   (or identity on the first call after setStabilizationMode)
@@ -201,6 +222,12 @@ void launch_lock_update(const double* Tfit, const int* fit_counts, const int* nr
                         int reset, double* lock_h, int* tap, cudaStream_t st) {
     count_launch(1);
     lock_update_kernel<<<1, 32, 0, st>>>(Tfit, fit_counts, nref, ncur, nmatch, reset, lock_h, tap);
+}
+
+void launch_reg_store(const double* Tfit, const int* fit_counts, const int* nref, const int* ncur, const int* nmatch,
+                      double* reg, cudaStream_t st) {
+    count_launch(1);
+    reg_store_kernel<<<1, 32, 0, st>>>(Tfit, fit_counts, nref, ncur, nmatch, reg);
 }
 
 void launch_acc_update(const double* T, long t_mod, long p, int reset, double* acc_state, cudaStream_t st) {

@@ -70,6 +70,12 @@ SYMBOLS = {
                                        C.c_int, C.c_long, _vp, _vp, C.c_size_t, C.c_size_t]),
     "vstab_offline_run_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_long, C.c_int, C.c_long, _vp, C.c_size_t,
                                        C.c_size_t]),
+    "vstab_offline_reference_bytes": (C.c_size_t, []),
+    "vstab_offline_reference_capture": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int]),
+    "vstab_offline_reference_export": (C.c_int, [_vp, _vp]),
+    "vstab_offline_reference_import": (C.c_int, [_vp, _vp, C.c_int]),
+    "vstab_offline_register": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
+    "vstab_offline_set_registrations": (C.c_int, [_vp, _vp, C.c_long]),
     "vstab_offline_synchronize": (C.c_int, [_vp]),
     "vstab_offline_prepare": (C.c_int, [_vp, _vp, C.c_long, C.c_int, C.c_long]),
     "vstab_offline_set_timing": (None, [_vp, C.c_int]),

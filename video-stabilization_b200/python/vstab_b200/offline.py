@@ -125,6 +125,32 @@ class OfflineStabilizer:
         _check(self._lib.vstab_offline_run_host(self._h, _vp(frames_ptr), frame_stride, step, n_total, mode, lock_call,
                                                 _vp(out_ptr), out_frame_stride, out_step), self._h)
 
+    # ---- ORB / SIFT registration (frame-independent units + one broadcast + one all-gather) -----------
+    def capture_reference(self, frame, mode: int):
+        """Reference set from the anchor frame (uint8 [rows, cols, 3] CUDA tensor); owner rank only."""
+        _check(self._lib.vstab_offline_reference_capture(self._h, _vp(frame.data_ptr()), frame.stride(0), mode), self._h)
+
+    def export_reference(self):
+        """Packed reference set as a uint8 CUDA tensor (to broadcast)."""
+        t = self._torch.empty(int(self._lib.vstab_offline_reference_bytes()), dtype=self._torch.uint8,
+                              device=f"cuda:{self.device}")
+        _check(self._lib.vstab_offline_reference_export(self._h, _vp(t.data_ptr())), self._h)
+        self.synchronize()
+        return t
+
+    def import_reference(self, pack, mode: int):
+        _check(self._lib.vstab_offline_reference_import(self._h, _vp(pack.data_ptr()), mode), self._h)
+
+    def register(self, frames, reg_out):
+        """reg_out[i] (float64 [n, 10]) <- {registration matrix of frames[i] [9], valid}."""
+        self._frames_ok(frames)
+        _check(self._lib.vstab_offline_register(self._h, _vp(frames.data_ptr()), frames.stride(0), frames.stride(1),
+                                                frames.shape[0], _vp(reg_out.data_ptr())), self._h)
+
+    def set_registrations(self, reg_all):
+        self._reg_all = reg_all          # keep alive
+        _check(self._lib.vstab_offline_set_registrations(self._h, _vp(reg_all.data_ptr()), reg_all.shape[0]), self._h)
+
     def read_h(self, ncalls: int):
         import numpy as np
         buf = np.zeros((ncalls, 9))
