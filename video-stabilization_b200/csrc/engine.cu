@@ -154,6 +154,9 @@ struct vstab {
     cudaEvent_t ev_in = nullptr;         // input frame is in the ring (caller may reuse its buffer)
     cudaEvent_t ev_fit = nullptr;        // T[n] and the channel sums of frame n are final
     cudaEvent_t ev_out = nullptr;        // output chain of the previous call has finished reading the ring
+    cudaStream_t gftt_stream = nullptr;  // corner detection of frame n runs beside LK / fit of frame n
+    cudaEvent_t ev_pyr = nullptr;        // gray pyramid of frame n is complete
+    cudaEvent_t ev_gftt = nullptr;       // corners of frame n are complete (needed by LK of frame n+1)
     size_t P = 15, F = 15;
     int working_height = 360;
     int mode = VSTAB_GLOBAL_SMOOTHING;
@@ -235,7 +238,9 @@ static vstab_status stream_estimate(vstab* s) {
     CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3, q));
     launch_ingest(g.plan, frame, g.pitch, g.frame_bytes, 1, s->pyr(cur), g.pd.frame_bytes, sums, q);   // :1169-1175
     launch_pyramid(g.pd, s->pyr(cur), 1, q);
+    CK(cudaEventRecord(s->ev_pyr, q));
     if (n > 0) {
+        CK(cudaStreamWaitEvent(q, s->ev_gftt, 0));                    // corners of frame n-1
         // :1187 trackFeatures
         launch_lk(s->pyr(prev), s->pyr(cur), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
                   s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), q);
@@ -245,8 +250,11 @@ static vstab_status stream_estimate(vstab* s) {
                    s->fitc.as<int>(), nullptr, n, q);
     }
     CK(cudaEventRecord(s->ev_fit, q));
+    // corner detection of this frame (:1318 / :1179) only feeds the next call's tracker: own stream
+    CK(cudaStreamWaitEvent(s->gftt_stream, s->ev_pyr, 0));
     launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                s->corners(cur), ccount + cur, s->gws.eig, q);                                         // :1318 / :1179
+                s->corners(cur), ccount + cur, s->gws.eig, s->gftt_stream);
+    CK(cudaEventRecord(s->ev_gftt, s->gftt_stream));
     CK(cudaGetLastError());
     return VSTAB_OK;
 }
@@ -461,7 +469,10 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
         cudaStreamCreateWithFlags(&s->out_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fit, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->gftt_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_gftt, cudaEventDisableTiming) != cudaSuccess) {
         g_err = "cudaStreamCreate failed"; vstab_destroy(s); return VSTAB_ERR_CUDA;
     }
     *out = s;
@@ -476,6 +487,9 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_in) cudaEventDestroy(s->ev_in);
     if (s->ev_fit) cudaEventDestroy(s->ev_fit);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
+    if (s->gftt_stream) { cudaStreamSynchronize(s->gftt_stream); cudaStreamDestroy(s->gftt_stream); }
+    if (s->ev_pyr) cudaEventDestroy(s->ev_pyr);
+    if (s->ev_gftt) cudaEventDestroy(s->ev_gftt);
     if (s->orb) orb_plan_destroy(s->orb);
     if (s->sift) sift_plan_destroy(s->sift);
     delete s;
@@ -503,6 +517,7 @@ vstab_status vstab_synchronize(vstab_t* s) {
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->out_stream));
+    CK(cudaStreamSynchronize(s->gftt_stream));
     return VSTAB_OK;
 }
 
@@ -562,6 +577,7 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
     if (cudaSetDevice(s->device) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s->out_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s->gftt_stream) != cudaSuccess) return -1;
     Geometry& g = s->g;
     const long last = s->n - 1;                 // index of the most recent frame
     const int cur = (int)(last & 1), prev = cur ^ 1;
@@ -951,12 +967,11 @@ extern "C" vstab_status vstab_offline_prepare(vstab_offline_t* o, const double* 
 
 // Whole-clip stabilization with HOST buffers on one GPU (the reference's --file mode: decoded
 // frames in host memory in, stabilized frames out).  Produces the outputs of stabilizeFrame calls
-// 0..n_total-1 (call c presents frame max(0, c - future)).  Two pipelined phases over chunks of
-// max_batch frames:
-//   1. upload chunk k+1 (copy-in stream)  ||  estimate chunk k (instance stream)
-//   2. smooth + warp chunk k (instance stream)  ||  download chunk k-1 (copy-out stream)
-// Every frame crosses PCIe exactly once in each direction; the clip stays resident in HBM between
-// the phases (6.2 MB per 1080p frame: ~29 k frames fit in 180 GB).
+// 0..n_total-1 (call c presents frame max(0, c - future)).  One software pipeline over chunks of
+// max_batch frames on three streams (both PCIe directions busy at the same time):
+//   upload chunk k+1  ||  estimate + smooth + warp chunk k  ||  download chunk k-1
+// Every frame crosses PCIe exactly once in each direction; the clip stays resident in HBM
+// (6.2 MB per 1080p frame: ~29 k frames fit in 180 GB).
 extern "C" vstab_status vstab_offline_run_host(vstab_offline_t* o, const uint8_t* frames, size_t frame_stride, size_t step,
                                                 long n_total, int mode, long lock_call, uint8_t* out,
                                                 size_t out_frame_stride, size_t out_step) {
@@ -987,39 +1002,58 @@ extern "C" vstab_status vstab_offline_run_host(vstab_offline_t* o, const uint8_t
     cudaEvent_t* ev_rd = ev.data() + nchunks;       // chunk k rendered
     cudaEvent_t* ev_dn = ev.data() + 2 * nchunks;   // chunk k downloaded
     vstab_status st = VSTAB_OK;
-    // ---- phase 1: upload + estimate -----------------------------------------------------------
+    const bool in_contig = step == g.pitch && frame_stride == g.frame_bytes;
+    const bool out_contig = out_step == g.pitch && out_frame_stride == g.frame_bytes;
+    // the accumulated-lock prefix is re-scanned after every chunk over the frames seen so far (a few
+    // thousand 3x3 products): size its buffer once so no reallocation happens while kernels are in flight
+    if (mode == VSTAB_ACCUMULATED_FULL_LOCK) {
+        const size_t mats = (size_t)n_total + (size_t)(n_total / 256 + 2);
+        if (o->acc_capacity < mats) { CK(o->acc.alloc(sizeof(double) * 9 * mats)); o->acc_capacity = mats; }
+    }
+    // Call c presents frame max(0, c - future) and needs transforms up to c - 1 only, so the calls of
+    // chunk k can be rendered as soon as chunk k has been estimated:
+    //   upload(k+1)  ||  estimate(k) -> [prefix scan] -> smooth + warp(k)  ||  download(k-1)
     for (long k = 0; k < nchunks && st == VSTAB_OK; ++k) {
         const long f0 = k * B, n = (n_total - f0 < B) ? n_total - f0 : B;
-        // one 2-D copy per chunk: rows of all frames of the chunk are `step` apart only inside a frame,
-        // so copy frame by frame (fewer, larger copies than per row; no batched-memcpy API)
-        for (long i = 0; i < n; ++i)
-            if (cudaMemcpy2DAsync(clip + (size_t)(f0 + i) * g.frame_bytes, g.pitch, frames + (size_t)(f0 + i) * frame_stride,
-                                  step, row_bytes, g.rows, cudaMemcpyHostToDevice, o->copy_in) != cudaSuccess) {
-                o->err = "upload failed"; st = VSTAB_ERR_CUDA; break;
-            }
+        const long seen = f0 + n;                                       // frames uploaded and estimated so far
+        if (in_contig) {            // tightly packed frames: one large copy per chunk
+            if (cudaMemcpyAsync(clip + (size_t)f0 * g.frame_bytes, frames + (size_t)f0 * frame_stride, (size_t)n * g.frame_bytes,
+                                cudaMemcpyHostToDevice, o->copy_in) != cudaSuccess) { o->err = "upload failed"; st = VSTAB_ERR_CUDA; }
+        } else {
+            for (long i = 0; i < n; ++i)
+                if (cudaMemcpy2DAsync(clip + (size_t)(f0 + i) * g.frame_bytes, g.pitch, frames + (size_t)(f0 + i) * frame_stride,
+                                      step, row_bytes, g.rows, cudaMemcpyHostToDevice, o->copy_in) != cudaSuccess) {
+                    o->err = "upload failed"; st = VSTAB_ERR_CUDA; break;
+                }
+        }
         if (st != VSTAB_OK) break;
         cudaEventRecord(ev_up[k], o->copy_in);
         cudaStreamWaitEvent(o->stream, ev_up[k], 0);
         st = vstab_offline_estimate(o, clip + (size_t)f0 * g.frame_bytes, g.frame_bytes, g.pitch, (int)n, f0,
                                     f0 > 0 ? clip + (size_t)(f0 - 1) * g.frame_bytes : nullptr, T + (size_t)f0 * 9,
                                     sums + (size_t)f0 * 3);
-    }
-    // ---- phase 2: smooth + warp + download ------------------------------------------------------
-    if (st == VSTAB_OK) st = vstab_offline_prepare(o, T, n_total, mode, lock_call);
-    for (long k = 0; k < nchunks && st == VSTAB_OK; ++k) {
-        const long c0 = k * B, n = (n_total - c0 < B) ? n_total - c0 : B;
+        if (st != VSTAB_OK) break;
+        const bool locked = mode == VSTAB_ACCUMULATED_FULL_LOCK && seen > lock_call - (long)o->F;   // anchor frame is in
+        const int rmode = (mode == VSTAB_ACCUMULATED_FULL_LOCK && !locked) ? VSTAB_GLOBAL_SMOOTHING : mode;
+        if (locked) st = vstab_offline_prepare(o, T, seen, mode, lock_call);
+        if (st != VSTAB_OK) break;
         uint8_t* ob = o->outbuf.as<uint8_t>() + (size_t)(k & 1) * B * g.frame_bytes;
         if (k >= 2) cudaStreamWaitEvent(o->stream, ev_dn[k - 2], 0);      // output half is free again
-        st = vstab_offline_render(o, clip, g.frame_bytes, g.pitch, 0, (int)n, c0, T, n_total, mode, lock_call, sums, ob,
+        st = vstab_offline_render(o, clip, g.frame_bytes, g.pitch, 0, (int)n, f0, T, seen, rmode, lock_call, sums, ob,
                                   g.frame_bytes, g.pitch);
         if (st != VSTAB_OK) break;
         cudaEventRecord(ev_rd[k], o->stream);
         cudaStreamWaitEvent(o->copy_out, ev_rd[k], 0);
-        for (long i = 0; i < n; ++i)
-            if (cudaMemcpy2DAsync(out + (size_t)(c0 + i) * out_frame_stride, out_step, ob + (size_t)i * g.frame_bytes, g.pitch,
-                                  row_bytes, g.rows, cudaMemcpyDeviceToHost, o->copy_out) != cudaSuccess) {
-                o->err = "download failed"; st = VSTAB_ERR_CUDA; break;
-            }
+        if (out_contig) {
+            if (cudaMemcpyAsync(out + (size_t)f0 * out_frame_stride, ob, (size_t)n * g.frame_bytes, cudaMemcpyDeviceToHost,
+                                o->copy_out) != cudaSuccess) { o->err = "download failed"; st = VSTAB_ERR_CUDA; }
+        } else {
+            for (long i = 0; i < n; ++i)
+                if (cudaMemcpy2DAsync(out + (size_t)(f0 + i) * out_frame_stride, out_step, ob + (size_t)i * g.frame_bytes, g.pitch,
+                                      row_bytes, g.rows, cudaMemcpyDeviceToHost, o->copy_out) != cudaSuccess) {
+                    o->err = "download failed"; st = VSTAB_ERR_CUDA; break;
+                }
+        }
         cudaEventRecord(ev_dn[k], o->copy_out);
     }
     cudaStreamSynchronize(o->copy_in);

@@ -13,6 +13,7 @@
 // and derivatives from the padded Scharr level (zero border) that K2 prepares, so no tap ever
 // needs border logic; both are tiny and L1/L2-resident.  The 2x2 system and the mismatch
 // vector are reduced exactly with redux.sync.
+#include <cstdlib>
 #include "kernels.h"
 
 namespace vstabk {
@@ -29,7 +30,8 @@ VSTAB_D long long warp_sum_i32(int v) {
     return ((long long)hi << 16) + (long long)lo;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks)
 lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
           size_t prev_stride, size_t next_stride, PyrDesc d,
           const float2* __restrict__ pts, const int* __restrict__ counts,
@@ -189,8 +191,16 @@ void launch_lk(const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_str
     if (nframes <= 0) return;
     dim3 grid((kMaxCorners + kWarpsPerBlock - 1) / kWarpsPerBlock, nframes);
     count_launch(1);
-    lk_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts,
-                                                     counts, out_pts, status);
+    // resident CTAs per SM the register allocation is tuned for (4: 128 regs, 5: 96, 6: 80 + small spills);
+    // measured on B200: 4 -> 8.2 ms, 5 -> 10.2 ms, 6 -> 8.8 ms per 512 frames, so 4 is the default
+    static int mb = 0;
+    if (mb == 0) { const char* e = getenv("VSTAB_LK_MINBLOCKS"); mb = e ? atoi(e) : 4; }
+    if (mb == 4)
+        lk_kernel<4><<<grid, kWarpsPerBlock * 32, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
+    else if (mb == 6)
+        lk_kernel<6><<<grid, kWarpsPerBlock * 32, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
+    else
+        lk_kernel<5><<<grid, kWarpsPerBlock * 32, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
 }
 
 }  // namespace vstabk
