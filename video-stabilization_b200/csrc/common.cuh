@@ -38,8 +38,10 @@ VSTAB_HD int reflect101_multi(int i, int n) {
 
 // A device-resident gray pyramid of one frame.  Level l exists three times inside the frame's
 // block: tight (w x h u8: pyrDown chain, corner detector, taps), padded by kLkPad with
-// BORDER_REFLECT_101 (u8, row pitch `pitch[l]`) and its Scharr derivative image, padded with
-// zeros (short2 {dx, dy}, same geometry) -- the two buffers cv::calcOpticalFlowPyrLK tracks on.
+// BORDER_REFLECT_101 (row pitch `pitch[l]`) as 4-byte bilinear "quads" (the 2x2 neighbourhood of
+// every pixel in one word, so a bilinear tap is one load + two dp2a) and its Scharr derivative
+// image, padded with zeros (short2 {dx, dy}, same geometry) -- the two buffers
+// cv::calcOpticalFlowPyrLK tracks on.
 struct PyrDesc {
     int w[kLkLevels];
     int h[kLkLevels];
@@ -48,6 +50,7 @@ struct PyrDesc {
     size_t off[kLkLevels];   // byte offset of the tight level l inside one frame's pyramid block
     size_t poff[kLkLevels];  // byte offset of padded pixel (-kLkPad, -kLkPad) of level l
     size_t doff[kLkLevels];  // byte offset of the padded derivative image (4 bytes per pixel)
+    size_t qoff[kLkLevels];  // byte offset of the padded "quad" image: {p(y,x), p(y,x+1), p(y+1,x), p(y+1,x+1)} per pixel
     size_t frame_bytes;      // bytes of one frame's pyramid block
 };
 

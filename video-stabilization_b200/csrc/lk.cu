@@ -24,6 +24,20 @@ constexpr int kPix = kLkWin * kLkWin;  // 441
 constexpr int kStrides = (kPix + 31) / 32;  // 14
 
 // exact warp-wide sum of one int32 per lane (|v| < 2^31) as a 64-bit integer: two redux.sync
+// dp2a with signed 16-bit weights and unsigned 8-bit pixels (w11 = 2^14 - w00 - w01 - w10 can be -1):
+// d = c + a.s16[0] * b.u8[2*hi] + a.s16[1] * b.u8[2*hi+1]
+VSTAB_D int dp2a_lo_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+VSTAB_D int dp2a_hi_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+VSTAB_D unsigned pack_w(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+
 VSTAB_D long long warp_sum_i32(int v) {
     const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
     const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
@@ -53,9 +67,9 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
     for (int L = d.nlev - 1; L >= 0; --L) {
         const int cols = d.w[L], rows = d.h[L], P = d.pitch[L];
         const size_t org = (size_t)kLkPad * P + kLkPad;          // padded offset of image pixel (0,0)
-        const uint8_t* I = pI + d.poff[L] + org;
-        const short* dI = reinterpret_cast<const short*>(pI + d.doff[L]) + org * 2;
-        const uint8_t* J = pJ + d.poff[L] + org;
+        const unsigned* I = reinterpret_cast<const unsigned*>(pI + d.qoff[L]) + org;      // bilinear quads of the previous frame
+        const unsigned* dI = reinterpret_cast<const unsigned*>(pI + d.doff[L]) + org;    // {dx, dy} short2
+        const unsigned* J = reinterpret_cast<const unsigned*>(pJ + d.qoff[L]) + org;      // bilinear quads of the next frame
         const float lscale = (float)(1. / (1 << L));
         float px = __fmul_rn(pt.x, lscale), py = __fmul_rn(pt.y, lscale);
         float nx, ny;
@@ -77,6 +91,7 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
             w10 = __float2int_rn(__fmul_rn(__fmul_rn(ia, b), 16384.f));
             w11 = 16384 - w00 - w01 - w10;
         }
+        const unsigned wt01 = pack_w(w00, w01), wt23 = pack_w(w10, w11);
         // offsets of the pixels this lane owns (k = lane + 32 s -> ky * P + kx), shared by the
         // template and every iteration of this level
         int koff[kStrides];
@@ -97,12 +112,15 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
                 Iw[s] = 0; Ix[s] = 0; Iy[s] = 0;
                 if (lane + 32 * s < kPix) {
                     const int o = o0 + koff[s];
-                    const uint8_t* q = I + o;
-                    const short* g = dI + 2 * o;
-                    const int iv = q[0] * w00 + q[1] * w01 + q[P] * w10 + q[P + 1] * w11;
-                    const int xv = g[0] * w00 + g[2] * w01 + g[2 * P] * w10 + g[2 * P + 2] * w11;
-                    const int yv = g[1] * w00 + g[3] * w01 + g[2 * P + 1] * w10 + g[2 * P + 3] * w11;
-                    Iw[s] = (iv + (1 << 8)) >> 9;
+                    const unsigned* g = dI + o;
+                    // the 2x2 neighbourhood in one word: 16-bit weights x 8-bit pixels, two dp2a
+                    const unsigned qi = __ldg(I + o);
+                    const int iv = dp2a_lo_su(wt01, qi, dp2a_hi_su(wt23, qi, 1 << 8));
+                    const unsigned d00 = __ldg(g), d01 = __ldg(g + 1), d10 = __ldg(g + P), d11 = __ldg(g + P + 1);
+                    const int xv = (int)(short)(d00 & 0xffffu) * w00 + (int)(short)(d01 & 0xffffu) * w01 +
+                                   (int)(short)(d10 & 0xffffu) * w10 + (int)(short)(d11 & 0xffffu) * w11;
+                    const int yv = ((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 + ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11;
+                    Iw[s] = iv >> 9;
                     Ix[s] = (xv + (1 << 13)) >> 14;
                     Iy[s] = (yv + (1 << 13)) >> 14;
                     sA11 += Ix[s] * Ix[s];
@@ -134,22 +152,23 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
                 if (L == 0) st = 0;
                 break;
             }
-            int v00, v01, v10, v11;
+            unsigned vt01, vt23;
             {
                 const float a = __fsub_rn(nx, (float)jx), b = __fsub_rn(ny, (float)jy);
                 const float ia = __fsub_rn(1.f, a), ib = __fsub_rn(1.f, b);
-                v00 = __float2int_rn(__fmul_rn(__fmul_rn(ia, ib), 16384.f));
-                v01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ib), 16384.f));
-                v10 = __float2int_rn(__fmul_rn(__fmul_rn(ia, b), 16384.f));
-                v11 = 16384 - v00 - v01 - v10;
+                const int v00 = __float2int_rn(__fmul_rn(__fmul_rn(ia, ib), 16384.f));
+                const int v01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ib), 16384.f));
+                const int v10 = __float2int_rn(__fmul_rn(__fmul_rn(ia, b), 16384.f));
+                const int v11 = 16384 - v00 - v01 - v10;
+                vt01 = pack_w(v00, v01); vt23 = pack_w(v10, v11);
             }
             int sb1 = 0, sb2 = 0;                   // per lane <= 14 * 8160 * 4080 < 2^31
             const int o0 = jy * P + jx;
 #pragma unroll
             for (int s = 0; s < kStrides; ++s) {
                 if (lane + 32 * s < kPix) {
-                    const uint8_t* q = J + (o0 + koff[s]);
-                    const int jv = (q[0] * v00 + q[1] * v01 + q[P] * v10 + q[P + 1] * v11 + (1 << 8)) >> 9;
+                    const unsigned q = __ldg(J + (o0 + koff[s]));
+                    const int jv = dp2a_lo_su(vt01, q, dp2a_hi_su(vt23, q, 1 << 8)) >> 9;
                     const int diff = jv - Iw[s];
                     sb1 += diff * Ix[s];
                     sb2 += diff * Iy[s];

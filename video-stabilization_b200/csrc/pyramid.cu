@@ -23,9 +23,10 @@ PyrDesc make_pyr_desc(int w, int h) {
     for (int l = 0; l < kLkLevels; ++l) {
         d.pitch[l] = (d.w[l] + 2 * kLkPad + 3) & ~3;
         const size_t px = (size_t)d.pitch[l] * (d.h[l] + 2 * kLkPad);
-        d.poff[l] = off;
-        off += (px + 255) & ~(size_t)255;
+        d.poff[l] = 0;                              // (plain padded u8 levels are not materialised: the quads carry them)
         d.doff[l] = off;
+        off += (px * 4 + 255) & ~(size_t)255;
+        d.qoff[l] = off;
         off += (px * 4 + 255) & ~(size_t)255;
     }
     d.frame_bytes = off;
@@ -84,7 +85,7 @@ struct PrepLevels {
     int w[kLkLevels], h[kLkLevels], pitch[kLkLevels];
     int tiles_x[kLkLevels];
     int first[kLkLevels + 1];        // first tile of each level
-    unsigned off[kLkLevels], poff[kLkLevels], doff[kLkLevels];
+    unsigned off[kLkLevels], poff[kLkLevels], doff[kLkLevels], qoff[kLkLevels];
 };
 
 __global__ void __launch_bounds__(PTX * PTY)
@@ -112,12 +113,11 @@ lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
     if (Y >= h + 2 * kLkPad || X >= pitch) return;
     const int r = threadIdx.y + 1, c0 = threadIdx.x * PPX + 1;
     const int iy = Y - kLkPad;
-    unsigned ipack = 0;
-    int dq[PPX];
+    int dq[PPX], qq[PPX];
 #pragma unroll
     for (int k = 0; k < PPX; ++k) {
         const int c = c0 + k, ix = X + k - kLkPad;
-        ipack |= (unsigned)t[r][c] << (8 * k);
+        qq[k] = (int)((unsigned)t[r][c] | ((unsigned)t[r][c + 1] << 8) | ((unsigned)t[r + 1][c] << 16) | ((unsigned)t[r + 1][c + 1] << 24));
         int dx = 0, dy = 0;
         if (ix >= 0 && ix < w && iy >= 0 && iy < h) {
             const int a00 = t[r - 1][c - 1], a01 = t[r - 1][c], a02 = t[r - 1][c + 1];
@@ -129,8 +129,8 @@ lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
         dq[k] = (dx & 0xffff) | (dy << 16);
     }
     // pitch is a multiple of 4 and X is a multiple of 4: aligned vector stores
-    *reinterpret_cast<unsigned*>(base + L.poff[l] + (size_t)Y * pitch + X) = ipack;
     *reinterpret_cast<int4*>(base + L.doff[l] + ((size_t)Y * pitch + X) * 4) = make_int4(dq[0], dq[1], dq[2], dq[3]);
+    *reinterpret_cast<int4*>(base + L.qoff[l] + ((size_t)Y * pitch + X) * 4) = make_int4(qq[0], qq[1], qq[2], qq[3]);
 }
 
 }  // namespace
@@ -148,7 +148,7 @@ void launch_pyramid(const PyrDesc& d, uint8_t* pyr, int nframes, cudaStream_t st
     int tiles = 0;
     for (int l = 0; l < kLkLevels; ++l) {
         L.w[l] = d.w[l]; L.h[l] = d.h[l]; L.pitch[l] = d.pitch[l];
-        L.off[l] = (unsigned)d.off[l]; L.poff[l] = (unsigned)d.poff[l]; L.doff[l] = (unsigned)d.doff[l];
+        L.off[l] = (unsigned)d.off[l]; L.poff[l] = (unsigned)d.poff[l]; L.doff[l] = (unsigned)d.doff[l]; L.qoff[l] = (unsigned)d.qoff[l];
         L.first[l] = tiles;
         L.tiles_x[l] = (d.pitch[l] + PTW - 1) / PTW;
         tiles += l < d.nlev ? L.tiles_x[l] * ((d.h[l] + 2 * kLkPad + PTY - 1) / PTY) : 0;
