@@ -258,8 +258,9 @@ if (x0 < w) {
     }
 }
 
-// Default variant: one CTA per tile, synchronous 16-byte loads into the stage.
-__global__ void __launch_bounds__(NTX * NTY)
+// Default variant (0): one CTA per tile, synchronous 16-byte loads into the stage; the block scheduler
+// overlaps the fill of one CTA with the arithmetic of the others resident on the SM.
+__global__ void __launch_bounds__(NTX * NTY, 4)
 warp_tile_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t frame_stride, long slot_mod,
                  const WarpParams* __restrict__ wps, int w, int h,
                  uint8_t* __restrict__ out, size_t out_pitch, size_t out_frame_stride) {
@@ -288,6 +289,81 @@ warp_tile_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t frame_
     __syncthreads();
     compute_tile(reinterpret_cast<const uint8_t*>(stage), box, I.M, I.border, I.src, pitch, w, h,
                  out + (size_t)oi * out_frame_stride, out_pitch, tx0, ty0, threadIdx.x, threadIdx.y);
+}
+
+// Experimental variant (VSTAB_WARP_VARIANT=2; bit-exact, measured slower than variant 0 on B200: 7.2 vs
+// 5.7 ms per 512 frames): persistent CTAs, each walking tiles blockIdx.x, +gridDim.x, ... with a two-stage
+// shared-memory pipeline: the staged source box of the NEXT tile is fetched with cp.async (LDGSTS, no
+// register staging) while the current tile is computed, so the global-load latency of the fill --
+// 30 % of the one-tile-per-CTA kernel's stall samples -- is hidden behind the arithmetic.
+struct PipeSmem {
+    unsigned char stage[2][kStageStride];
+    TileInfo info[3];
+};
+
+VSTAB_D void make_tile_info(TileInfo& I, long t, int tiles_per_frame, int ntx, const uint8_t* frames, size_t pitch,
+                            size_t frame_stride, long slot_mod, const WarpParams* wps, int w, int h) {
+    const int oi = (int)(t / tiles_per_frame);
+    const int tt = (int)(t - (long)oi * tiles_per_frame);
+    const int tyi = tt / ntx, txi = tt - tyi * ntx;
+    const WarpParams& P = wps[oi];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) I.M[i] = P.Minv[i];
+    I.border[0] = P.border[0]; I.border[1] = P.border[1]; I.border[2] = P.border[2];
+    I.src = frames + (size_t)(slot_mod > 0 ? (P.src_slot % slot_mod) : P.src_slot) * frame_stride;
+    I.oi = oi; I.tx0 = txi * TW; I.ty0 = tyi * TH;
+    I.box = tile_box(I.M, I.src, pitch, w, h, I.tx0, I.ty0);
+}
+
+VSTAB_D void prefetch_box(const TileInfo& I, unsigned char* stage, size_t pitch, int tx, int ty) {
+    const TileBox box = I.box;
+    if (box.SP > 0) {
+        const int vpr = box.SP >> 4;
+        for (int r = ty; r <= box.fyn; r += NTY) {
+            const uint8_t* g = I.src + (size_t)(box.fy0 + r) * pitch + box.b0;
+            const unsigned d = smem_u32(stage + (size_t)r * box.SP);
+            for (int c = tx; c < vpr; c += NTX)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + c * 16), "l"(g + c * 16) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTX * NTY, 3)
+warp_pipe_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t frame_stride, long slot_mod,
+                 const WarpParams* __restrict__ wps, int nout, int w, int h,
+                 uint8_t* __restrict__ out, size_t out_pitch, size_t out_frame_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PipeSmem& S = *reinterpret_cast<PipeSmem*>(smem_raw);
+    const int ntx = (w + TW - 1) / TW, nty = (h + TH - 1) / TH;
+    const int tiles_per_frame = ntx * nty;
+    const long ntiles = (long)tiles_per_frame * nout;
+    const int tid = threadIdx.y * NTX + threadIdx.x;
+    const long t0 = blockIdx.x, stride = gridDim.x;
+    if (t0 >= ntiles) return;
+    if (tid == 0) {
+        make_tile_info(S.info[0], t0, tiles_per_frame, ntx, frames, pitch, frame_stride, slot_mod, wps, w, h);
+        if (t0 + stride < ntiles)
+            make_tile_info(S.info[1], t0 + stride, tiles_per_frame, ntx, frames, pitch, frame_stride, slot_mod, wps, w, h);
+    }
+    __syncthreads();
+    prefetch_box(S.info[0], S.stage[0], pitch, threadIdx.x, threadIdx.y);
+    int it = 0;
+    for (long t = t0; t < ntiles; t += stride, ++it) {
+        const int cur = it & 1;
+        const bool has_next = t + stride < ntiles;
+        if (has_next) prefetch_box(S.info[(it + 1) % 3], S.stage[cur ^ 1], pitch, threadIdx.x, threadIdx.y);
+        if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // stage[cur] is complete and visible
+        // the tile after next: thread 0 prepares its box while the CTA computes
+        if (tid == 0 && t + 2 * stride < ntiles)
+            make_tile_info(S.info[(it + 2) % 3], t + 2 * stride, tiles_per_frame, ntx, frames, pitch, frame_stride, slot_mod, wps, w, h);
+        const TileInfo& I = S.info[it % 3];
+        compute_tile(S.stage[cur], I.box, I.M, I.border, I.src, pitch, w, h, out + (size_t)I.oi * out_frame_stride, out_pitch,
+                     I.tx0, I.ty0, threadIdx.x, threadIdx.y);
+        __syncthreads();                                   // stage[cur] may be refilled, info[(it+2)%3] is published
+    }
 }
 
 // Experimental variant (VSTAB_WARP_VARIANT=1; measured slower than the default on B200, see
@@ -380,6 +456,7 @@ void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem));
+        cudaFuncSetAttribute(warp_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem));
         if (num_sms <= 0) num_sms = 148;
         if (const char* e = getenv("VSTAB_WARP_VARIANT")) variant = atoi(e);
         if (const char* e = getenv("VSTAB_WARP_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 3;
@@ -393,6 +470,11 @@ void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long 
     }
     const long ntiles = (long)((w + TW - 1) / TW) * ((h + TH - 1) / TH) * nout;
     const int grid = (int)(ntiles < (long)num_sms * ctas_per_sm ? ntiles : (long)num_sms * ctas_per_sm);
+    if (variant == 2) {
+        warp_pipe_kernel<<<grid, dim3(NTX, NTY), sizeof(PipeSmem), st>>>(frames, pitch, frame_stride, slot_mod, wp, nout, w, h,
+                                                                         out, out_pitch, out_frame_stride);
+        return;
+    }
     warp_kernel<<<grid, kThreads, sizeof(WarpSmem), st>>>(frames, pitch, frame_stride, slot_mod, wp, nout, w, h, out,
                                                           out_pitch, out_frame_stride);
 }
