@@ -102,7 +102,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -353,6 +353,10 @@ def run_ours(args):
                          f"(ping-pong), oracle.StabilizerRef over cv2 with {arm.cores} threads; host has "
                          f"{os.cpu_count()} logical cores"}
 
+    modes = None
+    if world == 1 and rank == 0 and not args.no_mode_probes:
+        modes = run_mode_probes(args, torch, vs, lib, local)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -365,7 +369,7 @@ def run_ours(args):
                        "l2_policy": f"inputs_exceed_l2 ({n_local * 3 * W * H / 1e6:.0f} MB of frames per GPU per step vs 126 MB L2)",
                        "parallelism": f"frame-sharded x{world}, one all-gather of 72 B/frame" if world > 1 else "single GPU"},
             "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "other_modes_streaming": modes,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -447,10 +451,55 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
                           "d2h_bytes_per_step": per_step * nbytes}}
 
 
+def run_mode_probes(args, torch, vs, lib, local):
+    """Secondary figures (not the headline metric): streaming frames/s of the ORB and SIFT registration
+    modes at BASELINE configs 3 and 4, through the host-buffer C ABI (pinned memory)."""
+    from vstab_b200 import offline, synth
+    out = {}
+    tex = torch.from_numpy(synth.make_texture(2048)).to(f"cuda:{local}")
+    for name, w, h, wh, mode, n_distinct, n_timed in (
+            ("c3_orb_full_lock_1080p_wh1080", 1920, 1080, 1080, vs.ORB_FULL_LOCK, 24, 40),
+            ("c4_sift_full_lock_4k_wh2160", 3840, 2160, 2160, vs.SIFT_FULL_LOCK, 12, 16)):
+        nbytes = w * h * 3
+        frames = torch.empty((n_distinct, h, w, 3), dtype=torch.uint8, device=f"cuda:{local}")
+        offline.render_frames(tex, synth.camera_path(n_distinct, drift=PATH_DRIFT), h, w, synth.focal_for_width(w), frames,
+                              device=local)
+        hin = lib.vstab_host_alloc(n_distinct * nbytes)
+        hout = lib.vstab_host_alloc(nbytes)
+        np.ctypeslib.as_array((C.c_uint8 * (n_distinct * nbytes)).from_address(hin)).reshape(n_distinct, h, w, 3)[:] = \
+            frames.cpu().numpy()
+        del frames
+        st = vs.Stabilizer(PAST, FUTURE, wh, device=local)
+        i = 0
+
+        def run(n):
+            nonlocal i
+            for _ in range(n):
+                if i == 2:
+                    st.set_stabilization_mode(mode)
+                st.stabilize_frame_ptr(hin + pingpong(i, n_distinct) * nbytes, h, w, w * 3, hout, w * 3)
+                i += 1
+
+        run(8)
+        st.synchronize()
+        t0 = time.perf_counter()
+        run(n_timed)
+        st.synchronize()
+        dt = time.perf_counter() - t0
+        cnt = st.tap(vs.TAP_ORB_COUNTS)
+        st.close()
+        lib.vstab_host_free(C.c_void_p(hin))
+        lib.vstab_host_free(C.c_void_p(hout))
+        out[name] = {"value": n_timed / dt, "unit": UNIT, "api": "vstab_stabilize_frame (streaming, pinned host buffers)",
+                     "calls": n_timed, "keypoints_current": int(cnt[0]), "keypoints_reference": int(cnt[1]),
+                     "matches": int(cnt[2]), "inliers": int(cnt[3])}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=512)
@@ -463,6 +512,7 @@ def main():
     ap.add_argument("--cpu-frames-per-step", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-mode-probes", action="store_true", help="skip the ORB / SIFT streaming figures")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -159,7 +159,7 @@ def _sift_overlap(gray):
     return len(kps), len(ckps), hit, np.array(pos_err), np.array(ang_err), np.array(dsc_err)
 
 
-@pytest.mark.parametrize("W,H,wh", [(1280, 720, 360), (1920, 1080, 1080)])
+@pytest.mark.parametrize("W,H,wh", [(1280, 720, 360), (1920, 1080, 1080), (3840, 2160, 2160)])
 def test_sift_overlaps_opencv(texture, W, H, wh):
     """K11 is a float pipeline and not bit-pinned: the keypoint set must overlap cv2's
     (same octave/layer, position <= 0.05 px, orientation <= 2 deg) and matched descriptors must agree."""

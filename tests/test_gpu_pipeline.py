@@ -252,3 +252,12 @@ def test_sift_full_lock_matches_oracle(texture, W, H, wh, n):
     st.close()
     print(f"SIFT lock {W}x{H} wh{wh}: worst corner difference {worst_h:.4f} px")
     assert worst_h <= H_TOL_PX
+
+
+def test_config5_shape_4k_wh360(texture):
+    """BASELINE config 5 geometry (3840x2160, working height 360: scale 1/6 ingest path), shortened."""
+    frames = render_clip(texture, 3840, 2160, 10)
+    s = _run_both(frames, 4, 3, 360)
+    assert s["corners_differ"] == 0 and s["status"] == 0
+    assert s["lk"] <= 0.05 and s["t"] <= H_TOL_PX and s["h"] <= H_TOL_PX
+    assert s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
