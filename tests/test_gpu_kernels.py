@@ -219,6 +219,7 @@ def test_warp_bit_exact(texture, shape):
     frame = render_clip(texture, shape[1], shape[0], 1)[0]
     for src in (frame, noise):
         for Hm in (_rigid(0.01, 3.3, -7.7), _rigid(-0.05, 40.2, 11.9), np.eye(3), _rigid(3.0, 500.0, 300.0),
+                   _rigid(0.12, -20.5, 30.25), _rigid(-0.3, 100.0, -50.0), _rigid(0.7, 300.0, -200.0),
                    np.array([[0.98, 0.02, 5.5], [-0.015, 1.01, -3.25], [1e-5, -2e-5, 1.0]]),
                    _rigid(0.0, 1e7, 0.0)):                      # everything lands on the border colour
             bd = tuple(0.5 * v for v in cv2.mean(src))

@@ -18,151 +18,160 @@
 namespace vstabk {
 namespace {
 
-constexpr int ETX = 32, ETY = 16;                 // candidate tile
-constexpr int EW = ETX + 2, EH = ETY + 2;         // eig footprint (halo 1)
-constexpr int PW = ETX + 4, PH = ETY + 4;         // product footprint (halo 2)
-constexpr int GW = ETX + 6, GH = ETY + 6;         // gray footprint (halo 3)
 constexpr unsigned short kEmpty16 = 0xffffu;
 constexpr int kCellCap = 4;                       // u16 slots per cell ({dy,dx} relative to the cell)
 constexpr int kGreedySmemMax = 200 * 1024;
 
-__global__ void __launch_bounds__(ETX * ETY)
-eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h,
+// Pass A as a register/shuffle stream, no shared memory: one warp owns a strip of kStripW = 28 columns and
+// marches down a segment of kSegH rows.  Lane l holds the derivative products of column sx0-2+l (reflected into
+// the image like cv::boxFilter's BORDER_REFLECT_101 does with the covariance images); the horizontal 3-sums come
+// from shfl.down on the f64 products, the vertical 3-sums from the last three rows kept in registers (f64, the
+// order of OpenCV's row/column sums), the eigenvalue row from those, and the 3x3 local-maximum test from the last
+// three eigenvalue rows (horizontal neighbours by shuffle).  Each gray row is read once per strip (+4 halo
+// columns, +4 halo rows per segment); every f32 product is converted to f64 once.
+constexpr int kStripW = 28, kSegH = 60, kEigWarps = 4;
+
+struct D3 { double xx, xy, yy; };
+
+__global__ void __launch_bounds__(32 * kEigWarps)
+eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs,
            float* __restrict__ eig_out, unsigned int* __restrict__ maxbits,
            unsigned long long* __restrict__ keys, int* __restrict__ seg_end, int cap, double quality) {
-    __shared__ float g[GH][GW + 1];
-    __shared__ float pxx[PH][PW + 1], pxy[PH][PW + 1], pyy[PH][PW + 1];
-    __shared__ float se[EH][EW + 1];
-    __shared__ float wmax[ETX * ETY / 32];
-    const int frame = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kEigWarps + (threadIdx.x >> 5);
+    const int frame = blockIdx.y;
+    if (item >= nstrips * nsegs) return;
+    const int seg = item / nstrips, strip = item - seg * nstrips;
+    const int sx0 = strip * kStripW;
+    const int ya = seg * kSegH, yb = min(ya + kSegH, h);
     const uint8_t* src = gray + (size_t)frame * gray_stride;
-    const int x0 = blockIdx.x * ETX, y0 = blockIdx.y * ETY;
-    const int tid = threadIdx.y * ETX + threadIdx.x;
-
-    for (int i = tid; i < GH * GW; i += ETX * ETY) {
-        const int r = i / GW, c = i - r * GW;
-        int yy = min(max(y0 - 3 + r, -(h - 1)), 2 * h - 2);
-        int xx = min(max(x0 - 3 + c, -(w - 1)), 2 * w - 2);
-        yy = reflect101(yy, h);
-        xx = reflect101(xx, w);
-        g[r][c] = (float)src[(size_t)yy * w + xx];
-    }
-    __syncthreads();
 
     // scale = 1 / (2^(ksize-1) * blockSize * 255) ; k1 = float(scale), k0 = float(2*scale)
     const float k1 = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float k0 = (float)(2.0 / (4.0 * 3.0 * 255.0));
-    for (int i = tid; i < PH * PW; i += ETX * ETY) {
-        const int r = i / PW, c = i - r * PW;
-        // image position of this product sample, reflected into the image (box BORDER_REFLECT_101)
-        int py = min(max(y0 - 2 + r, -(h - 1)), 2 * h - 2);
-        int px = min(max(x0 - 2 + c, -(w - 1)), 2 * w - 2);
-        py = reflect101(py, h);
-        px = reflect101(px, w);
-        // tile coordinates of that position (clamped: out-of-tile only for unused samples)
-        const int tr = min(max(py - (y0 - 3), 1), GH - 2);
-        const int tc = min(max(px - (x0 - 3), 1), GW - 2);
-        // Dx = fma(S[y-1] + S[y+1], k1, S[y]*k0),  S[y] = p[y][x+1] - p[y][x-1]
-        const float sm = g[tr - 1][tc + 1] - g[tr - 1][tc - 1];
-        const float s0 = g[tr][tc + 1] - g[tr][tc - 1];
-        const float sp = g[tr + 1][tc + 1] - g[tr + 1][tc - 1];
-        const float dx = __fmaf_rn(__fadd_rn(sm, sp), k1, __fmul_rn(s0, k0));
-        // Dy = R[y+1] - R[y-1],  R[y] = fma(p[x+1], k1, fma(p[x], k0, p[x-1]*k1))
-        // OpenCV's row filter runs its FMA vector body over the first floor(w/32)*32 columns and a
-        // scalar, un-contracted tail over the rest ([probe] cv2 4.13.0 on AVX-512 hosts; all
-        // production widths 640/1280/1920/3840 are multiples of 32 and never reach the tail).
-        float rm, rp;
-        if (px < (w & ~31)) {
-            rm = __fmaf_rn(g[tr - 1][tc + 1], k1, __fmaf_rn(g[tr - 1][tc], k0, __fmul_rn(g[tr - 1][tc - 1], k1)));
-            rp = __fmaf_rn(g[tr + 1][tc + 1], k1, __fmaf_rn(g[tr + 1][tc], k0, __fmul_rn(g[tr + 1][tc - 1], k1)));
-        } else {
-            rm = __fadd_rn(__fadd_rn(__fmul_rn(g[tr - 1][tc - 1], k1), __fmul_rn(g[tr - 1][tc], k0)),
-                           __fmul_rn(g[tr - 1][tc + 1], k1));
-            rp = __fadd_rn(__fadd_rn(__fmul_rn(g[tr + 1][tc - 1], k1), __fmul_rn(g[tr + 1][tc], k0)),
-                           __fmul_rn(g[tr + 1][tc + 1], k1));
-        }
-        const float dy = __fsub_rn(rp, rm);
-        pxx[r][c] = __fmul_rn(dx, dx);
-        pxy[r][c] = __fmul_rn(dx, dy);
-        pyy[r][c] = __fmul_rn(dy, dy);
-    }
-    __syncthreads();
+    // this lane's product column, reflected into the image, and its Sobel taps (BORDER_REFLECT_101 of the gray image)
+    const int xr = reflect101(min(sx0 - 2 + lane, w + 1), w);
+    const int cm = reflect101(xr - 1, w), cp = reflect101(xr + 1, w);
+    // OpenCV's row filter runs its FMA vector body over the first floor(w/32)*32 columns and a scalar,
+    // un-contracted tail over the rest ([probe] cv2 4.13.0 on AVX-512 hosts; all production widths
+    // 640/1280/1920/3840 are multiples of 32 and never reach the tail).
+    const bool fma_col = xr < (w & ~31);
+    // S = p[x+1] - p[x-1] (Dx row term), R = k1 p[x-1] + k0 p[x] + k1 p[x+1] (Dy row term) of gray row y
+    auto load_row = [&](int y, float& S, float& R) {
+        const int ro = y * w;                                    // (a working image has far fewer than 2^31 pixels)
+        const float gm = (float)__ldg(src + (ro + cm)), g0 = (float)__ldg(src + (ro + xr)), gp = (float)__ldg(src + (ro + cp));
+        S = __fsub_rn(gp, gm);
+        R = fma_col ? __fmaf_rn(gp, k1, __fmaf_rn(g0, k0, __fmul_rn(gm, k1)))
+                    : __fadd_rn(__fadd_rn(__fmul_rn(gm, k1), __fmul_rn(g0, k0)), __fmul_rn(gp, k1));
+    };
 
-    // min eigenvalue on the (ETX+2) x (ETY+2) footprint; positions outside the image stay 0
-    // (never compared: candidates exclude the 1-px image border)
-    float m = 0.f;
-    for (int i = tid; i < EH * EW; i += ETX * ETY) {
-        const int r = i / EW, c = i - r * EW;           // eig (r,c) <-> image (y0-1+r, x0-1+c); products r..r+2
-        const int x = x0 - 1 + c, y = y0 - 1 + r;
-        float e = 0.f;
-        if (x >= 0 && x < w && y >= 0 && y < h) {
-            double sxx = 0.0, sxy = 0.0, syy = 0.0;
+    const int xe = sx0 - 1 + lane;                              // eigenvalue column of this lane (lanes 0..29)
+    const bool e_valid = lane < 30 && xe >= 0 && xe < w;
+    const bool own_col = lane >= 1 && lane <= kStripW && xe < w;
+    const bool cand_col = own_col && xe >= 1 && xe < w - 1;
+    const int ye_lo = max(ya - 1, 0), ye_hi = min(yb, h - 1);   // eigenvalue rows this segment needs
+    const int p_lo = max(ye_lo - 1, 0), p_hi = min(ye_hi + 1, h - 1);   // product rows (all inside the image)
+    const int yc_lo = max(ya, 1), yc_hi = min(yb, h - 1);       // candidate rows [yc_lo, yc_hi)
+
+    // rolling state, indexed by compile-time slots (the row loop is unrolled by 3, so nothing is ever moved):
+    // gray row g -> slot (g - p_lo + 1) % 3; product row yp -> slot j = (yp - p_lo) % 3; eigenvalue row yp-1 -> slot j
+    float S[3], R[3];
+    D3 RS[3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // horizontal 3-sums of the product rows
+    float E[3] = {0.f, 0.f, 0.f}, HM[3] = {0.f, 0.f, 0.f}, H3[3] = {0.f, 0.f, 0.f};   // eig row: value, max(left,right), 3-max
+    load_row(reflect101(p_lo - 1, h), S[0], R[0]);
+    load_row(p_lo, S[1], R[1]);
+    float vmax = 0.f;
+    // candidates must exceed this (0: the eigenvalue must be positive)
+    float cut = (float)((double)__uint_as_float(*(volatile unsigned int*)(maxbits + frame)) * quality) * 0.999f;
+    __shared__ unsigned long long queue_all[kEigWarps][64];
+    unsigned long long* queue = queue_all[threadIdx.x >> 5];
+    int qn = 0;
+    bool done = false;
+    for (int yp0 = p_lo; !done; yp0 += 3) {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const double rxx = __dadd_rn(__dadd_rn((double)pxx[r + dy][c], (double)pxx[r + dy][c + 1]),
-                                             (double)pxx[r + dy][c + 2]);
-                const double rxy = __dadd_rn(__dadd_rn((double)pxy[r + dy][c], (double)pxy[r + dy][c + 1]),
-                                             (double)pxy[r + dy][c + 2]);
-                const double ryy = __dadd_rn(__dadd_rn((double)pyy[r + dy][c], (double)pyy[r + dy][c + 1]),
-                                             (double)pyy[r + dy][c + 2]);
-                sxx = __dadd_rn(sxx, rxx);
-                sxy = __dadd_rn(sxy, rxy);
-                syy = __dadd_rn(syy, ryy);
+        for (int j = 0; j < 3; ++j) {
+            const int yp = yp0 + j;
+            if (yp > p_hi + 1 || (yp > p_hi && p_hi != h - 1)) { done = true; break; }
+            const int jA = (j + 1) % 3, jB = (j + 2) % 3;           // slots of rows yp-2, yp-1
+            if (yp <= p_hi) {
+                load_row(reflect101(yp + 1, h), S[jB], R[jB]);       // gray row yp+1
+                // Dx = fma(S[y-1] + S[y+1], k1, S[y]*k0),  Dy = R[y+1] - R[y-1]
+                const float dx = __fmaf_rn(__fadd_rn(S[j], S[jB]), k1, __fmul_rn(S[jA], k0));
+                const float dy = __fsub_rn(R[jB], R[j]);
+                const double pxx = (double)__fmul_rn(dx, dx), pxy = (double)__fmul_rn(dx, dy), pyy = (double)__fmul_rn(dy, dy);
+                RS[j].xx = __dadd_rn(__dadd_rn(pxx, __shfl_down_sync(0xffffffffu, pxx, 1)), __shfl_down_sync(0xffffffffu, pxx, 2));
+                RS[j].xy = __dadd_rn(__dadd_rn(pxy, __shfl_down_sync(0xffffffffu, pxy, 1)), __shfl_down_sync(0xffffffffu, pxy, 2));
+                RS[j].yy = __dadd_rn(__dadd_rn(pyy, __shfl_down_sync(0xffffffffu, pyy, 1)), __shfl_down_sync(0xffffffffu, pyy, 2));
+            } else {
+                RS[j] = RS[jA];                                     // below the last image row: product row h == row h-2
             }
-            const float a = __fmul_rn((float)sxx, 0.5f);
-            const float b = (float)sxy;
-            const float cc = __fmul_rn((float)syy, 0.5f);
-            const float d = __fsub_rn(a, cc);
-            const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b)));
-            e = __fsub_rn(__fadd_rn(a, cc), rad);
-            const bool own = r >= 1 && r <= ETY && c >= 1 && c <= ETX;   // pixel of this tile (not halo)
-            if (own) {
-                m = fmaxf(m, e);
-                if (eig_out) eig_out[(size_t)frame * w * h + (size_t)y * w + x] = e;
+            const int ye = yp - 1;
+            if (ye >= ye_lo && ye <= ye_hi) {
+                const D3 U = ye == 0 ? RS[j] : RS[jA];              // above the first image row: product row -1 == row 1
+                const double sxx = __dadd_rn(__dadd_rn(U.xx, RS[jB].xx), RS[j].xx);
+                const double sxy = __dadd_rn(__dadd_rn(U.xy, RS[jB].xy), RS[j].xy);
+                const double syy = __dadd_rn(__dadd_rn(U.yy, RS[jB].yy), RS[j].yy);
+                const float a = __fmul_rn((float)sxx, 0.5f);
+                const float b = (float)sxy;
+                const float cc = __fmul_rn((float)syy, 0.5f);
+                const float d = __fsub_rn(a, cc);
+                const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b)));
+                const float e = e_valid ? __fsub_rn(__fadd_rn(a, cc), rad) : 0.f;
+                if (own_col && ye >= ya && ye < yb) {
+                    vmax = fmaxf(vmax, e);
+                    if (eig_out) eig_out[(size_t)frame * w * h + (size_t)ye * w + xe] = e;
+                }
+                const float hm = fmaxf(__shfl_up_sync(0xffffffffu, e, 1), __shfl_down_sync(0xffffffffu, e, 1));
+                E[j] = e; HM[j] = hm; H3[j] = fmaxf(hm, e);
+                // 3x3 local maxima of row yc = ye - 1 (ties kept, like eig == dilate(eig)) inside the 1-px image border
+                const int yc = ye - 1;
+                if (yc >= yc_lo && yc < yc_hi) {
+                    const float v = E[jB];
+                    // conservative early cut: the running maximum only grows, so anything at or below
+                    // 0.01 * (maximum seen so far) is certainly below the final threshold
+                    const bool is_cand = cand_col && v > cut && v >= HM[jB] && v >= H3[jA] && v >= H3[j];
+                    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+                    if (ball) {
+                        // append to this warp's queue; 32 keys leave with one atomic and one coalesced 256-byte store
+                        if (is_cand)
+                            queue[qn + __popc(ball & ((1u << lane) - 1u))] =
+                                ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(unsigned)(yc * w + xe);
+                        qn += __popc(ball);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            int pos0 = 0;
+                            if (lane == 0) pos0 = atomicAdd(seg_end + frame, 32);
+                            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                            const unsigned long long k0 = queue[lane], k1 = queue[32 + lane];
+                            if (pos0 + lane < (frame + 1) * cap) keys[pos0 + lane] = k0;
+                            __syncwarp();
+                            queue[lane] = k1;
+                            qn -= 32;
+                            __syncwarp();
+                        }
+                    }
+                }
             }
         }
-        se[r][c] = e;
-    }
+        // publish the running maximum every 12 rows (and at the end), and refresh the early cut from the frame's
+        // maximum so far
+        if (done || (yp0 - p_lo) % 12 == 9) {
+            float m = vmax;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0) wmax[tid >> 5] = m;
-    __syncthreads();
-    if (tid < 32) {
-        float v = tid < ETX * ETY / 32 ? wmax[tid] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (tid == 0 && v > 0.f) atomicMax(maxbits + frame, __float_as_uint(v));
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            unsigned old = 0u;
+            if (lane == 0) old = atomicMax(maxbits + frame, __float_as_uint(m));      // non-negative floats order like their bits
+            old = __shfl_sync(0xffffffffu, old, 0);
+            const float lb = fmaxf(__uint_as_float(old), m);
+            cut = fmaxf(cut, (float)((double)lb * quality) * 0.999f);
+        }
     }
-
-    // 3x3 local maxima (ties kept, like eig == dilate(eig)) inside the 1-px image border
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const int r = threadIdx.y + 1, c = threadIdx.x + 1;
-    const float v = se[r][c];
-    bool is_cand = x >= 1 && x < w - 1 && y >= 1 && y < h - 1 && v > 0.f;
-    if (is_cand) {
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx)
-                if (se[r + dy][c + dx] > v) is_cand = false;
-    }
-    // conservative early cut: the running maximum only grows, so anything at or below
-    // 0.01 * (maximum so far) is certainly below the final threshold
-    if (is_cand) {
-        const float lb = __uint_as_float(*(volatile unsigned int*)(maxbits + frame));
-        if (v <= (float)((double)lb * quality) * 0.999f) is_cand = false;
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-    if (ball) {
-        const int lane = tid & 31;
+    // flush the rest of the queue
+    if (qn > 0) {
         int pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(seg_end + frame, __popc(ball));
+        if (lane == 0) pos0 = atomicAdd(seg_end + frame, qn);
         pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-        if (is_cand) {
-            const int pos = pos0 + __popc(ball & ((1u << lane) - 1u));
-            if (pos < (frame + 1) * cap)
-                keys[pos] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(unsigned)(y * w + x);
-        }
+        if (lane < qn && pos0 + lane < (frame + 1) * cap) keys[pos0 + lane] = queue[lane];
     }
 }
 
@@ -180,82 +189,100 @@ __global__ void clamp_segments_kernel(int* seg_end, int cap, int nframes) {
     if (f < nframes) seg_end[f] = min(seg_end[f], (f + 1) * cap);
 }
 
-// Greedy minimum-distance selection, one warp per frame.  The cell grid (4 u16 slots per
-// cell, {dy,dx} relative to the cell origin) lives in shared memory when it fits, else in
-// the global scratch `grid_glob`.
-__global__ void __launch_bounds__(32)
+// Greedy minimum-distance selection, one warp per frame (the other warps of the CTA only help to clear the grid).
+// The cell grid (4 u16 slots per cell, {dy,dx} relative to the cell origin) lives in shared memory when it
+// fits, else in the global scratch `grid_glob`.  32 candidates per step, in rank order:
+//   1. every lane tests its candidate against the accepted points of the 3 x 3 cells around it (branch-free);
+//   2. conflicts inside the batch: every lane builds the mask of lower-ranked lanes closer than min_distance, then
+//      the accept / reject sets grow to their fixed point with two ballots per round (a lane is accepted once all
+//      its conflicting lower lanes are rejected, rejected once one of them is accepted) -- the same set and order
+//      as OpenCV's sequential loop, without a serial pass over the lanes;
+//   3. accepted lanes append their point and register it in the grid.
+constexpr int kGreedyThreads = 128;
+
+__global__ void __launch_bounds__(kGreedyThreads)
 greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ seg_begin,
               const int* __restrict__ seg_end, const unsigned int* __restrict__ maxbits, double quality,
               int w, int min_distance, int cell, int grid_w, int grid_h,
               unsigned short* grid_glob, int use_smem, int max_corners,
               float2* __restrict__ pts, int* __restrict__ counts) {
     extern __shared__ unsigned short grid_sm[];
+    __shared__ int bxy[32];
     const int frame = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const unsigned long long* k = keys + seg_begin[frame];
     const int n = seg_end[frame] - seg_begin[frame];
     const int ncells = grid_w * grid_h;
     unsigned short* gfr = use_smem ? grid_sm : grid_glob + (size_t)frame * ncells * kCellCap;
     {
         uint2* g2 = reinterpret_cast<uint2*>(gfr);
-        for (int i = lane; i < ncells; i += 32) g2[i] = make_uint2(0xffffffffu, 0xffffffffu);
+        for (int i = threadIdx.x; i < ncells; i += kGreedyThreads) g2[i] = make_uint2(0xffffffffu, 0xffffffffu);
     }
-    __syncwarp();
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
     float2* out = pts + (size_t)frame * kMaxCorners;
     const int md2 = min_distance * min_distance;
     const float maxv = __uint_as_float(maxbits[frame]);
     const float thr = (float)((double)maxv * quality);       // cv::threshold takes float(thresh)
+    const unsigned lt = (1u << lane) - 1u;
     int accepted = 0;
+    unsigned long long key_next = lane < n ? k[lane] : 0ull;
 
     for (int base = 0; base < n && accepted < max_corners; base += 32) {
         const int rank = base + lane;
-        bool valid = rank < n;
-        int x = 0, y = 0;
-        if (valid) {
-            const unsigned long long key = k[rank];
-            valid = __uint_as_float((unsigned)(key >> 32)) > thr;     // THRESH_TOZERO cut: a prefix of the sorted list
-            const unsigned idx = (unsigned)(key & 0xffffffffull);
-            y = idx / w;
-            x = idx - y * w;
-        }
+        const unsigned long long key = key_next;
+        if (rank + 32 < n) key_next = k[rank + 32];
+        // THRESH_TOZERO cut: a prefix of the sorted list
+        const bool valid = rank < n && __uint_as_float((unsigned)(key >> 32)) > thr;
         if (!__any_sync(0xffffffffu, valid)) break;
+        const unsigned idx = (unsigned)(key & 0xffffffffull);
+        const int y = valid ? (int)(idx / (unsigned)w) : 0;
+        const int x = valid ? (int)(idx - (unsigned)y * (unsigned)w) : 0;
         bool ok = valid;
         int cx = 0, cy = 0;
         if (min_distance >= 1) {
             cx = x / cell;
             cy = y / cell;
-            if (valid) {
-                const int x1 = max(cx - 1, 0), x2 = min(cx + 1, grid_w - 1);
-                const int y1 = max(cy - 1, 0), y2 = min(cy + 1, grid_h - 1);
-                for (int gy = y1; gy <= y2 && ok; ++gy)
-                    for (int gx = x1; gx <= x2 && ok; ++gx) {
-                        const uint2 sl = *reinterpret_cast<const uint2*>(gfr + ((size_t)gy * grid_w + gx) * kCellCap);
-                        const unsigned s[4] = {sl.x & 0xffffu, sl.x >> 16, sl.y & 0xffffu, sl.y >> 16};
 #pragma unroll
-                        for (int q = 0; q < kCellCap; ++q) {
-                            if (s[q] != kEmpty16) {
-                                const int dx = x - (gx * cell + (int)(s[q] & 0xffu));
-                                const int dy = y - (gy * cell + (int)(s[q] >> 8));
-                                if (dx * dx + dy * dy < md2) ok = false;
-                            }
-                        }
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int gx = cx + dx, gy = cy + dy;
+                    const bool inb = gx >= 0 && gx < grid_w && gy >= 0 && gy < grid_h;
+                    const int gxc = min(max(gx, 0), grid_w - 1), gyc = min(max(gy, 0), grid_h - 1);
+                    uint2 sl = *reinterpret_cast<const uint2*>(gfr + ((size_t)gyc * grid_w + gxc) * kCellCap);
+                    if (!inb) sl = make_uint2(0xffffffffu, 0xffffffffu);
+                    const unsigned s4[4] = {sl.x & 0xffffu, sl.x >> 16, sl.y & 0xffffu, sl.y >> 16};
+                    const int ox = x - gxc * cell, oy = y - gyc * cell;
+#pragma unroll
+                    for (int q = 0; q < kCellCap; ++q) {
+                        const int ddx = ox - (int)(s4[q] & 0xffu), ddy = oy - (int)(s4[q] >> 8);
+                        if (s4[q] != kEmpty16 && ddx * ddx + ddy * ddy < md2) ok = false;
                     }
-            }
-            // resolve conflicts inside the batch in rank order
-            unsigned pending = __ballot_sync(0xffffffffu, ok);
-            while (pending) {
-                const int kk = __ffs(pending) - 1;             // lowest-rank still-ok lane: accepted
-                const int bx = __shfl_sync(0xffffffffu, x, kk);
-                const int by = __shfl_sync(0xffffffffu, y, kk);
-                if (lane > kk && ok) {
-                    const int dx = x - bx, dy = y - by;
-                    if (dx * dx + dy * dy < md2) ok = false;
                 }
-                pending = __ballot_sync(0xffffffffu, ok) & ~((2u << kk) - 1u);
+            // conflicts inside the batch, resolved in rank order
+            bxy[lane] = x | (y << 16);
+            __syncwarp();
+            unsigned cm = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int o = bxy[j];
+                const int ddx = x - (o & 0xffff), ddy = y - (o >> 16);
+                if (ddx * ddx + ddy * ddy < md2) cm |= 1u << j;
             }
+            __syncwarp();
+            const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+            cm &= lt & okmask;                                 // lower-ranked candidates that passed the grid test
+            unsigned acc = 0, rej = ~okmask;
+            for (;;) {
+                acc |= __ballot_sync(0xffffffffu, ok && (cm & ~rej) == 0);
+                rej |= __ballot_sync(0xffffffffu, ok && (cm & acc) != 0);
+                if ((acc | rej) == 0xffffffffu) break;
+            }
+            ok = (acc >> lane) & 1u;
         }
-        const unsigned acc = __ballot_sync(0xffffffffu, ok);
-        const int my = accepted + __popc(acc & ((1u << lane) - 1u));
+        const unsigned accm = __ballot_sync(0xffffffffu, ok);
+        const int my = accepted + __popc(accm & lt);
         if (ok && my < max_corners) {
             out[my] = make_float2((float)x, (float)y);
             if (min_distance >= 1) {
@@ -265,7 +292,7 @@ greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict
                     if (atomicCAS(cellp + q, kEmpty16, val) == kEmpty16) break;
             }
         }
-        accepted += __popc(acc);
+        accepted += __popc(accm);
         __syncwarp();
     }
     if (lane == 0) counts[frame] = min(accepted, max_corners);
@@ -324,9 +351,10 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     count_launch(4);   // reset, eig+candidates, clamp, greedy (+ cub's radix-sort passes, not counted)
     gftt_reset_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.maxbits, ws.seg_begin, ws.seg_end, ws.cap, nframes);
     {
-        dim3 grid((w + ETX - 1) / ETX, (h + ETY - 1) / ETY, nframes);
-        dim3 block(ETX, ETY);
-        eig_kernel<<<grid, block, 0, st>>>(gray, gray_frame_stride, w, h, eig_out, ws.maxbits, ws.keys, ws.seg_end, ws.cap, quality);
+        const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + kSegH - 1) / kSegH;
+        dim3 grid((nstrips * nsegs + kEigWarps - 1) / kEigWarps, nframes);
+        eig_kernel<<<grid, 32 * kEigWarps, 0, st>>>(gray, gray_frame_stride, w, h, nstrips, nsegs, eig_out, ws.maxbits, ws.keys,
+                                                    ws.seg_end, ws.cap, quality);
     }
     clamp_segments_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.seg_end, ws.cap, nframes);
     size_t temp = ws.cub_temp_bytes;
@@ -339,7 +367,7 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
         cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
         attr_set = true;
     }
-    greedy_kernel<<<nframes, 32, smem, st>>>(ws.keys_alt, ws.seg_begin, ws.seg_end, ws.maxbits, quality, w, min_distance,
+    greedy_kernel<<<nframes, kGreedyThreads, smem, st>>>(ws.keys_alt, ws.seg_begin, ws.seg_end, ws.maxbits, quality, w, min_distance,
                                              ws.cell, ws.grid_w, ws.grid_h, ws.grid, ws.grid_in_smem, max_corners,
                                              pts, counts);
 }
