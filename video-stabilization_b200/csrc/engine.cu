@@ -10,6 +10,8 @@
 // and the accumulated transform (:444).  The host keeps only integer indices, so a call
 // enqueues kernels and copies without ever reading a result back except the output frame.
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -179,6 +181,9 @@ struct vstab {
     DevBuf feat_ws, feat_gray, nn_x, nn_y, ref_kps, ref_desc, cur_kps, cur_desc, orb_counts, m_idx, m_d0, m_d1, m_good,
         m_ref, m_cur, m_status, lock_fit, lock_h, lock_tap;
     std::string err;
+    // VSTAB_TRACE=1: host wall-clock split of the streaming call (printed by vstab_destroy)
+    double trace_us[4] = {0, 0, 0, 0};   // enqueue output chain | enqueue upload + estimation | wait upload | wait output
+    long trace_calls = 0;
 
     void set_err(const std::string& e) { err = e; }
     uint8_t* pyr(int i) { return (i & 1) ? pyr1.as<uint8_t>() : pyr0.as<uint8_t>(); }
@@ -375,6 +380,10 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
     uint8_t* warp_dst = device_out ? out : s->dout.as<uint8_t>();
     const size_t warp_pitch = device_out ? out_step : g.pitch;
     const bool out_first = s->n > 0 && s->F >= 1;      // output chain does not need this call's transform
+    static const bool trace = getenv("VSTAB_TRACE") != nullptr;
+    auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tr0 = trace ? now_us() : 0.0;
+    double tr1 = 0.0;
 
     if (out_first) {
         CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));          // T[n-1], sums of frames <= n-1
@@ -383,6 +392,7 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
         if (!device_out)
             CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
     }
+    if (trace) tr1 = now_us();
     // estimation chain.  The ring slot being overwritten held frame n-W; its readers (the warp and the
     // channel sums of an earlier call's output chain) are ordered before this copy by ev_out.
     if (s->n > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_out, 0));
@@ -405,9 +415,16 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
         }
     }
     CK(cudaEventRecord(s->ev_out, s->out_stream));
+    const double tr2 = trace ? now_us() : 0.0;
     if (host_wait) {
         CK(cudaEventSynchronize(s->ev_in));                            // caller may reuse `in` (the reference clones, :160)
+        const double tr3 = trace ? now_us() : 0.0;
         CK(cudaStreamSynchronize(s->out_stream));                      // `out` is complete
+        if (trace) {
+            const double tr4 = now_us();
+            s->trace_us[0] += tr1 - tr0; s->trace_us[1] += tr2 - tr1; s->trace_us[2] += tr3 - tr2; s->trace_us[3] += tr4 - tr3;
+            s->trace_calls += 1;
+        }
     }
     s->n += 1;
     return VSTAB_OK;
@@ -482,6 +499,10 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
 void vstab_destroy(vstab_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->trace_calls > 0)
+        fprintf(stderr, "[vstab trace] %ld calls, per call: enqueue-output %.1f us, enqueue-upload+estimation %.1f us, "
+                        "wait-upload %.1f us, wait-output %.1f us\n", s->trace_calls, s->trace_us[0] / s->trace_calls,
+                s->trace_us[1] / s->trace_calls, s->trace_us[2] / s->trace_calls, s->trace_us[3] / s->trace_calls);
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
     if (s->out_stream) { cudaStreamSynchronize(s->out_stream); cudaStreamDestroy(s->out_stream); }
     if (s->ev_in) cudaEventDestroy(s->ev_in);

@@ -36,6 +36,11 @@ VSTAB_D int dp2a_hi_su(unsigned a, unsigned b, int c) {
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// keep a computed pointer in registers (ptxas otherwise rematerialises the 64-bit base arithmetic at every tap)
+VSTAB_D const unsigned* pin(const unsigned* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
 VSTAB_D unsigned pack_w(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 
 VSTAB_D long long warp_sum_i32(int v) {
@@ -106,26 +111,48 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
         int Iw[kStrides], Ix[kStrides], Iy[kStrides];
         int sA11 = 0, sA12 = 0, sA22 = 0;          // per lane <= 14 * 4080^2 < 2^31
         {
-            const int o0 = iy * P + ix;
+            // window origin as pinned 64-bit pointers: one 32->64-bit multiply-add per tap, nothing rematerialised
+            const unsigned* Ip = pin(I + (iy * P + ix));
+            const unsigned* Dp = pin(dI + (iy * P + ix));
+            const unsigned* DpP = pin(Dp + P);
+            if (w00 == (1 << 14)) {
+                // integer window origin (always at level 0: Shi-Tomasi corners are integer-valued): the bilinear taps
+                // collapse to the pixel itself -- (16384 p + 256) >> 9 == 32 p, (16384 d + 8192) >> 14 == d
 #pragma unroll
-            for (int s = 0; s < kStrides; ++s) {
-                Iw[s] = 0; Ix[s] = 0; Iy[s] = 0;
-                if (lane + 32 * s < kPix) {
-                    const int o = o0 + koff[s];
-                    const unsigned* g = dI + o;
-                    // the 2x2 neighbourhood in one word: 16-bit weights x 8-bit pixels, two dp2a
-                    const unsigned qi = __ldg(I + o);
-                    const int iv = dp2a_lo_su(wt01, qi, dp2a_hi_su(wt23, qi, 1 << 8));
-                    const unsigned d00 = __ldg(g), d01 = __ldg(g + 1), d10 = __ldg(g + P), d11 = __ldg(g + P + 1);
-                    const int xv = (int)(short)(d00 & 0xffffu) * w00 + (int)(short)(d01 & 0xffffu) * w01 +
-                                   (int)(short)(d10 & 0xffffu) * w10 + (int)(short)(d11 & 0xffffu) * w11;
-                    const int yv = ((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 + ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11;
-                    Iw[s] = iv >> 9;
-                    Ix[s] = (xv + (1 << 13)) >> 14;
-                    Iy[s] = (yv + (1 << 13)) >> 14;
-                    sA11 += Ix[s] * Ix[s];
-                    sA12 += Ix[s] * Iy[s];
-                    sA22 += Iy[s] * Iy[s];
+                for (int s = 0; s < kStrides; ++s) {
+                    Iw[s] = 0; Ix[s] = 0; Iy[s] = 0;
+                    if (lane + 32 * s < kPix) {
+                        const unsigned qi = __ldg(Ip + koff[s]);
+                        const unsigned d00 = __ldg(Dp + koff[s]);
+                        Iw[s] = (int)(qi & 0xffu) << 5;
+                        Ix[s] = (int)(short)(d00 & 0xffffu);
+                        Iy[s] = (int)d00 >> 16;
+                        sA11 += Ix[s] * Ix[s];
+                        sA12 += Ix[s] * Iy[s];
+                        sA22 += Iy[s] * Iy[s];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < kStrides; ++s) {
+                    Iw[s] = 0; Ix[s] = 0; Iy[s] = 0;
+                    if (lane + 32 * s < kPix) {
+                        const unsigned* g = Dp + koff[s];
+                        const unsigned* gP = DpP + koff[s];
+                        // the 2x2 neighbourhood in one word: 16-bit weights x 8-bit pixels, two dp2a
+                        const unsigned qi = __ldg(Ip + koff[s]);
+                        const int iv = dp2a_lo_su(wt01, qi, dp2a_hi_su(wt23, qi, 1 << 8));
+                        const unsigned d00 = __ldg(g), d01 = __ldg(g + 1), d10 = __ldg(gP), d11 = __ldg(gP + 1);
+                        const int xv = (int)(short)(d00 & 0xffffu) * w00 + (int)(short)(d01 & 0xffffu) * w01 +
+                                       (int)(short)(d10 & 0xffffu) * w10 + (int)(short)(d11 & 0xffffu) * w11;
+                        const int yv = ((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 + ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11;
+                        Iw[s] = iv >> 9;
+                        Ix[s] = (xv + (1 << 13)) >> 14;
+                        Iy[s] = (yv + (1 << 13)) >> 14;
+                        sA11 += Ix[s] * Ix[s];
+                        sA12 += Ix[s] * Iy[s];
+                        sA22 += Iy[s] * Iy[s];
+                    }
                 }
             }
         }
@@ -163,11 +190,11 @@ lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next
                 vt01 = pack_w(v00, v01); vt23 = pack_w(v10, v11);
             }
             int sb1 = 0, sb2 = 0;                   // per lane <= 14 * 8160 * 4080 < 2^31
-            const int o0 = jy * P + jx;
+            const unsigned* Jp = pin(J + (jy * P + jx));
 #pragma unroll
             for (int s = 0; s < kStrides; ++s) {
                 if (lane + 32 * s < kPix) {
-                    const unsigned q = __ldg(J + (o0 + koff[s]));
+                    const unsigned q = __ldg(Jp + koff[s]);
                     const int jv = dp2a_lo_su(vt01, q, dp2a_hi_su(vt23, q, 1 << 8)) >> 9;
                     const int diff = jv - Iw[s];
                     sb1 += diff * Ix[s];

@@ -49,13 +49,26 @@ pyrdown_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ pyr_out, s
     const int dx0 = blockIdx.x * TX, dy0 = blockIdx.y * TY;
     const int sx0 = 2 * dx0 - 2, sy0 = 2 * dy0 - 2;
     const int tid = threadIdx.y * TX + threadIdx.x;
-    for (int i = tid; i < SH * SW; i += TX * TY) {
-        const int r = i / SW, c = i - r * SW;
-        // rows/cols beyond what the clipped tile needs are still valid reflect indices
-        int yy = sy0 + r, xx = sx0 + c;
-        yy = reflect101(min(max(yy, -(sh - 1)), 2 * sh - 2), sh);
-        xx = reflect101(min(max(xx, -(sw - 1)), 2 * sw - 2), sw);
-        tile[r][c] = src[(size_t)yy * sw + xx];
+    {
+        // all loads of a thread in flight together
+        constexpr int kN = (SH * SW + TX * TY - 1) / (TX * TY);
+        uint8_t v[kN];
+#pragma unroll
+        for (int k = 0; k < kN; ++k) {
+            const int i = tid + k * TX * TY;
+            const int r = i / SW, c = i - r * SW;
+            // rows/cols beyond what the clipped tile needs are still valid reflect indices
+            int yy = sy0 + r, xx = sx0 + c;
+            yy = reflect101(min(max(yy, -(sh - 1)), 2 * sh - 2), sh);
+            xx = reflect101(min(max(xx, -(sw - 1)), 2 * sw - 2), sw);
+            if (i < SH * SW) v[k] = src[yy * sw + xx];
+        }
+#pragma unroll
+        for (int k = 0; k < kN; ++k) {
+            const int i = tid + k * TX * TY;
+            const int r = i / SW, c = i - r * SW;
+            if (i < SH * SW) tile[r][c] = v[k];
+        }
     }
     __syncthreads();
     // horizontal pass: SH rows x TX dst columns
@@ -88,9 +101,19 @@ struct PrepLevels {
     unsigned off[kLkLevels], poff[kLkLevels], doff[kLkLevels], qoff[kLkLevels];
 };
 
+// u8 pixels x s8 weights
+VSTAB_D int dp4a_us(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+constexpr int PTS = PTW + 8;                          // staged row stride (bytes, multiple of 4): PTW + 2 used
+
 __global__ void __launch_bounds__(PTX * PTY)
 lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
-    __shared__ uint8_t t[PTY + 2][PTW + 4];
+    __shared__ __align__(16) uint8_t t[PTY + 2][PTS];
+    __shared__ int sxs[PTW + 2], sys[PTY + 2];        // reflected source column / row offset of every staged column / row
     const int tile = blockIdx.x;
     int l = 0;
 #pragma unroll
@@ -102,31 +125,49 @@ lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
     uint8_t* base = pyr + (size_t)blockIdx.y * frame_bytes;
     const uint8_t* src = base + L.off[l];
     const int tid = threadIdx.y * PTX + threadIdx.x;
-    for (int i = tid; i < (PTY + 2) * (PTW + 2); i += PTX * PTY) {
-        const int r = i / (PTW + 2), c = i - r * (PTW + 2);
-        const int y = reflect101_multi(Y0 + r - 1 - kLkPad, h);
-        const int x = reflect101_multi(X0 + c - 1 - kLkPad, w);
-        t[r][c] = src[(size_t)y * w + x];
+    if (tid < PTW + 2) sxs[tid] = reflect101_multi(X0 + tid - 1 - kLkPad, w);
+    else if (tid < PTW + 2 + PTY + 2) sys[tid - (PTW + 2)] = reflect101_multi(Y0 + (tid - (PTW + 2)) - 1 - kLkPad, h) * w;
+    __syncthreads();
+    {
+        // all loads of a thread in flight together
+        constexpr int kN = ((PTY + 2) * (PTW + 2) + PTX * PTY - 1) / (PTX * PTY);
+        uint8_t v[kN];
+#pragma unroll
+        for (int k = 0; k < kN; ++k) {
+            const int i = tid + k * PTX * PTY;
+            const int r = i / (PTW + 2), c = i - r * (PTW + 2);
+            if (i < (PTY + 2) * (PTW + 2)) v[k] = src[sys[r] + sxs[c]];
+        }
+#pragma unroll
+        for (int k = 0; k < kN; ++k) {
+            const int i = tid + k * PTX * PTY;
+            const int r = i / (PTW + 2), c = i - r * (PTW + 2);
+            if (i < (PTY + 2) * (PTW + 2)) t[r][c] = v[k];
+        }
     }
     __syncthreads();
     const int Y = Y0 + threadIdx.y, X = X0 + threadIdx.x * PPX;
     if (Y >= h + 2 * kLkPad || X >= pitch) return;
-    const int r = threadIdx.y + 1, c0 = threadIdx.x * PPX + 1;
+    // staged bytes 4*tx .. 4*tx+5 of rows r-1, r, r+1 hold columns c-1 .. c+4 of this thread's 4 pixels
+    const int r = threadIdx.y + 1;
+    const unsigned* rm = reinterpret_cast<const unsigned*>(&t[r - 1][0]) + threadIdx.x;
+    const unsigned* r0 = reinterpret_cast<const unsigned*>(&t[r][0]) + threadIdx.x;
+    const unsigned* rp = reinterpret_cast<const unsigned*>(&t[r + 1][0]) + threadIdx.x;
+    const unsigned mlo = rm[0], mhi = rm[1], zlo = r0[0], zhi = r0[1], plo = rp[0], phi = rp[1];
     const int iy = Y - kLkPad;
+    const bool yin = iy >= 0 && iy < h;
     int dq[PPX], qq[PPX];
 #pragma unroll
     for (int k = 0; k < PPX; ++k) {
-        const int c = c0 + k, ix = X + k - kLkPad;
-        qq[k] = (int)((unsigned)t[r][c] | ((unsigned)t[r][c + 1] << 8) | ((unsigned)t[r + 1][c] << 16) | ((unsigned)t[r + 1][c + 1] << 24));
-        int dx = 0, dy = 0;
-        if (ix >= 0 && ix < w && iy >= 0 && iy < h) {
-            const int a00 = t[r - 1][c - 1], a01 = t[r - 1][c], a02 = t[r - 1][c + 1];
-            const int a10 = t[r][c - 1], a12 = t[r][c + 1];
-            const int a20 = t[r + 1][c - 1], a21 = t[r + 1][c], a22 = t[r + 1][c + 1];
-            dx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
-            dy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
-        }
-        dq[k] = (dx & 0xffff) | (dy << 16);
+        // columns (c-1, c, c+1, c+2) of the three rows
+        const unsigned wm = __funnelshift_r(mlo, mhi, 8 * k), w0 = __funnelshift_r(zlo, zhi, 8 * k),
+                       wp = __funnelshift_r(plo, phi, 8 * k);
+        qq[k] = (int)__byte_perm(w0, wp, 0x6521);           // {p(y,x), p(y,x+1), p(y+1,x), p(y+1,x+1)}
+        // Scharr: dx = 3 (p[-1,+1] - p[-1,-1]) + 10 (p[0,+1] - p[0,-1]) + 3 (p[+1,+1] - p[+1,-1]),  dy transposed
+        const int dx = dp4a_us(wp, 0x000300fdu, dp4a_us(w0, 0x000a00f6u, dp4a_us(wm, 0x000300fdu, 0)));
+        const int dy = dp4a_us(wp, 0x00030a03u, dp4a_us(wm, 0x00fdf6fdu, 0));
+        const int ix = X + k - kLkPad;
+        dq[k] = (yin && ix >= 0 && ix < w) ? ((dx & 0xffff) | (dy << 16)) : 0;
     }
     // pitch is a multiple of 4 and X is a multiple of 4: aligned vector stores
     *reinterpret_cast<int4*>(base + L.doff[l] + ((size_t)Y * pitch + X) * 4) = make_int4(dq[0], dq[1], dq[2], dq[3]);
