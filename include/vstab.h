@@ -124,7 +124,7 @@ typedef enum vstab_tap {
     VSTAB_TAP_H_STABILIZE = 10,/* f64 9     H_stabilize (working-res, :1266-1288)                 */
     VSTAB_TAP_H_SCALED = 11,   /* f64 9     H_stabilize_scaled (:1291-1296)                       */
     VSTAB_TAP_BORDER = 12,     /* u8  3     border colour after saturate_cast (:1309)             */
-    VSTAB_TAP_EIG = 13,        /* f32 working_h*working_w  min-eigenvalue map of the current gray  */
+    VSTAB_TAP_EIG = 13,        /* f32 working_h*working_w  min-eigenvalue map of the current gray (kept only with VSTAB_DEBUG_TAPS=1 in the environment) */
     VSTAB_TAP_INLIERS = 14,    /* i32 2     {n tracked, n RANSAC inliers}                         */
     VSTAB_TAP_CHANNEL_SUMS = 15,/* u64 3    per-channel byte sums of the presentation frame       */
     VSTAB_TAP_LOCK_H = 16,     /* f64 9     ORB registration: matrix returned by calculateFullLockStabilization (:784-787) */

@@ -1,10 +1,11 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pipeline.py -q -m gpu -x 2>&1 | tail -8
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-mode-probes > gpurun_out/exp.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k "gftt or lk" 2>&1 | tail -3
+for mb in 4 5 6; do
+VSTAB_LK_MINBLOCKS=$mb timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-mode-probes --no-e2e > gpurun_out/exp.log 2>&1
 python - <<PY
 import json,sys
 d=json.loads(open("gpurun_out/exp.log").read().strip().splitlines()[-1])
-s=d["stages"]; n=d["config"]["frames_per_gpu"]
-print("value", round(d["value"]), {k: round(v["ms_per_step"],3) for k,v in s.items()})
-print("e2e", d["e2e"]["value"], "streaming", d["e2e"]["streaming"]["value"])
+s=d["stages"]
+print("lk minblocks $mb value", round(d["value"]), {k: round(v["ms_per_step"],3) for k,v in s.items()})
 PY
+done

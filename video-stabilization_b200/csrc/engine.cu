@@ -157,6 +157,7 @@ struct vstab {
     cudaEvent_t ev_fit = nullptr;        // T[n] and the channel sums of frame n are final
     cudaEvent_t ev_out = nullptr;        // output chain of the previous call has finished reading the ring
     cudaStream_t gftt_stream = nullptr;  // corner detection of frame n runs beside LK / fit of frame n
+    cudaStream_t copy_stream = nullptr;  // host-to-device upload of frame n runs beside the estimation of frame n-1
     cudaEvent_t ev_pyr = nullptr;        // gray pyramid of frame n is complete
     cudaEvent_t ev_gftt = nullptr;       // corners of frame n are complete (needed by LK of frame n+1)
     size_t P = 15, F = 15;
@@ -184,6 +185,16 @@ struct vstab {
     // VSTAB_TRACE=1: host wall-clock split of the streaming call (printed by vstab_destroy)
     double trace_us[4] = {0, 0, 0, 0};   // enqueue output chain | enqueue upload + estimation | wait upload | wait output
     long trace_calls = 0;
+    // device-side marks of one call (timing events): 0 upload start, 1 upload end, 2 estimation start, 3 pyramid done,
+    // 4 LK+fit done, 5 corners start, 6 corners done, 7 output start, 8 smoothing done, 9 warp done, 10 download done
+    // (two sets, alternating per call: the marks of call n-1 are read at the end of call n, without draining the pipeline)
+    cudaEvent_t tev[2][11] = {};
+    double tev_ms[11] = {};              // [10]: upload start of the next call (the period)
+    long tev_calls = 0;
+    void mark(int i, cudaStream_t q) {
+        if (!tev[0][0]) return;
+        cudaEventRecord(tev[n & 1][i], q);
+    }
 
     void set_err(const std::string& e) { err = e; }
     uint8_t* pyr(int i) { return (i & 1) ? pyr1.as<uint8_t>() : pyr0.as<uint8_t>(); }
@@ -240,10 +251,12 @@ static vstab_status stream_estimate(vstab* s) {
     const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)slot * g.frame_bytes;
     unsigned long long* sums = s->sums.as<unsigned long long>() + slot * 3;
     int* ccount = s->ccount.as<int>();
+    s->mark(2, q);
     CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3, q));
     launch_ingest(g.plan, frame, g.pitch, g.frame_bytes, 1, s->pyr(cur), g.pd.frame_bytes, sums, q);   // :1169-1175
     launch_pyramid(g.pd, s->pyr(cur), 1, q);
     CK(cudaEventRecord(s->ev_pyr, q));
+    s->mark(3, q);
     if (n > 0) {
         CK(cudaStreamWaitEvent(q, s->ev_gftt, 0));                    // corners of frame n-1
         // :1187 trackFeatures
@@ -255,11 +268,15 @@ static vstab_status stream_estimate(vstab* s) {
                    s->fitc.as<int>(), nullptr, n, q);
     }
     CK(cudaEventRecord(s->ev_fit, q));
+    s->mark(4, q);
     // corner detection of this frame (:1318 / :1179) only feeds the next call's tracker: own stream
     CK(cudaStreamWaitEvent(s->gftt_stream, s->ev_pyr, 0));
+    s->mark(5, s->gftt_stream);
+    static const bool tap_eig = getenv("VSTAB_DEBUG_TAPS") != nullptr;   // the min-eigenvalue map is a debug tap only
     launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                s->corners(cur), ccount + cur, s->gws.eig, s->gftt_stream);
+                s->corners(cur), ccount + cur, tap_eig ? s->gws.eig : nullptr, s->gftt_stream);
     CK(cudaEventRecord(s->ev_gftt, s->gftt_stream));
+    s->mark(6, s->gftt_stream);
     CK(cudaGetLastError());
     return VSTAB_OK;
 }
@@ -342,6 +359,7 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
     cudaStream_t q = s->out_stream;
     const long n = s->n;
     const long p = n - (long)s->F > 0 ? n - (long)s->F : 0;                                            // :1226-1229
+    s->mark(7, q);
     if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) {                                                      // :317-338
         launch_acc_update(s->T.as<double>(), s->t_mod, p, s->acc_valid ? 0 : 1, s->acc.as<double>(), q);
         s->acc_valid = true;
@@ -362,8 +380,10 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
     a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
     a.npix = (double)g.rows * (double)g.cols;
     launch_smooth(a, n, 1, s->wp.as<WarpParams>(), q);                                                 // :1234-1296
+    s->mark(8, q);
     launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
                 d_out, out_pitch, 0, q);                                                               // :1309-1313
+    s->mark(9, q);
     CK(cudaGetLastError());
     s->last_presented = p;
     return VSTAB_OK;
@@ -384,6 +404,8 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
     auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = trace ? now_us() : 0.0;
     double tr1 = 0.0;
+    if (trace && !s->tev[0][0])
+        for (auto& set : s->tev) for (auto& e : set) cudaEventCreate(&e);
 
     if (out_first) {
         CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));          // T[n-1], sums of frames <= n-1
@@ -395,9 +417,14 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
     if (trace) tr1 = now_us();
     // estimation chain.  The ring slot being overwritten held frame n-W; its readers (the warp and the
     // channel sums of an earlier call's output chain) are ordered before this copy by ev_out.
-    if (s->n > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_out, 0));
-    CK(cudaMemcpy2DAsync(slot, g.pitch, in, step, row_bytes, rows, in_kind, s->stream));
-    CK(cudaEventRecord(s->ev_in, s->stream));
+    // Host input: the upload runs on its own stream, beside the estimation of the previous frame.
+    cudaStream_t up = in_kind == cudaMemcpyHostToDevice ? s->copy_stream : s->stream;
+    if (s->n > 0) CK(cudaStreamWaitEvent(up, s->ev_out, 0));
+    s->mark(0, up);
+    CK(cudaMemcpy2DAsync(slot, g.pitch, in, step, row_bytes, rows, in_kind, up));
+    s->mark(1, up);
+    CK(cudaEventRecord(s->ev_in, up));
+    if (up != s->stream) CK(cudaStreamWaitEvent(s->stream, s->ev_in, 0));
     vstab_status st = stream_estimate(s);
     if (st != VSTAB_OK) return st;
     if (!out_first) {
@@ -414,6 +441,7 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
                 CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
         }
     }
+    s->mark(10, s->out_stream);
     CK(cudaEventRecord(s->ev_out, s->out_stream));
     const double tr2 = trace ? now_us() : 0.0;
     if (host_wait) {
@@ -424,6 +452,18 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
             const double tr4 = now_us();
             s->trace_us[0] += tr1 - tr0; s->trace_us[1] += tr2 - tr1; s->trace_us[2] += tr3 - tr2; s->trace_us[3] += tr4 - tr3;
             s->trace_calls += 1;
+            // device-side marks of the previous call relative to its upload start (skipped while its corner
+            // detection is still running)
+            const int pv = (int)((s->n - 1) & 1), cu = (int)(s->n & 1);
+            if (out_first && s->n > 3 && cudaEventQuery(s->tev[pv][6]) == cudaSuccess && cudaEventQuery(s->tev[pv][4]) == cudaSuccess) {
+                for (int i = 1; i <= 10; ++i) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, s->tev[pv][0], s->tev[pv][i]) == cudaSuccess) s->tev_ms[i - 1] += ms;
+                }
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, s->tev[pv][0], s->tev[cu][0]) == cudaSuccess) s->tev_ms[10] += ms;
+                s->tev_calls += 1;
+            }
         }
     }
     s->n += 1;
@@ -488,6 +528,7 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
         cudaEventCreateWithFlags(&s->ev_fit, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->gftt_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_gftt, cudaEventDisableTiming) != cudaSuccess) {
         g_err = "cudaStreamCreate failed"; vstab_destroy(s); return VSTAB_ERR_CUDA;
@@ -503,12 +544,20 @@ void vstab_destroy(vstab_t* s) {
         fprintf(stderr, "[vstab trace] %ld calls, per call: enqueue-output %.1f us, enqueue-upload+estimation %.1f us, "
                         "wait-upload %.1f us, wait-output %.1f us\n", s->trace_calls, s->trace_us[0] / s->trace_calls,
                 s->trace_us[1] / s->trace_calls, s->trace_us[2] / s->trace_calls, s->trace_us[3] / s->trace_calls);
+    if (s->tev_calls > 0) {
+        static const char* nm[10] = {"upload end", "estimation start", "pyramid done", "LK+fit done", "corners start",
+                                     "corners done", "output start", "smoothing done", "warp done", "download done"};
+        fprintf(stderr, "[vstab trace] device marks of a call relative to its upload start (us, %ld calls):", s->tev_calls);
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %.1f;", nm[i], 1e3 * s->tev_ms[i] / s->tev_calls);
+        fprintf(stderr, " next upload start %.1f\n", 1e3 * s->tev_ms[10] / s->tev_calls);
+    }
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
     if (s->out_stream) { cudaStreamSynchronize(s->out_stream); cudaStreamDestroy(s->out_stream); }
     if (s->ev_in) cudaEventDestroy(s->ev_in);
     if (s->ev_fit) cudaEventDestroy(s->ev_fit);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
     if (s->gftt_stream) { cudaStreamSynchronize(s->gftt_stream); cudaStreamDestroy(s->gftt_stream); }
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     if (s->ev_pyr) cudaEventDestroy(s->ev_pyr);
     if (s->ev_gftt) cudaEventDestroy(s->ev_gftt);
     if (s->orb) orb_plan_destroy(s->orb);
@@ -539,6 +588,7 @@ vstab_status vstab_synchronize(vstab_t* s) {
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->out_stream));
     CK(cudaStreamSynchronize(s->gftt_stream));
+    CK(cudaStreamSynchronize(s->copy_stream));
     return VSTAB_OK;
 }
 

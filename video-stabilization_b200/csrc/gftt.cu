@@ -12,6 +12,7 @@
 //   pass C  greedy min-distance suppression in sorted order on a cell grid held in shared
 //           memory, one warp per frame, 32 candidates per step with ballot/shuffle conflict
 //           resolution -- the accepted set and its order equal the sequential OpenCV loop.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include "kernels.h"
 
@@ -33,7 +34,7 @@ constexpr int kStripW = 28, kSegH = 60, kEigWarps = 4;
 
 struct D3 { double xx, xy, yy; };
 
-__global__ void __launch_bounds__(32 * kEigWarps)
+__global__ void __launch_bounds__(32 * kEigWarps, 8)
 eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs,
            float* __restrict__ eig_out, unsigned int* __restrict__ maxbits,
            unsigned long long* __restrict__ keys, int* __restrict__ seg_end, int cap, double quality) {
@@ -193,7 +194,8 @@ __global__ void clamp_segments_kernel(int* seg_end, int cap, int nframes) {
 // The cell grid (4 u16 slots per cell, {dy,dx} relative to the cell origin) lives in shared memory when it
 // fits, else in the global scratch `grid_glob`.  32 candidates per step, in rank order:
 //   1. every lane tests its candidate against the accepted points of the 3 x 3 cells around it (branch-free);
-//   2. conflicts inside the batch: every lane builds the mask of lower-ranked lanes closer than min_distance, then
+//   2. conflicts inside the batch: every surviving lane builds the mask of lower-ranked survivors closer than
+//      min_distance, then
 //      the accept / reject sets grow to their fixed point with two ballots per round (a lane is accepted once all
 //      its conflicting lower lanes are rejected, rejected once one of them is accepted) -- the same set and order
 //      as OpenCV's sequential loop, without a serial pass over the lanes;
@@ -260,19 +262,20 @@ greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict
                         if (s4[q] != kEmpty16 && ddx * ddx + ddy * ddy < md2) ok = false;
                     }
                 }
-            // conflicts inside the batch, resolved in rank order
-            bxy[lane] = x | (y << 16);
+            // conflicts inside the batch, resolved in rank order: one pass over the compact list of the survivors
+            const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+            const int nok = __popc(okmask);
+            if (ok) bxy[__popc(okmask & lt)] = x | (y << 12) | (lane << 24);     // (x, y < 4096)
             __syncwarp();
             unsigned cm = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int o = bxy[j];
-                const int ddx = x - (o & 0xffff), ddy = y - (o >> 16);
-                if (ddx * ddx + ddy * ddy < md2) cm |= 1u << j;
+#pragma unroll 4
+            for (int t = 0; t < nok; ++t) {
+                const int o = bxy[t];
+                const int ddx = x - (o & 0xfff), ddy = y - ((o >> 12) & 0xfff);
+                if (ddx * ddx + ddy * ddy < md2) cm |= 1u << (o >> 24);
             }
             __syncwarp();
-            const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-            cm &= lt & okmask;                                 // lower-ranked candidates that passed the grid test
+            cm &= lt;                                          // lower-ranked candidates that passed the grid test
             unsigned acc = 0, rej = ~okmask;
             for (;;) {
                 acc |= __ballot_sync(0xffffffffu, ok && (cm & ~rej) == 0);
@@ -315,6 +318,12 @@ size_t gftt_workspace_bytes(int w, int h, int min_distance, int max_frames, Gftt
     cub::DeviceSegmentedRadixSort::SortKeysDescending(
         nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
         (int)((size_t)ws.cap * max_frames), max_frames, (const int*)nullptr, (const int*)nullptr, 0, 64);
+    // a single frame (streaming) is sorted with the device-wide radix sort instead: the segmented sort would put the
+    // whole segment on one CTA
+    size_t temp1 = 0;
+    cub::DeviceRadixSort::SortKeysDescending(nullptr, temp1, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                             ws.cap, 0, 63);
+    if (temp1 > temp) temp = temp1;
     ws.cub_temp_bytes = temp;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -349,6 +358,8 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     if (nframes <= 0) return;
     if (max_corners > kMaxCorners) max_corners = kMaxCorners;
     count_launch(4);   // reset, eig+candidates, clamp, greedy (+ cub's radix-sort passes, not counted)
+    // one frame: unused key slots are zero, so the whole buffer can be sorted (every candidate key is > 0)
+    if (nframes == 1) cudaMemsetAsync(ws.keys, 0, sizeof(unsigned long long) * (size_t)ws.cap, st);
     gftt_reset_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.maxbits, ws.seg_begin, ws.seg_end, ws.cap, nframes);
     {
         const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + kSegH - 1) / kSegH;
@@ -358,9 +369,12 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     }
     clamp_segments_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.seg_end, ws.cap, nframes);
     size_t temp = ws.cub_temp_bytes;
-    cub::DeviceSegmentedRadixSort::SortKeysDescending(
-        ws.cub_temp, temp, (const unsigned long long*)ws.keys, ws.keys_alt, (int)((size_t)ws.cap * nframes),
-        nframes, (const int*)ws.seg_begin, (const int*)ws.seg_end, 0, 63, st);
+    if (nframes == 1)
+        cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, (const unsigned long long*)ws.keys, ws.keys_alt, ws.cap, 0, 63, st);
+    else
+        cub::DeviceSegmentedRadixSort::SortKeysDescending(
+            ws.cub_temp, temp, (const unsigned long long*)ws.keys, ws.keys_alt, (int)((size_t)ws.cap * nframes),
+            nframes, (const int*)ws.seg_begin, (const int*)ws.seg_end, 0, 63, st);
     const size_t smem = ws.grid_in_smem ? (size_t)ws.ncells * kCellCap * sizeof(unsigned short) : 0;
     static bool attr_set = false;
     if (!attr_set) {

@@ -17,6 +17,8 @@
 namespace vstabk {
 namespace {
 
+constexpr int kSmoothMaxTerms = 256;         // window terms staged in shared memory (18 KB); longer windows read global memory
+
 VSTAB_D const double* t_at(const SmoothArgs& a, long k) { return a.T + (size_t)(k % a.t_mod) * 9; }
 
 __global__ void __launch_bounds__(32)
@@ -29,25 +31,51 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
     const long lo = c - W + 1 > 0 ? c - W + 1 : 0;
     const long p = c - a.F > 0 ? c - a.F : 0;
 
+    // lock modes before their lock call still present the window average (mode 5)
+    int mode = a.mode;
+    if ((mode == 0 || mode == 1 || mode == 2) && c < a.lock_call) mode = 5;
+
     double sum[9];
     for (int i = 0; i < 9; ++i) sum[i] = 0.0;
     int count = 0;
-    if (lane == 0) {
-        double acc[9], inv[9], tmp[9];
-        eye3(acc);
-        for (long k = p; k > lo; --k) {                 // T[p], T[p-1], ..., T[lo+1]
-            invert3(t_at(a, k), inv);
-            matmul3(inv, acc, tmp);
-            for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sum[i] += tmp[i]; }
-            ++count;
+    // The window's transforms are staged in shared memory (the chains below would otherwise pay a global-memory
+    // round trip per term) and the past ones are inverted in parallel, one matrix per lane at a time; the two
+    // chains themselves stay sequential in the reference's order (lane 0: past, lane 1: future).
+    __shared__ double sT[kSmoothMaxTerms][9];
+    const long npast = p - lo, nfut = c - 1 - p > 0 ? c - 1 - p : 0;
+    const bool staged = npast + nfut <= kSmoothMaxTerms;
+    if (mode == 5 && staged) {
+        for (long t = lane; t < npast + nfut; t += 32) {
+            // slot t < npast: inverse of T[p - t]; slot npast + r: T[p + 1 + r]
+            const double* src = t < npast ? t_at(a, p - t) : t_at(a, p + 1 + (t - npast));
+            double m[9];
+            for (int i = 0; i < 9; ++i) m[i] = src[i];
+            if (t < npast) invert3(m, sT[t]);
+            else for (int i = 0; i < 9; ++i) sT[t][i] = m[i];
         }
-    } else if (lane == 1) {
-        double acc[9], tmp[9];
-        eye3(acc);
-        for (long k = p + 1; k <= c - 1; ++k) {         // T[p+1] ... T[c-1]
-            matmul3(acc, t_at(a, k), tmp);
-            for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sum[i] += tmp[i]; }
-            ++count;
+        __syncwarp();
+    }
+    if (mode == 5) {
+        if (lane == 0) {
+            double acc[9], inv[9], tmp[9];
+            eye3(acc);
+            for (long k = p; k > lo; --k) {                 // T[p], T[p-1], ..., T[lo+1]
+                if (staged) for (int i = 0; i < 9; ++i) inv[i] = sT[p - k][i];
+                else invert3(t_at(a, k), inv);
+                matmul3(inv, acc, tmp);
+                for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sum[i] += tmp[i]; }
+                ++count;
+            }
+        } else if (lane == 1) {
+            double acc[9], tmp[9], cur[9];
+            eye3(acc);
+            for (long k = p + 1; k <= c - 1; ++k) {         // T[p+1] ... T[c-1]
+                const double* src = staged ? sT[npast + (k - p - 1)] : t_at(a, k);
+                for (int i = 0; i < 9; ++i) cur[i] = src[i];
+                matmul3(acc, cur, tmp);
+                for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sum[i] += tmp[i]; }
+                ++count;
+            }
         }
     }
     // combine: avg = past_sum + future_sum (the reference adds past terms first)
@@ -69,8 +97,6 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
     }
 
     // ---- full-lock transform -------------------------------------------------------------
-    int mode = a.mode;
-    if ((mode == 0 || mode == 1 || mode == 2) && c < a.lock_call) mode = 5;   // lock not yet set at this call
     double Hl[9];
     eye3(Hl);
     if (mode == 0) {
