@@ -1,11 +1,4 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k "gftt or lk" 2>&1 | tail -3
-for mb in 4 5 6; do
-VSTAB_LK_MINBLOCKS=$mb timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-mode-probes --no-e2e > gpurun_out/exp.log 2>&1
-python - <<PY
-import json,sys
-d=json.loads(open("gpurun_out/exp.log").read().strip().splitlines()[-1])
-s=d["stages"]
-print("lk minblocks $mb value", round(d["value"]), {k: round(v["ms_per_step"],3) for k,v in s.items()})
-PY
-done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/stream_launches.csv python tools/stream_probe.py 56 > gpurun_out/stream_probe.log 2>&1
+tail -2 gpurun_out/stream_probe.log
+wc -l gpurun_out/stream_launches.csv

@@ -12,7 +12,8 @@
 //   pass C  greedy min-distance suppression in sorted order on a cell grid held in shared
 //           memory, one warp per frame, 32 candidates per step with ballot/shuffle conflict
 //           resolution -- the accepted set and its order equal the sequential OpenCV loop.
-#include <cub/device/device_radix_sort.cuh>
+#include <cstdlib>
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include "kernels.h"
 
@@ -35,7 +36,7 @@ constexpr int kStripW = 28, kSegH = 60, kEigWarps = 4;
 struct D3 { double xx, xy, yy; };
 
 __global__ void __launch_bounds__(32 * kEigWarps, 8)
-eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs,
+eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs, int idx_bits,
            float* __restrict__ eig_out, unsigned int* __restrict__ maxbits,
            unsigned long long* __restrict__ keys, int* __restrict__ seg_end, int cap, double quality) {
     const int lane = threadIdx.x & 31;
@@ -136,7 +137,7 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
                         // append to this warp's queue; 32 keys leave with one atomic and one coalesced 256-byte store
                         if (is_cand)
                             queue[qn + __popc(ball & ((1u << lane) - 1u))] =
-                                ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(unsigned)(yc * w + xe);
+                                ((unsigned long long)__float_as_uint(v) << idx_bits) | (unsigned long long)(unsigned)(yc * w + xe);
                         qn += __popc(ball);
                         __syncwarp();
                         if (qn >= 32) {
@@ -202,42 +203,25 @@ __global__ void clamp_segments_kernel(int* seg_end, int cap, int nframes) {
 //   3. accepted lanes append their point and register it in the grid.
 constexpr int kGreedyThreads = 128;
 
-__global__ void __launch_bounds__(kGreedyThreads)
-greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ seg_begin,
-              const int* __restrict__ seg_end, const unsigned int* __restrict__ maxbits, double quality,
-              int w, int min_distance, int cell, int grid_w, int grid_h,
-              unsigned short* grid_glob, int use_smem, int max_corners,
-              float2* __restrict__ pts, int* __restrict__ counts) {
-    extern __shared__ unsigned short grid_sm[];
-    __shared__ int bxy[32];
-    const int frame = blockIdx.x;
+// Steps 1-3 for the sorted candidates k[0..n) of one frame, executed by one warp; `accepted` carries over between
+// chunks of the same frame.  Returns false once a candidate at or below the quality threshold shows up (everything
+// after it is below, too).
+VSTAB_D bool greedy_warp(const unsigned long long* __restrict__ k, int n, int idx_bits, float thr, int w, int min_distance,
+                         int cell, int grid_w, int grid_h, unsigned short* gfr, int* bxy, int max_corners,
+                         float2* __restrict__ out, int& accepted) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long* k = keys + seg_begin[frame];
-    const int n = seg_end[frame] - seg_begin[frame];
-    const int ncells = grid_w * grid_h;
-    unsigned short* gfr = use_smem ? grid_sm : grid_glob + (size_t)frame * ncells * kCellCap;
-    {
-        uint2* g2 = reinterpret_cast<uint2*>(gfr);
-        for (int i = threadIdx.x; i < ncells; i += kGreedyThreads) g2[i] = make_uint2(0xffffffffu, 0xffffffffu);
-    }
-    __syncthreads();
-    if (threadIdx.x >= 32) return;
-    float2* out = pts + (size_t)frame * kMaxCorners;
     const int md2 = min_distance * min_distance;
-    const float maxv = __uint_as_float(maxbits[frame]);
-    const float thr = (float)((double)maxv * quality);       // cv::threshold takes float(thresh)
     const unsigned lt = (1u << lane) - 1u;
-    int accepted = 0;
+    const unsigned long long idx_mask = (1ull << idx_bits) - 1ull;
     unsigned long long key_next = lane < n ? k[lane] : 0ull;
-
     for (int base = 0; base < n && accepted < max_corners; base += 32) {
         const int rank = base + lane;
         const unsigned long long key = key_next;
         if (rank + 32 < n) key_next = k[rank + 32];
         // THRESH_TOZERO cut: a prefix of the sorted list
-        const bool valid = rank < n && __uint_as_float((unsigned)(key >> 32)) > thr;
-        if (!__any_sync(0xffffffffu, valid)) break;
-        const unsigned idx = (unsigned)(key & 0xffffffffull);
+        const bool valid = rank < n && __uint_as_float((unsigned)(key >> idx_bits)) > thr;
+        if (!__any_sync(0xffffffffu, valid)) return false;
+        const unsigned idx = (unsigned)(key & idx_mask);
         const int y = valid ? (int)(idx / (unsigned)w) : 0;
         const int x = valid ? (int)(idx - (unsigned)y * (unsigned)w) : 0;
         bool ok = valid;
@@ -298,7 +282,152 @@ greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict
         accepted += __popc(accm);
         __syncwarp();
     }
-    if (lane == 0) counts[frame] = min(accepted, max_corners);
+    return true;
+}
+
+// Unfused schedule: the keys were sorted by cub (one segment per frame).
+__global__ void __launch_bounds__(kGreedyThreads)
+greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ seg_begin,
+              const int* __restrict__ seg_end, const unsigned int* __restrict__ maxbits, double quality, int idx_bits,
+              int w, int min_distance, int cell, int grid_w, int grid_h,
+              unsigned short* grid_glob, int use_smem, int max_corners,
+              float2* __restrict__ pts, int* __restrict__ counts) {
+    extern __shared__ unsigned short grid_sm[];
+    __shared__ int bxy[32];
+    const int frame = blockIdx.x;
+    const int ncells = grid_w * grid_h;
+    unsigned short* gfr = use_smem ? grid_sm : grid_glob + (size_t)frame * ncells * kCellCap;
+    {
+        uint2* g2 = reinterpret_cast<uint2*>(gfr);
+        for (int i = threadIdx.x; i < ncells; i += kGreedyThreads) g2[i] = make_uint2(0xffffffffu, 0xffffffffu);
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const float thr = (float)((double)__uint_as_float(maxbits[frame]) * quality);       // cv::threshold takes float(thresh)
+    int accepted = 0;
+    greedy_warp(keys + seg_begin[frame], seg_end[frame] - seg_begin[frame], idx_bits, thr, w, min_distance, cell, grid_w,
+                grid_h, gfr, bxy, max_corners, pts + (size_t)frame * kMaxCorners, accepted);
+    if ((threadIdx.x & 31) == 0) counts[frame] = min(accepted, max_corners);
+}
+
+// Fused schedule (the default): one CTA per frame selects, sorts and consumes the candidates without leaving the SM.
+//   * the unsorted candidate keys of the frame (value << idx_bits | pixel index: unique, so "k-th largest" is exact) are
+//     taken in chunks of at most kTkCap = 8192, largest first: when more are left than a chunk holds, a radix select
+//     (10-bit digits, MSB first, histograms in shared memory) finds the key T with exactly kTkCap keys in [T, upper);
+//   * the chunk is gathered into shared memory, sorted with cub::BlockRadixSort (1024 threads x 8 keys, only the
+//     significant bits) and handed to warp 0 for the greedy pass; the next chunk is only needed when fewer than
+//     max_corners points were accepted and candidates above the quality threshold remain (rare: 0.01 * max cuts the
+//     list to ~4.5 k keys at working height 360, ~16 k at 1080).
+constexpr int kTkThreads = 1024, kTkItems = 8, kTkCap = kTkThreads * kTkItems;
+typedef cub::BlockRadixSort<unsigned long long, kTkThreads, kTkItems> TkSort;
+union TkScratch {
+    typename TkSort::TempStorage sort;
+    unsigned long long keys[kTkCap];
+};
+
+__global__ void __launch_bounds__(kTkThreads)
+topk_greedy_kernel(const unsigned long long* __restrict__ keys_all, const int* __restrict__ seg_begin,
+                   int* __restrict__ seg_end, unsigned int* __restrict__ maxbits, double quality, int idx_bits, int cap,
+                   int w, int min_distance, int cell, int grid_w, int grid_h, int max_corners,
+                   float2* __restrict__ pts, int* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    TkScratch& S = *reinterpret_cast<TkScratch*>(tk_smem);
+    unsigned short* gfr = reinterpret_cast<unsigned short*>(tk_smem + sizeof(TkScratch));
+    __shared__ unsigned hist[1024];
+    __shared__ int bxy[32];
+    __shared__ int s_cnt, s_accepted, s_more, s_digit, s_k;
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned long long* keys = keys_all + seg_begin[frame];
+    const int n = min(seg_end[frame] - seg_begin[frame], cap);
+    const int ncells = grid_w * grid_h;
+    {
+        uint2* g2 = reinterpret_cast<uint2*>(gfr);
+        for (int i = tid; i < ncells; i += kTkThreads) g2[i] = make_uint2(0xffffffffu, 0xffffffffu);
+    }
+    if (tid == 0) { s_accepted = 0; s_more = 1; }
+    const float thr = (float)((double)__uint_as_float(maxbits[frame]) * quality);       // cv::threshold takes float(thresh)
+    const int key_bits = 31 + idx_bits;
+    unsigned long long upper = ~0ull;                  // keys not yet consumed are < upper
+    int remaining = n;
+    __syncthreads();
+    while (remaining > 0) {
+        // ---- threshold of this chunk: the kTkCap-th largest key below `upper` (0: take everything that is left)
+        unsigned long long T = 0ull;
+        if (remaining > kTkCap) {
+            unsigned long long prefix = 0ull, pmask = 0ull;
+            if (tid == 0) s_k = kTkCap;
+            for (int top = key_bits; top > 0; top -= 10) {
+                const int shift = top > 10 ? top - 10 : 0;
+                const unsigned dmask = (1u << (top - shift)) - 1u;
+                hist[tid] = 0u;
+                __syncthreads();
+                for (int i = tid; i < n; i += kTkThreads) {
+                    const unsigned long long key = keys[i];
+                    if (key < upper && (key & pmask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & dmask], 1u);
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    // lane l owns digits [32 l, 32 l + 32); find the digit where the count from the top reaches k
+                    unsigned sum = 0;
+                    for (int d = 0; d < 32; ++d) sum += hist[lane * 32 + d];
+                    unsigned above = 0;                // keys in digits owned by higher lanes
+                    for (int o = 1; o < 32; ++o) {
+                        const unsigned v = __shfl_down_sync(0xffffffffu, sum, o);
+                        if (lane + o < 32) above += v;
+                    }
+                    const unsigned k = (unsigned)s_k;
+                    if (above < k && above + sum >= k) {
+                        unsigned cum = above;
+                        for (int d = 31; d >= 0; --d) {
+                            const unsigned c = hist[lane * 32 + d];
+                            if (cum + c >= k) { s_digit = lane * 32 + d; s_k = (int)(k - cum); break; }
+                            cum += c;
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= (unsigned long long)(unsigned)s_digit << shift;
+                pmask |= (unsigned long long)dmask << shift;
+                __syncthreads();
+            }
+            T = prefix;
+        }
+        // ---- gather the chunk [T, upper) into shared memory, sort it (descending), hand it to warp 0
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kTkThreads) {
+            const unsigned long long key = keys[i];
+            if (key >= T && key < upper) S.keys[atomicAdd(&s_cnt, 1)] = key;
+        }
+        __syncthreads();
+        const int m = s_cnt;
+        unsigned long long mine[kTkItems];
+#pragma unroll
+        for (int i = 0; i < kTkItems; ++i) mine[i] = tid * kTkItems + i < m ? S.keys[tid * kTkItems + i] : 0ull;
+        __syncthreads();
+        TkSort(S.sort).SortDescending(mine, 0, key_bits);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kTkItems; ++i) S.keys[tid * kTkItems + i] = mine[i];
+        __syncthreads();
+        if (tid < 32) {
+            int accepted = s_accepted;
+            const bool more = greedy_warp(S.keys, m, idx_bits, thr, w, min_distance, cell, grid_w, grid_h, gfr, bxy, max_corners,
+                                          pts + (size_t)frame * kMaxCorners, accepted);
+            if (lane == 0) { s_accepted = accepted; s_more = (more && accepted < max_corners) ? 1 : 0; }
+        }
+        __syncthreads();
+        remaining -= m;
+        upper = T;
+        if (!s_more || T == 0ull) break;
+    }
+    if (tid == 0) {
+        counts[frame] = min(s_accepted, max_corners);
+        // leave the per-frame counters ready for the next launch (saves a reset kernel per call)
+        maxbits[frame] = 0u;
+        seg_end[frame] = seg_begin[frame];
+    }
 }
 
 }  // namespace
@@ -318,13 +447,10 @@ size_t gftt_workspace_bytes(int w, int h, int min_distance, int max_frames, Gftt
     cub::DeviceSegmentedRadixSort::SortKeysDescending(
         nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
         (int)((size_t)ws.cap * max_frames), max_frames, (const int*)nullptr, (const int*)nullptr, 0, 64);
-    // a single frame (streaming) is sorted with the device-wide radix sort instead: the segmented sort would put the
-    // whole segment on one CTA
-    size_t temp1 = 0;
-    cub::DeviceRadixSort::SortKeysDescending(nullptr, temp1, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                             ws.cap, 0, 63);
-    if (temp1 > temp) temp = temp1;
     ws.cub_temp_bytes = temp;
+    ws.idx_bits = 1;
+    while (((size_t)1 << ws.idx_bits) < (size_t)w * h) ++ws.idx_bits;
+    ws.counters_ready = 0;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     // offsets are stored in the pointer fields and rebased by gftt_bind_workspace
@@ -357,33 +483,48 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
                  float2* pts, int* counts, float* eig_out, cudaStream_t st) {
     if (nframes <= 0) return;
     if (max_corners > kMaxCorners) max_corners = kMaxCorners;
-    count_launch(4);   // reset, eig+candidates, clamp, greedy (+ cub's radix-sort passes, not counted)
-    // one frame: unused key slots are zero, so the whole buffer can be sorted (every candidate key is > 0)
-    if (nframes == 1) cudaMemsetAsync(ws.keys, 0, sizeof(unsigned long long) * (size_t)ws.cap, st);
-    gftt_reset_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.maxbits, ws.seg_begin, ws.seg_end, ws.cap, nframes);
-    {
-        const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + kSegH - 1) / kSegH;
-        dim3 grid((nstrips * nsegs + kEigWarps - 1) / kEigWarps, nframes);
-        eig_kernel<<<grid, 32 * kEigWarps, 0, st>>>(gray, gray_frame_stride, w, h, nstrips, nsegs, eig_out, ws.maxbits, ws.keys,
-                                                    ws.seg_end, ws.cap, quality);
-    }
-    clamp_segments_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.seg_end, ws.cap, nframes);
-    size_t temp = ws.cub_temp_bytes;
-    if (nframes == 1)
-        cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, (const unsigned long long*)ws.keys, ws.keys_alt, ws.cap, 0, 63, st);
-    else
-        cub::DeviceSegmentedRadixSort::SortKeysDescending(
-            ws.cub_temp, temp, (const unsigned long long*)ws.keys, ws.keys_alt, (int)((size_t)ws.cap * nframes),
-            nframes, (const int*)ws.seg_begin, (const int*)ws.seg_end, 0, 63, st);
-    const size_t smem = ws.grid_in_smem ? (size_t)ws.ncells * kCellCap * sizeof(unsigned short) : 0;
+    static const bool allow_fused = !(getenv("VSTAB_GFTT_FUSED") && atoi(getenv("VSTAB_GFTT_FUSED")) == 0);
+    const size_t grid_bytes = (size_t)ws.ncells * kCellCap * sizeof(unsigned short);
+    const size_t fused_smem = sizeof(TkScratch) + grid_bytes;
+    const bool fused = allow_fused && fused_smem <= (size_t)220 * 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
+        cudaFuncSetAttribute(topk_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set = true;
     }
-    greedy_kernel<<<nframes, kGreedyThreads, smem, st>>>(ws.keys_alt, ws.seg_begin, ws.seg_end, ws.maxbits, quality, w, min_distance,
-                                             ws.cell, ws.grid_w, ws.grid_h, ws.grid, ws.grid_in_smem, max_corners,
-                                             pts, counts);
+    const int key_bits = 31 + ws.idx_bits;
+    // the fused kernel leaves the per-frame counters reset behind it
+    if (!(fused && ws.counters_ready && nframes == 1)) {
+        count_launch(1);
+        gftt_reset_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.maxbits, ws.seg_begin, ws.seg_end, ws.cap, nframes);
+    }
+    ws.counters_ready = fused ? 1 : 0;
+    {
+        const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + kSegH - 1) / kSegH;
+        dim3 grid((nstrips * nsegs + kEigWarps - 1) / kEigWarps, nframes);
+        count_launch(1);
+        eig_kernel<<<grid, 32 * kEigWarps, 0, st>>>(gray, gray_frame_stride, w, h, nstrips, nsegs, ws.idx_bits, eig_out, ws.maxbits,
+                                                    ws.keys, ws.seg_end, ws.cap, quality);
+    }
+    if (fused) {
+        count_launch(1);
+        topk_greedy_kernel<<<nframes, kTkThreads, fused_smem, st>>>(ws.keys, ws.seg_begin, ws.seg_end, ws.maxbits, quality,
+                                                                    ws.idx_bits, ws.cap, w, min_distance, ws.cell, ws.grid_w,
+                                                                    ws.grid_h, max_corners, pts, counts);
+        return;
+    }
+    // unfused schedule: clamp, cub radix sort (its passes are not counted as launches of ours), greedy
+    count_launch(2);
+    clamp_segments_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(ws.seg_end, ws.cap, nframes);
+    size_t temp = ws.cub_temp_bytes;
+    cub::DeviceSegmentedRadixSort::SortKeysDescending(
+        ws.cub_temp, temp, (const unsigned long long*)ws.keys, ws.keys_alt, (int)((size_t)ws.cap * nframes),
+        nframes, (const int*)ws.seg_begin, (const int*)ws.seg_end, 0, key_bits, st);
+    const size_t smem = ws.grid_in_smem ? grid_bytes : 0;
+    greedy_kernel<<<nframes, kGreedyThreads, smem, st>>>(ws.keys_alt, ws.seg_begin, ws.seg_end, ws.maxbits, quality, ws.idx_bits, w,
+                                                         min_distance, ws.cell, ws.grid_w, ws.grid_h, ws.grid, ws.grid_in_smem,
+                                                         max_corners, pts, counts);
 }
 
 }  // namespace vstabk

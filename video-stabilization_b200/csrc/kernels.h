@@ -48,6 +48,8 @@ struct GfttWorkspace {
     int ncells, grid_w, grid_h, cell;
     int grid_in_smem;
     int max_frames;
+    int idx_bits;                  // candidate key = min-eigenvalue bits << idx_bits | pixel index
+    int counters_ready;            // host flag: maxbits / seg_end were left reset by the fused kernel
 };
 size_t gftt_workspace_bytes(int w, int h, int min_distance, int max_frames, GfttWorkspace* layout);
 void gftt_bind_workspace(void* base, GfttWorkspace* ws);     // base: cudaMalloc'ed block
