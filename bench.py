@@ -503,7 +503,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=128, help="frames per kernel launch (offline batch)")
+    ap.add_argument("--batch", type=int, default=256, help="frames per kernel launch (offline batch)")
     ap.add_argument("--e2e-frames-per-step", type=int, default=512, help="frames of the host clip (one step = one clip)")
     ap.add_argument("--e2e-batch", type=int, default=16, help="chunk size of the host-clip pipeline")
     ap.add_argument("--e2e-stream-frames", type=int, default=128, help="streaming calls per step")

@@ -188,8 +188,8 @@ struct vstab {
     // device-side marks of one call (timing events): 0 upload start, 1 upload end, 2 estimation start, 3 pyramid done,
     // 4 LK+fit done, 5 corners start, 6 corners done, 7 output start, 8 smoothing done, 9 warp done, 10 download done
     // (two sets, alternating per call: the marks of call n-1 are read at the end of call n, without draining the pipeline)
-    cudaEvent_t tev[2][11] = {};
-    double tev_ms[11] = {};              // [10]: upload start of the next call (the period)
+    cudaEvent_t tev[2][13] = {};
+    double tev_ms[13] = {};              // [10]: upload start of the next call (the period); [11] LK start, [12] LK done
     long tev_calls = 0;
     void mark(int i, cudaStream_t q) {
         if (!tev[0][0]) return;
@@ -259,9 +259,11 @@ static vstab_status stream_estimate(vstab* s) {
     s->mark(3, q);
     if (n > 0) {
         CK(cudaStreamWaitEvent(q, s->ev_gftt, 0));                    // corners of frame n-1
+        s->mark(11, q);
         // :1187 trackFeatures
         launch_lk(s->pyr(prev), s->pyr(cur), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
                   s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), q);
+        s->mark(12, q);
         // :1203 estimateMotion, :1209 updateTransformations
         launch_fit(s->corners(prev), s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), ccount + prev, 1, 3.0,
                    g.ww / 2.0, g.wh / 2.0, s->T.as<double>() + (size_t)(n % s->t_mod) * 9, s->Mtap.as<double>(),
@@ -462,6 +464,8 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
                 }
                 float ms = 0.f;
                 if (cudaEventElapsedTime(&ms, s->tev[pv][0], s->tev[cu][0]) == cudaSuccess) s->tev_ms[10] += ms;
+                if (cudaEventElapsedTime(&ms, s->tev[pv][0], s->tev[pv][11]) == cudaSuccess) s->tev_ms[11] += ms;
+                if (cudaEventElapsedTime(&ms, s->tev[pv][0], s->tev[pv][12]) == cudaSuccess) s->tev_ms[12] += ms;
                 s->tev_calls += 1;
             }
         }
@@ -522,12 +526,16 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
     vstab* s = new (std::nothrow) vstab();
     if (!s) return VSTAB_ERR_CUDA;
     s->device = device; s->P = past_frames; s->F = future_frames; s->working_height = working_height;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->out_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the tracker / fit chain and the output chain are on the critical path of a call; corner detection has a whole
+    // call of slack, so it runs at the lowest priority and yields SMs to them
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->out_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fit, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->gftt_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->gftt_stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_gftt, cudaEventDisableTiming) != cudaSuccess) {
@@ -549,7 +557,8 @@ void vstab_destroy(vstab_t* s) {
                                      "corners done", "output start", "smoothing done", "warp done", "download done"};
         fprintf(stderr, "[vstab trace] device marks of a call relative to its upload start (us, %ld calls):", s->tev_calls);
         for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %.1f;", nm[i], 1e3 * s->tev_ms[i] / s->tev_calls);
-        fprintf(stderr, " next upload start %.1f\n", 1e3 * s->tev_ms[10] / s->tev_calls);
+        fprintf(stderr, " LK start %.1f; LK done %.1f; next upload start %.1f\n", 1e3 * s->tev_ms[11] / s->tev_calls,
+                1e3 * s->tev_ms[12] / s->tev_calls, 1e3 * s->tev_ms[10] / s->tev_calls);
     }
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
     if (s->out_stream) { cudaStreamSynchronize(s->out_stream); cudaStreamDestroy(s->out_stream); }

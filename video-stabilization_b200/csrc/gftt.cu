@@ -36,7 +36,7 @@ constexpr int kStripW = 28, kSegH = 60, kEigWarps = 4;
 struct D3 { double xx, xy, yy; };
 
 __global__ void __launch_bounds__(32 * kEigWarps, 8)
-eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs, int idx_bits,
+eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs, int seg_h, int idx_bits,
            float* __restrict__ eig_out, unsigned int* __restrict__ maxbits,
            unsigned long long* __restrict__ keys, int* __restrict__ seg_end, int cap, double quality) {
     const int lane = threadIdx.x & 31;
@@ -45,7 +45,7 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
     if (item >= nstrips * nsegs) return;
     const int seg = item / nstrips, strip = item - seg * nstrips;
     const int sx0 = strip * kStripW;
-    const int ya = seg * kSegH, yb = min(ya + kSegH, h);
+    const int ya = seg * seg_h, yb = min(ya + seg_h, h);
     const uint8_t* src = gray + (size_t)frame * gray_stride;
 
     // scale = 1 / (2^(ksize-1) * blockSize * 255) ; k1 = float(scale), k0 = float(2*scale)
@@ -58,13 +58,22 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
     // un-contracted tail over the rest ([probe] cv2 4.13.0 on AVX-512 hosts; all production widths
     // 640/1280/1920/3840 are multiples of 32 and never reach the tail).
     const bool fma_col = xr < (w & ~31);
-    // S = p[x+1] - p[x-1] (Dx row term), R = k1 p[x-1] + k0 p[x] + k1 p[x+1] (Dy row term) of gray row y
-    auto load_row = [&](int y, float& S, float& R) {
+    // S = p[x+1] - p[x-1] (Dx row term), R = k1 p[x-1] + k0 p[x] + k1 p[x+1] (Dy row term) of a gray row; the three
+    // bytes of a row are fetched one row ahead of their use (load_raw / row_terms), so the loop never waits for them
+    auto load_raw = [&](int y, unsigned& a, unsigned& b, unsigned& c) {
         const int ro = y * w;                                    // (a working image has far fewer than 2^31 pixels)
-        const float gm = (float)__ldg(src + (ro + cm)), g0 = (float)__ldg(src + (ro + xr)), gp = (float)__ldg(src + (ro + cp));
+        a = __ldg(src + (ro + cm)); b = __ldg(src + (ro + xr)); c = __ldg(src + (ro + cp));
+    };
+    auto row_terms = [&](unsigned a, unsigned b, unsigned c, float& S, float& R) {
+        const float gm = (float)a, g0 = (float)b, gp = (float)c;
         S = __fsub_rn(gp, gm);
         R = fma_col ? __fmaf_rn(gp, k1, __fmaf_rn(g0, k0, __fmul_rn(gm, k1)))
                     : __fadd_rn(__fadd_rn(__fmul_rn(gm, k1), __fmul_rn(g0, k0)), __fmul_rn(gp, k1));
+    };
+    auto load_row = [&](int y, float& S, float& R) {
+        unsigned a, b, c;
+        load_raw(y, a, b, c);
+        row_terms(a, b, c, S, R);
     };
 
     const int xe = sx0 - 1 + lane;                              // eigenvalue column of this lane (lanes 0..29)
@@ -82,6 +91,8 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
     float E[3] = {0.f, 0.f, 0.f}, HM[3] = {0.f, 0.f, 0.f}, H3[3] = {0.f, 0.f, 0.f};   // eig row: value, max(left,right), 3-max
     load_row(reflect101(p_lo - 1, h), S[0], R[0]);
     load_row(p_lo, S[1], R[1]);
+    unsigned ra, rb, rc;                                        // raw bytes of gray row yp + 1
+    load_raw(reflect101(p_lo + 1, h), ra, rb, rc);
     float vmax = 0.f;
     // candidates must exceed this (0: the eigenvalue must be positive)
     float cut = (float)((double)__uint_as_float(*(volatile unsigned int*)(maxbits + frame)) * quality) * 0.999f;
@@ -96,7 +107,8 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
             if (yp > p_hi + 1 || (yp > p_hi && p_hi != h - 1)) { done = true; break; }
             const int jA = (j + 1) % 3, jB = (j + 2) % 3;           // slots of rows yp-2, yp-1
             if (yp <= p_hi) {
-                load_row(reflect101(yp + 1, h), S[jB], R[jB]);       // gray row yp+1
+                row_terms(ra, rb, rc, S[jB], R[jB]);                 // gray row yp+1
+                load_raw(reflect101(yp + 2, h), ra, rb, rc);         // (h + 1 at most: still a valid reflection)
                 // Dx = fma(S[y-1] + S[y+1], k1, S[y]*k0),  Dy = R[y+1] - R[y-1]
                 const float dx = __fmaf_rn(__fadd_rn(S[j], S[jB]), k1, __fmul_rn(S[jA], k0));
                 const float dy = __fsub_rn(R[jB], R[j]);
@@ -501,10 +513,13 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     }
     ws.counters_ready = fused ? 1 : 0;
     {
-        const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + kSegH - 1) / kSegH;
+        // rows per warp: long segments amortise the 4 halo rows; a few frames alone (streaming) want more, shorter
+        // warps instead (latency)
+        const int seg_h = nframes >= 8 ? kSegH : kSegH / 4;
+        const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + seg_h - 1) / seg_h;
         dim3 grid((nstrips * nsegs + kEigWarps - 1) / kEigWarps, nframes);
         count_launch(1);
-        eig_kernel<<<grid, 32 * kEigWarps, 0, st>>>(gray, gray_frame_stride, w, h, nstrips, nsegs, ws.idx_bits, eig_out, ws.maxbits,
+        eig_kernel<<<grid, 32 * kEigWarps, 0, st>>>(gray, gray_frame_stride, w, h, nstrips, nsegs, seg_h, ws.idx_bits, eig_out, ws.maxbits,
                                                     ws.keys, ws.seg_end, ws.cap, quality);
     }
     if (fused) {
