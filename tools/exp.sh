@@ -1,11 +1,12 @@
 cd /root/repo
-VSTAB_TRACE=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mode-probes --frames-per-gpu 128 > gpurun_out/exp.log 2> gpurun_out/exp.err
-grep "vstab trace" gpurun_out/exp.err
-for i in 1 2; do
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-mode-probes --frames-per-gpu 128 > gpurun_out/exp.log 2>&1
-python - <<PY
-import json,sys
-d=json.loads(open("gpurun_out/exp.log").read().strip().splitlines()[-1])
-print("e2e", d["e2e"]["value"], "streaming", d["e2e"]["streaming"]["value"])
+timeout 1200 python -m pytest tests/test_gpu_orb.py -q -m gpu -x 2>&1 | tail -4
+timeout 600 python - <<PY
+import json, subprocess, sys
+sys.argv=["bench.py"]
 PY
-done
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --frames-per-gpu 128 > gpurun_out/exp.log 2>&1
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/exp.log").read().strip().splitlines()[-1])
+print(json.dumps(d["other_modes_streaming"], indent=1))
+PY

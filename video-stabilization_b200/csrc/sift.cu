@@ -88,6 +88,81 @@ sift_blur_kernel(const float* __restrict__ src, float* __restrict__ dst, int w, 
     }
 }
 
+// Same blur for a radius known at compile time (the six radii SIFT's sigmas produce): 64 x 64 output tile, reflect
+// indices from small tables, the horizontal pass register-blocked 4 outputs wide on 16-byte shared-memory loads, the
+// vertical pass as a register window sliding down 16 rows of a column; taps are accumulated in the same order as the
+// generic kernel (bit-identical results).
+constexpr int TBX = 64, TBY = 64;
+template <int R>
+__global__ void __launch_bounds__(256)
+sift_blur_t_kernel(const float* __restrict__ src, float* __restrict__ dst, int w, int h, int ki) {
+    constexpr int TW = TBX + 2 * R, TH = TBY + 2 * R, TWS = (TW + 3) & ~3, NT = 2 * R + 1;
+    extern __shared__ __align__(16) float sm[];
+    float* tile = sm;                       // TH x TWS
+    float* rowf = sm + TH * TWS;            // TH x TBX
+    __shared__ int sx[TW], sy[TH];
+    const int x0 = blockIdx.x * TBX, y0 = blockIdx.y * TBY;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < TW; i += 256) sx[i] = reflect101_multi(x0 + i - R, w);
+    for (int i = tid; i < TH; i += 256) sy[i] = reflect101_multi(y0 + i - R, h) * w;      // (< 2^31: at most 7680 x 4320)
+    __syncthreads();
+    for (int i = tid; i < TH * TW; i += 256) {
+        const int r = i / TW, c = i - r * TW;
+        tile[r * TWS + c] = __ldg(src + sy[r] + sx[c]);
+    }
+    __syncthreads();
+    float k[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) k[j] = c_gk[ki][j];
+    // horizontal: TH rows x 16 groups of 4 outputs
+    for (int it = tid; it < TH * (TBX / 4); it += 256) {
+        const int r = it / (TBX / 4), c4 = (it - r * (TBX / 4)) * 4;
+        constexpr int NV = (NT + 3 + 3) / 4;                    // float4 loads covering taps c4 .. c4 + NT + 2
+        float v[NV * 4];
+        const float4* t4 = reinterpret_cast<const float4*>(tile + r * TWS + c4);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 f = t4[q];
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) s += v[u + j] * k[j];
+            o[u] = s;
+        }
+        *reinterpret_cast<float4*>(rowf + r * TBX + c4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    // vertical: column c, 16 consecutive output rows per thread
+    {
+        const int c = tid & (TBX - 1), r0 = (tid / TBX) * 16;
+        float v[16 + 2 * R];
+#pragma unroll
+        for (int i = 0; i < 16 + 2 * R; ++i) v[i] = rowf[(r0 + i) * TBX + c];
+        const int x = x0 + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) s += v[i + j] * k[j];
+            const int y = y0 + r0 + i;
+            if (x < w && y < h) dst[(size_t)y * w + x] = s;
+        }
+    }
+}
+
+template <int R>
+static void launch_blur_t(const float* src, float* dst, int w, int h, int ki, cudaStream_t st) {
+    constexpr int TW = TBX + 2 * R, TH = TBY + 2 * R, TWS = (TW + 3) & ~3;
+    constexpr int smem = (int)(sizeof(float) * (TH * TWS + TH * TBX));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sift_blur_t_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    sift_blur_t_kernel<R><<<dim3((w + TBX - 1) / TBX, (h + TBY - 1) / TBY), 256, smem, st>>>(src, dst, w, h, ki);
+}
+
 __global__ void __launch_bounds__(256)
 sift_decimate_kernel(const float* __restrict__ src, int sw, float* __restrict__ dst, int dw, int dh) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -586,6 +661,15 @@ void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t
     const int* hr = P->radii;
     auto blur = [&](const float* src, float* dst, int w, int h, int ki) {
         const int R = hr[ki];
+        switch (R) {                       // the radii of SIFT's sigmas; anything else takes the generic kernel
+            case 3: launch_blur_t<3>(src, dst, w, h, ki, st); return;
+            case 4: launch_blur_t<4>(src, dst, w, h, ki, st); return;
+            case 5: launch_blur_t<5>(src, dst, w, h, ki, st); return;
+            case 6: launch_blur_t<6>(src, dst, w, h, ki, st); return;
+            case 8: launch_blur_t<8>(src, dst, w, h, ki, st); return;
+            case 10: launch_blur_t<10>(src, dst, w, h, ki, st); return;
+            default: break;
+        }
         const int smem = (int)(sizeof(float) * ((GBY + 2 * R) * (GBX + 2 * R) + (GBY + 2 * R) * GBX));
         sift_blur_kernel<<<dim3((w + GBX - 1) / GBX, (h + GBY - 1) / GBY), 256, smem, st>>>(src, dst, w, h, ki);
     };

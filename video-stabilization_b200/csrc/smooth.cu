@@ -193,16 +193,22 @@ __global__ void acc_update_kernel(const double* T, long t_mod, long p, int reset
 // incoming prefix (phase 3).  Products are left-multiplications in frame order.
 constexpr int kScanChunk = 256;
 
-__global__ void acc_chunk_reduce_kernel(const double* __restrict__ T, long n_total, long anchor,
-                                        double* __restrict__ chunk_tot) {
-    const long chunk = blockIdx.x * (long)blockDim.x + threadIdx.x;
+// One CTA per chunk: the chunk's transforms are staged in shared memory by all threads (the serial chain would
+// otherwise pay a global-memory round trip per product), then thread 0 walks the chain.
+__global__ void __launch_bounds__(128)
+acc_chunk_reduce_kernel(const double* __restrict__ T, long n_total, long anchor, double* __restrict__ chunk_tot) {
+    __shared__ double sT[kScanChunk * 9];
+    const long chunk = blockIdx.x;
     const long k0 = anchor + 1 + chunk * kScanChunk;
     if (k0 >= n_total) return;
     const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
+    for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) sT[i] = T[(size_t)k0 * 9 + i];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double acc[9], tmp[9];
     eye3(acc);
     for (long k = k0; k < k1; ++k) {
-        matmul3(T + (size_t)k * 9, acc, tmp);
+        matmul3(sT + (size_t)(k - k0) * 9, acc, tmp);
         for (int i = 0; i < 9; ++i) acc[i] = tmp[i];
     }
     for (int i = 0; i < 9; ++i) chunk_tot[(size_t)chunk * 9 + i] = acc[i];
@@ -221,19 +227,28 @@ __global__ void acc_chunk_scan_kernel(double* chunk_tot, long nchunks) {
     }
 }
 
-__global__ void acc_chunk_apply_kernel(const double* __restrict__ T, long n_total, long anchor,
-                                       const double* __restrict__ chunk_pre, double* __restrict__ acc_out) {
-    const long chunk = blockIdx.x * (long)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+acc_chunk_apply_kernel(const double* __restrict__ T, long n_total, long anchor,
+                       const double* __restrict__ chunk_pre, double* __restrict__ acc_out) {
+    __shared__ double sT[kScanChunk * 9];
+    const long chunk = blockIdx.x;
     const long k0 = anchor + 1 + chunk * kScanChunk;
-    if (chunk == 0 && anchor < n_total) eye3(acc_out + (size_t)anchor * 9);
+    if (chunk == 0 && threadIdx.x == 0 && anchor < n_total) eye3(acc_out + (size_t)anchor * 9);
     if (k0 >= n_total) return;
     const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
-    double acc[9], tmp[9];
-    for (int i = 0; i < 9; ++i) acc[i] = chunk_pre[(size_t)chunk * 9 + i];
-    for (long k = k0; k < k1; ++k) {
-        matmul3(T + (size_t)k * 9, acc, tmp);
-        for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; acc_out[(size_t)k * 9 + i] = tmp[i]; }
+    for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) sT[i] = T[(size_t)k0 * 9 + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc[9], tmp[9];
+        for (int i = 0; i < 9; ++i) acc[i] = chunk_pre[(size_t)chunk * 9 + i];
+        for (long k = k0; k < k1; ++k) {
+            matmul3(sT + (size_t)(k - k0) * 9, acc, tmp);
+            // the running product replaces the transform in shared memory; all threads write the chunk out below
+            for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sT[(size_t)(k - k0) * 9 + i] = tmp[i]; }
+        }
     }
+    __syncthreads();
+    for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) acc_out[(size_t)k0 * 9 + i] = sT[i];
 }
 
 }  // namespace
@@ -267,8 +282,8 @@ void launch_acc_scan(const double* T, long n_total, long anchor, double* acc, cu
     const long n = n_total - anchor - 1;
     const long nchunks = n > 0 ? (n + kScanChunk - 1) / kScanChunk : 0;
     double* chunk = acc + (size_t)n_total * 9;
-    const int threads = 64;
-    const int blocks = (int)((nchunks > 0 ? nchunks : 1) + threads - 1) / threads;
+    const int threads = 128;
+    const int blocks = (int)(nchunks > 0 ? nchunks : 1);
     count_launch(nchunks > 0 ? 3 : 1);
     if (nchunks > 0) {
         acc_chunk_reduce_kernel<<<blocks, threads, 0, st>>>(T, n_total, anchor, chunk);
