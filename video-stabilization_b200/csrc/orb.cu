@@ -478,40 +478,39 @@ orb_describe_kernel(const unsigned long long* __restrict__ keys, const int* __re
 }
 
 // ---------------------------------------------------------------- Hamming 2-NN + ratio test
-constexpr int HQ = 64;          // query rows per CTA (one thread per query row), train tiles of 64 in smem
-__global__ void __launch_bounds__(HQ)
+// One warp per query row: lane l scans train rows l, l+32, ... (in index order, so ties keep the lowest index), then
+// the 32 partial (best, index, second) triples are merged; `second` is the second order statistic of the distances.
+constexpr int HQ = 4;           // query rows (warps) per CTA
+__global__ void __launch_bounds__(32 * HQ)
 hamming_knn2_kernel(const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_p, int nq_max,
                     const uint8_t* __restrict__ tdesc, const int* __restrict__ nt_p, int nt_max, float ratio,
                     int* __restrict__ best_idx, int* __restrict__ best_d, int* __restrict__ second_d,
                     uint8_t* __restrict__ good) {
-    __shared__ uint4 tile[HQ][2];
     const int nq = min(*nq_p, nq_max), nt = min(*nt_p, nt_max);
-    const int q = blockIdx.x * HQ + threadIdx.x;
-    if (blockIdx.x * HQ >= nq) return;
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-    if (q < nq) {
-        const uint4* p = reinterpret_cast<const uint4*>(qdesc + (size_t)q * 32);
-        a0 = p[0]; a1 = p[1];
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * HQ + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const uint4* qp = reinterpret_cast<const uint4*>(qdesc + (size_t)q * 32);
+    const uint4 a0 = __ldg(qp), a1 = __ldg(qp + 1);
+    constexpr int kNone = 1 << 30;
+    int b0 = kNone, b1 = kNone, bi = 0x7fffffff;
+    for (int j = lane; j < nt; j += 32) {
+        const uint4* tp = reinterpret_cast<const uint4*>(tdesc + (size_t)j * 32);
+        const uint4 c0 = __ldg(tp), c1 = __ldg(tp + 1);
+        const int d = __popc(a0.x ^ c0.x) + __popc(a0.y ^ c0.y) + __popc(a0.z ^ c0.z) + __popc(a0.w ^ c0.w) +
+                      __popc(a1.x ^ c1.x) + __popc(a1.y ^ c1.y) + __popc(a1.z ^ c1.z) + __popc(a1.w ^ c1.w);
+        if (d < b0) { b1 = b0; b0 = d; bi = j; }
+        else if (d < b1) { b1 = d; }
     }
-    int b0 = 1 << 30, b1 = 1 << 30, bi = -1;
-    for (int t0 = 0; t0 < nt; t0 += HQ) {
-        __syncthreads();
-        if (t0 + threadIdx.x < nt) {
-            const uint4* p = reinterpret_cast<const uint4*>(tdesc + (size_t)(t0 + threadIdx.x) * 32);
-            tile[threadIdx.x][0] = p[0]; tile[threadIdx.x][1] = p[1];
-        }
-        __syncthreads();
-        const int m = min(HQ, nt - t0);
-        for (int j = 0; j < m; ++j) {
-            const uint4 c0 = tile[j][0], c1 = tile[j][1];
-            const int d = __popc(a0.x ^ c0.x) + __popc(a0.y ^ c0.y) + __popc(a0.z ^ c0.z) + __popc(a0.w ^ c0.w) +
-                          __popc(a1.x ^ c1.x) + __popc(a1.y ^ c1.y) + __popc(a1.z ^ c1.z) + __popc(a1.w ^ c1.w);
-            if (d < b0) { b1 = b0; b0 = d; bi = t0 + j; }
-            else if (d < b1) { b1 = d; }
-        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob0 = __shfl_xor_sync(0xffffffffu, b0, o), ob1 = __shfl_xor_sync(0xffffffffu, b1, o),
+                  obi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob0 < b0 || (ob0 == b0 && obi < bi)) { b1 = min(ob1, b0); b0 = ob0; bi = obi; }   // the other side wins
+        else { b1 = min(b1, ob0); }
     }
-    if (q < nq) {
-        best_idx[q] = bi; best_d[q] = b0; second_d[q] = b1;
+    if (lane == 0) {
+        best_idx[q] = b0 == kNone ? -1 : bi; best_d[q] = b0; second_d[q] = b1;
         // knnMatch returns 2 neighbours only when the train set has >= 2 rows; Lowe ratio in float (:661-662)
         good[q] = (nt >= 2 && (float)b0 < __fmul_rn(ratio, (float)b1)) ? 1 : 0;
     }
@@ -700,7 +699,7 @@ void launch_hamming_match(const uint8_t* ref_desc, const int* nref, const OrbKey
                           int* second_d, uint8_t* good, float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch,
                           cudaStream_t st) {
     count_launch(2);
-    hamming_knn2_kernel<<<(max_kp + HQ - 1) / HQ, HQ, 0, st>>>(ref_desc, nref, max_kp, cur_desc, ncur, max_kp, ratio, best_idx,
+    hamming_knn2_kernel<<<(max_kp + HQ - 1) / HQ, 32 * HQ, 0, st>>>(ref_desc, nref, max_kp, cur_desc, ncur, max_kp, ratio, best_idx,
                                                                  best_d, second_d, good);
     match_gather_kernel<<<1, 256, 0, st>>>(ref_kps, nref, max_kp, cur_kps, best_idx, good, ref_pts, cur_pts, status, nmatch);
 }

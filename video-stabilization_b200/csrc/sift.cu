@@ -219,6 +219,87 @@ sift_extrema_kernel(const float* __restrict__ pyr, SiftOctaves O, int o, int thr
     }
 }
 
+// Same test on shared-memory tiles: one CTA stages the 5 DoG layers of a 64 x 16 tile (+1 halo) -- every Gaussian
+// sample is read once per tile instead of up to 27 times per layer -- and every thread tests 4 rows x 3 layers.
+constexpr int EXW = 64, EXH = 16;
+__global__ void __launch_bounds__(256)
+sift_extrema_tile_kernel(const float* __restrict__ pyr, SiftOctaves O, int o, int threshold,
+                         unsigned long long* __restrict__ cand, int* __restrict__ ncand, int cap) {
+    constexpr int TW = EXW + 2, TH = EXH + 2, NE = (TW * TH + 255) / 256;
+    __shared__ float D[kGauss - 1][TH][TW];
+    const int w = O.w[o], h = O.h[o];
+    const size_t plane = (size_t)w * h;
+    const float* g = pyr + O.off[o];
+    const int x0 = kBorder + blockIdx.x * EXW, y0 = kBorder + blockIdx.y * EXH;
+    const int tid = threadIdx.x;
+    {
+        float prev[NE];
+#pragma unroll
+        for (int l = 0; l < kGauss; ++l) {
+            float cur[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int i = tid + e * 256;
+                const int r = i / TW, c = i - r * TW;
+                const int yy = min(y0 - 1 + r, h - 1), xx = min(x0 - 1 + c, w - 1);
+                cur[e] = i < TW * TH ? __ldg(g + (size_t)l * plane + (size_t)yy * w + xx) : 0.f;
+            }
+            if (l > 0) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int i = tid + e * 256;
+                    const int r = i / TW, c = i - r * TW;
+                    if (i < TW * TH) D[l - 1][r][c] = cur[e] - prev[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) prev[e] = cur[e];
+        }
+    }
+    __syncthreads();
+    const int c = 1 + (tid & (EXW - 1));
+    const int x = x0 + c - 1;
+    const int lane = tid & 31;
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = 1 + (tid / EXW) * 4 + rr;
+        const int y = y0 + r - 1;
+#pragma unroll 1
+        for (int layer = 1; layer <= kLayers; ++layer) {
+            bool is_ext = false;
+            if (x < w - kBorder && y < h - kBorder) {
+                const float val = D[layer][r][c];
+                if (fabsf(val) > (float)threshold) {
+                    bool mx = val > 0.f, mn = val < 0.f;
+#pragma unroll
+                    for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const float v = D[layer + dl][r + dy][c + dx];
+                                mx = mx && val >= v;
+                                mn = mn && val <= v;
+                            }
+                    is_ext = mx || mn;
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, is_ext);
+            if (ball) {
+                int pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(ncand, __popc(ball));
+                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                if (is_ext) {
+                    const int pos = pos0 + __popc(ball & ((1u << lane) - 1u));
+                    if (pos < cap)
+                        cand[pos] = ((unsigned long long)o << 56) | ((unsigned long long)layer << 48) | ((unsigned long long)y << 24) |
+                                    (unsigned long long)x;
+                }
+            }
+        }
+    }
+}
+
 // DoG value: layer l (0..4) of octave image set `g0` (Gaussian 0), at (r, c)
 VSTAB_D float dogv(const float* __restrict__ g0, size_t plane, int w, int l, int r, int c) {
     const size_t p = (size_t)r * w + c;
@@ -693,7 +774,7 @@ void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t
         }
         for (int i = 1; i < kGauss; ++i) { blur(g + (size_t)(i - 1) * plane, g + (size_t)i * plane, w, h, i); ++launches; }
         if (w > 2 * kBorder && h > 2 * kBorder) {
-            sift_extrema_kernel<<<dim3((w - 2 * kBorder + 255) / 256, h - 2 * kBorder, kLayers), 256, 0, st>>>(
+            sift_extrema_tile_kernel<<<dim3((w - 2 * kBorder + EXW - 1) / EXW, (h - 2 * kBorder + EXH - 1) / EXH), 256, 0, st>>>(
                 P->pyr, O, o, threshold, P->cand, P->counters + 0, P->cand_cap);
             ++launches;
         }
