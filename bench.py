@@ -335,6 +335,16 @@ def run_ours(args):
                 "frac": d["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": d["avg_launch_ms"],
                 "share_of_step": d["share"]}
+    # context for the reader (not part of the contract): the whole path against the same roofline, the two stages
+    # that are HBM-bound by construction, and why the dominant kernel sits far below an HBM roofline
+    path_bytes = sum(bpf[k] for k in ("ingest", "pyramid", "gftt", "lk", "fit", "smooth", "warp"))
+    roofline["path"] = {"algorithmic_bytes_per_frame": path_bytes, "achieved": path_bytes * value / 1e9 / max(world, 1),
+                        "frac": path_bytes * value / 1e9 / max(world, 1) / peak, "unit": "GB/s per GPU"}
+    roofline["hbm_bound_stages"] = {k: {"achieved": stage_rows[k]["achieved_gbs"], "frac": stage_rows[k]["frac"]}
+                                    for k in ("ingest", "warp") if k in stage_rows}
+    roofline["note"] = ("the dominant kernel (pyramidal LK, one warp per feature) moves 0.6 MB of algorithmic bytes per "
+                        "frame and is bound by instruction issue on the integer ALU pipe (ncu: profiles/), not by HBM; "
+                        "ingest and warp are the stages an HBM roofline describes")
 
     # ---- e2e: host-buffer C ABI (pinned host frames in, stabilized host frames out) ------------------
     e2e = None if args.no_e2e else run_e2e(args, torch, vs, lib, frames, local, world, dev, dist)

@@ -106,9 +106,22 @@ sift_blur_t_kernel(const float* __restrict__ src, float* __restrict__ dst, int w
     for (int i = tid; i < TW; i += 256) sx[i] = reflect101_multi(x0 + i - R, w);
     for (int i = tid; i < TH; i += 256) sy[i] = reflect101_multi(y0 + i - R, h) * w;      // (< 2^31: at most 7680 x 4320)
     __syncthreads();
-    for (int i = tid; i < TH * TW; i += 256) {
-        const int r = i / TW, c = i - r * TW;
-        tile[r * TWS + c] = __ldg(src + sy[r] + sx[c]);
+    {
+        // all loads of a thread in flight together (one memory round trip per tile instead of one per element)
+        constexpr int NE = (TH * TW + 255) / 256;
+        float v[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i = tid + e * 256;
+            const int r = i / TW, c = i - r * TW;
+            v[e] = i < TH * TW ? __ldg(src + sy[r] + sx[c]) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i = tid + e * 256;
+            const int r = i / TW, c = i - r * TW;
+            if (i < TH * TW) tile[r * TWS + c] = v[e];
+        }
     }
     __syncthreads();
     float k[NT];
