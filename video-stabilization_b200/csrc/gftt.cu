@@ -374,9 +374,13 @@ topk_greedy_kernel(const unsigned long long* __restrict__ keys_all, const int* _
                 const unsigned dmask = (1u << (top - shift)) - 1u;
                 hist[tid] = 0u;
                 __syncthreads();
-                for (int i = tid; i < n; i += kTkThreads) {
-                    const unsigned long long key = keys[i];
-                    if (key < upper && (key & pmask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & dmask], 1u);
+                for (int i0 = tid; i0 < n; i0 += 4 * kTkThreads) {         // 4 loads in flight per thread
+                    unsigned long long kk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) kk[u] = i0 + u * kTkThreads < n ? keys[i0 + u * kTkThreads] : ~0ull;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kk[u] < upper && (kk[u] & pmask) == prefix) atomicAdd(&hist[(unsigned)(kk[u] >> shift) & dmask], 1u);
                 }
                 __syncthreads();
                 if (tid < 32) {
@@ -408,9 +412,13 @@ topk_greedy_kernel(const unsigned long long* __restrict__ keys_all, const int* _
         // ---- gather the chunk [T, upper) into shared memory, sort it (descending), hand it to warp 0
         if (tid == 0) s_cnt = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += kTkThreads) {
-            const unsigned long long key = keys[i];
-            if (key >= T && key < upper) S.keys[atomicAdd(&s_cnt, 1)] = key;
+        for (int i0 = tid; i0 < n; i0 += 4 * kTkThreads) {
+            unsigned long long kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = i0 + u * kTkThreads < n ? keys[i0 + u * kTkThreads] : ~0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (kk[u] >= T && kk[u] < upper) S.keys[atomicAdd(&s_cnt, 1)] = kk[u];
         }
         __syncthreads();
         const int m = s_cnt;

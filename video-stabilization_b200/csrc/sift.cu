@@ -364,9 +364,10 @@ sift_refine_kernel(const float* __restrict__ pyr, SiftOctaves O, const unsigned 
                    const int* __restrict__ ncand, int cap, SiftKp* __restrict__ kps, int* __restrict__ nkp, int kcap) {
     __shared__ float hist_s[4][40];
     const int n = min(*ncand, cap);
-    const int ci = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    if (ci >= n) return;
+    // a fixed grid walks the candidate list (the capacity is ~2 M entries at 4K, the list a few tens of thousands)
+    for (int ci = blockIdx.x * 4 + wl; ci < n; ci += gridDim.x * 4) {
+    __syncwarp();
     const unsigned long long key = cand[ci];
     const int o = (int)(key >> 56);
     int layer = (int)((key >> 48) & 0xff), r = (int)((key >> 24) & 0xffffff), c = (int)(key & 0xffffff);
@@ -423,7 +424,7 @@ sift_refine_kernel(const float* __restrict__ pyr, SiftOctaves O, const unsigned 
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
-    if (!ok) return;
+    if (!ok) continue;
     layer = __shfl_sync(0xffffffffu, layer, 0); r = __shfl_sync(0xffffffffu, r, 0); c = __shfl_sync(0xffffffffu, c, 0);
     xi = __shfl_sync(0xffffffffu, xi, 0); xr = __shfl_sync(0xffffffffu, xr, 0); xc = __shfl_sync(0xffffffffu, xc, 0);
     contr = __shfl_sync(0xffffffffu, contr, 0);
@@ -486,6 +487,7 @@ sift_refine_kernel(const float* __restrict__ pyr, SiftOctaves O, const unsigned 
             const int pos = atomicAdd(nkp, 1);
             if (pos < kcap) kps[pos] = k2;
         }
+    }
     }
 }
 
@@ -793,7 +795,7 @@ void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t
         }
     }
     SiftKp* kps = (SiftKp*)P->kps;
-    sift_refine_kernel<<<(P->cand_cap + 3) / 4, 128, 0, st>>>(P->pyr, O, P->cand, P->counters + 0, P->cand_cap, kps, P->counters + 1,
+    sift_refine_kernel<<<std::min((P->cand_cap + 3) / 4, 148 * 16), 128, 0, st>>>(P->pyr, O, P->cand, P->counters + 0, P->cand_cap, kps, P->counters + 1,
                                                              P->kp_cap);
     sift_keys_kernel<<<(P->kp_cap + 255) / 256, 256, 0, st>>>(kps, P->counters + 1, P->kp_cap, P->keys, P->idx);
     size_t temp = P->cub_bytes;
