@@ -17,7 +17,7 @@
 //   * tiles touching the image border, non-affine H, footprints larger than a stage: per-pixel path with
 //     border substitution (generic_pixel).
 // Two schedules of the same tile code:
-//   variant 0  one CTA per tile, the box is filled with 16-byte ld.global by the CTA itself;
+//   variant 0  one CTA per tile, the box is filled with 16-byte cp.async copies by the CTA itself;
 //   variant 1  persistent CTAs (one wave), a producer thread has the TMA engine copy the box of the NEXT tile
 //              (cp.async.bulk.tensor.3d over a {pitch/4, rows, frames} u32 tensor map, zero fill outside)
 //              into the free stage while the 8 consumer warps blend the current one; mbarrier full/empty pairs.
@@ -319,12 +319,15 @@ warp_tile_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t frame_
     if (box.SP > 0) {
         // nb <= 512: one 16-byte chunk per lane and row
         const int vpr = box.nb >> 4;
+        // asynchronous 16-byte copies (LDGSTS): every row of the box is in flight at once, no registers involved
         if ((int)threadIdx.x < vpr) {
-            const uint4* g = reinterpret_cast<const uint4*>(I.src + (size_t)box.fy0 * pitch + box.b0) + threadIdx.x;
-            const size_t pv = pitch >> 4;
-#pragma unroll 2
-            for (int r = threadIdx.y; r <= box.fyn; r += NTY) stage[r * (kSP / 16) + threadIdx.x] = __ldg(g + r * pv);
+            const uint8_t* g = I.src + (size_t)box.fy0 * pitch + box.b0 + (size_t)threadIdx.x * 16;
+            const unsigned d = (unsigned)__cvta_generic_to_shared(stage) + threadIdx.x * 16;
+            for (int r = threadIdx.y; r <= box.fyn; r += NTY)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + r * kSP), "l"(g + (size_t)r * pitch) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     uint8_t* dst = out + (size_t)oi * out_frame_stride;
