@@ -78,11 +78,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(stage):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+def ncu_traffic(stage, frames_per_launch):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
+    captured at 256 frames per launch; scaled to this run's frames per launch)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(stage)
+            t = json.load(f)
+        v = t.get(stage)
+        return None if v is None else float(v) * frames_per_launch / float(t.get("frames_per_launch", 256))
     except Exception:
         return None
 
@@ -332,7 +335,7 @@ def run_ours(args):
     d = stage_rows[dom]
     bytes_per_launch = d["achieved_gbs"] * 1e9 * d["avg_launch_ms"] * 1e-3
     roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "frac": d["frac"], "traffic": ncu_traffic(dom, min(args.batch, n_local)), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": d["avg_launch_ms"],
                 "share_of_step": d["share"]}
     # context for the reader (not part of the contract): the whole path against the same roofline, the two stages

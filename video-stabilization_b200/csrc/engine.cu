@@ -28,6 +28,16 @@ namespace vstabk {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+bool graphs_enabled() {
+    static const bool on = !(getenv("VSTAB_GRAPHS") && atoi(getenv("VSTAB_GRAPHS")) == 0);
+    return on;
+}
+GraphCache::~GraphCache() {
+    for (auto& e : entries) {
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+        if (e.graph) cudaGraphDestroy(e.graph);
+    }
+}
 }  // namespace vstabk
 
 namespace {

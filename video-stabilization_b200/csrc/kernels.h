@@ -121,6 +121,54 @@ size_t featprep_workspace_bytes(int w, int h);
 void launch_featprep(const uint8_t* frame, size_t pitch, const int* xofs, const int* yofs, int w, int h,
                      void* workspace, uint8_t* out, cudaStream_t st);
 
+
+// ---------------------------------------------------------------- CUDA-graph replay of fixed launch sequences
+// The ORB and SIFT front ends are long sequences of small dependent launches (44 / 118 per frame) whose arguments
+// do not change from call to call in streaming.  The second call with the same arguments captures the sequence on
+// its stream (thread-local capture) and every later one replays the graph: one launch, no per-kernel host cost,
+// back-to-back scheduling on the device.  VSTAB_GRAPHS=0 disables it.
+struct GraphCache {
+    struct Entry { unsigned long long key[5]; cudaGraphExec_t exec; cudaGraph_t graph; int launches; int seen; };
+    std::vector<Entry> entries;
+    ~GraphCache();
+};
+bool graphs_enabled();
+// body(): enqueues the sequence on `st` (must be capturable: no allocation, no synchronisation)
+template <class F>
+void run_graphed(GraphCache& gc, const unsigned long long (&key)[5], cudaStream_t st, F&& body) {
+    if (!graphs_enabled()) { body(); return; }
+    GraphCache::Entry* e = nullptr;
+    for (auto& x : gc.entries) {
+        bool same = true;
+        for (int i = 0; i < 5; ++i) same = same && x.key[i] == key[i];
+        if (same) { e = &x; break; }
+    }
+    if (!e) {
+        if (gc.entries.size() >= 8) { body(); return; }
+        GraphCache::Entry n{};
+        for (int i = 0; i < 5; ++i) n.key[i] = key[i];
+        gc.entries.push_back(n);
+        body();                                     // first call: plain launches (also runs one-time attribute setup)
+        return;
+    }
+    if (e->exec) { cudaGraphLaunch(e->exec, st); count_launch(e->launches); return; }
+    if (e->seen < 0) { body(); return; }            // capture failed once: stay on plain launches
+    const long long l0 = launch_count();
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); e->seen = -1; body(); return; }
+    body();
+    cudaGraph_t g = nullptr;
+    if (cudaStreamEndCapture(st, &g) != cudaSuccess || !g || cudaGraphInstantiate(&e->exec, g, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        e->exec = nullptr; e->seen = -1;
+        body();
+        return;
+    }
+    e->graph = g;
+    e->launches = (int)(launch_count() - l0);
+    cudaGraphLaunch(e->exec, st);
+}
+
 // ---------------------------------------------------------------- K9 ORB, K10 Hamming matcher
 constexpr int kOrbLevels = 12;             // ORB::create nlevels, src/stabilizer.cpp:485
 constexpr int kOrbMaxKp = 4096;            // 2500 requested + retainBest ties, rounded up
@@ -137,6 +185,7 @@ struct OrbPlan {
     unsigned int* hist = nullptr;
     int* counters = nullptr;
     void* cub_temp = nullptr;
+    GraphCache graphs;
 };
 // size_ratio: the reference's filterKeypointByRelativeSize ratio (0.10 for ORB; <= 0 keeps every level)
 OrbPlan* orb_plan_create(int w, int h, double size_ratio, int max_keypoints, std::string* err);
@@ -165,6 +214,7 @@ struct SiftPlan {
     unsigned int *rkeys = nullptr, *rkeys_sorted = nullptr;
     uint8_t* alive = nullptr;
     void* cub_temp = nullptr;
+    GraphCache graphs;
 };
 SiftPlan* sift_plan_create(int w, int h, double size_ratio, int max_keypoints, std::string* err);
 void sift_plan_destroy(SiftPlan* P);

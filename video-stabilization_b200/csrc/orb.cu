@@ -656,8 +656,20 @@ int orb_levels_used(const OrbPlan* P) { return ((const OrbLevels*)P->levels)->nl
 
 // gray: device u8 w x h (tight).  Outputs: kps[max_kp], desc[max_kp][32], *count (device int) = number of keypoints.
 // reference_order: additionally put the keypoints of every level into OpenCV's retainBest order.
+static void launch_orb_body(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, bool reference_order,
+                            cudaStream_t st);
+
 void launch_orb(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, bool reference_order,
                 cudaStream_t st) {
+    // the reference capture (once per mode switch) uploads a host flag: plain launches; everything else replays a graph
+    if (reference_order) { launch_orb_body(P, gray, kps, desc, count, true, st); return; }
+    const unsigned long long key[5] = {(unsigned long long)gray, (unsigned long long)kps, (unsigned long long)desc,
+                                       (unsigned long long)count, (unsigned long long)st};
+    run_graphed(P->graphs, key, st, [&] { launch_orb_body(P, gray, kps, desc, count, false, st); });
+}
+
+static void launch_orb_body(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, uint8_t* desc, int* count, bool reference_order,
+                            cudaStream_t st) {
     OrbLevels& L = *(OrbLevels*)P->levels;
     count_launch(8 + (L.nlevels_used - 1) + (reference_order ? 1 : 0));
     cudaMemcpyAsync(P->pyr, gray, (size_t)P->w * P->h, cudaMemcpyDeviceToDevice, st);

@@ -749,7 +749,16 @@ void sift_plan_destroy(SiftPlan* P) {
     delete P;
 }
 
+static void launch_sift_body(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t* desc, int* count, cudaStream_t st);
+
 void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t* desc, int* count, cudaStream_t st) {
+    // ~120 small dependent launches per frame: replayed as one CUDA graph from the third call with the same buffers on
+    const unsigned long long key[5] = {(unsigned long long)gray, (unsigned long long)kps_out, (unsigned long long)desc,
+                                       (unsigned long long)count, (unsigned long long)st};
+    run_graphed(P->graphs, key, st, [&] { launch_sift_body(P, gray, kps_out, desc, count, st); });
+}
+
+static void launch_sift_body(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t* desc, int* count, cudaStream_t st) {
     SiftOctaves& O = *(SiftOctaves*)P->octaves;
     static bool attr = false;
     const int max_smem = (int)(sizeof(float) * ((GBY + 2 * kMaxRadius) * (GBX + 2 * kMaxRadius) + (GBY + 2 * kMaxRadius) * GBX));
