@@ -168,6 +168,15 @@ struct vstab {
     cudaEvent_t ev_out = nullptr;        // output chain of the previous call has finished reading the ring
     cudaStream_t gftt_stream = nullptr;  // corner detection of frame n runs beside LK / fit of frame n
     cudaStream_t copy_stream = nullptr;  // host-to-device upload of frame n runs beside the estimation of frame n-1
+    // ORB / SIFT registration one call ahead: the presentation frame of call n+1 is already in the ring during call n
+    // (future >= 1), so its registration is enqueued on feat_stream right after the smoothing of call n and overlaps the
+    // download of call n, the host's return and the next upload.  lock_h / lock_tap are double-buffered by call parity.
+    cudaStream_t feat_stream = nullptr;
+    cudaEvent_t ev_feat = nullptr;       // look-ahead registration finished
+    cudaEvent_t ev_reg = nullptr;        // this call's registration / smoothing no longer needs the scratch buffers
+    long feat_p = -1;                    // presentation frame the pending look-ahead result belongs to
+    bool feat_pending = false;           // something was enqueued on feat_stream since the last wait
+    int lock_slot = 0;                   // lock_h / lock_tap half of the current call
     cudaEvent_t ev_pyr = nullptr;        // gray pyramid of frame n is complete
     cudaEvent_t ev_gftt = nullptr;       // corners of frame n are complete (needed by LK of frame n+1)
     size_t P = 15, F = 15;
@@ -296,17 +305,16 @@ static vstab_status stream_estimate(vstab* s) {
 // calculateFullLockStabilization, ORB / SIFT branch (stabilizer.cpp:440-787) for presentation frame p, on
 // the output stream: condition the full-resolution frame, detect + describe, and either capture the
 // reference (first call after setStabilizationMode) or match against it and fit.
-static vstab_status stream_feature_lock(vstab* s, long p) {
+static vstab_status stream_feature_lock(vstab* s, long p, cudaStream_t q, int slot) {
     auto set_err = [&](const std::string& e) { s->err = e; };
     Geometry& g = s->g;
-    cudaStream_t q = s->out_stream;
     const bool is_orb = s->mode == VSTAB_ORB_FULL_LOCK;
     if (!s->feat_ws.p) {
         std::vector<int> xo(g.ww), yo(g.wh);
         build_nn_table(g.cols, g.ww, xo.data());
         build_nn_table(g.rows, g.wh, yo.data());
         CK(s->feat_ws.alloc(featprep_workspace_bytes(g.ww, g.wh)));
-        CK(s->feat_gray.alloc((size_t)g.ww * g.wh));
+        CK(s->feat_gray.alloc((size_t)g.ww * g.wh * 2));                     // one conditioned image per lock slot
         CK(s->nn_x.alloc(sizeof(int) * g.ww)); CK(s->nn_y.alloc(sizeof(int) * g.wh));
         CK(cudaMemcpy(s->nn_x.p, xo.data(), sizeof(int) * g.ww, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s->nn_y.p, yo.data(), sizeof(int) * g.wh, cudaMemcpyHostToDevice));
@@ -317,8 +325,8 @@ static vstab_status stream_feature_lock(vstab* s, long p) {
         CK(s->m_good.alloc(kOrbMaxKp)); CK(s->m_status.alloc(kOrbMaxKp));
         CK(s->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(s->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
         CK(s->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));        // T[9], M[6], counts[2]
-        CK(s->lock_h.alloc(sizeof(double) * 9));
-        CK(s->lock_tap.alloc(sizeof(int) * 8));
+        CK(s->lock_h.alloc(sizeof(double) * 9 * 2));
+        CK(s->lock_tap.alloc(sizeof(int) * 8 * 2));
         CK(cudaMemsetAsync(s->orb_counts.p, 0, sizeof(int) * 4, q));
     }
     if (is_orb && !s->orb) {
@@ -330,19 +338,23 @@ static vstab_status stream_feature_lock(vstab* s, long p) {
         if (!s->sift) return VSTAB_ERR_CUDA;
     }
     const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)(p % s->W) * g.frame_bytes;           // :444
-    launch_featprep(frame, g.pitch, s->nn_x.as<int>(), s->nn_y.as<int>(), g.ww, g.wh, s->feat_ws.p,
-                    s->feat_gray.as<uint8_t>(), q);                                                // :448-477
+    uint8_t* feat_gray = s->feat_gray.as<uint8_t>() + (size_t)slot * g.ww * g.wh;
+    launch_featprep(frame, g.pitch, s->nn_x.as<int>(), s->nn_y.as<int>(), g.ww, g.wh, s->feat_ws.p, feat_gray, q);  // :448-477
     int* counts = s->orb_counts.as<int>();
     double* Tfit = s->lock_fit.as<double>();
     int* fitc = reinterpret_cast<int*>(Tfit + 16);
     const bool capture = !s->has_reference;                                                      // :520-589
+    double* lock_h = s->lock_h.as<double>() + 9 * slot;
+    int* lock_tap = s->lock_tap.as<int>() + 8 * slot;
+    // "previously returned H" (:446) carries over from the other half
+    if (!capture) CK(cudaMemcpyAsync(lock_h, s->lock_h.as<double>() + 9 * (slot ^ 1), sizeof(double) * 9, cudaMemcpyDeviceToDevice, q));
     OrbKeypoint* kps = capture ? s->ref_kps.as<OrbKeypoint>() : s->cur_kps.as<OrbKeypoint>();
     uint8_t* desc = capture ? s->ref_desc.as<uint8_t>() : s->cur_desc.as<uint8_t>();
     int* cnt = counts + (capture ? 0 : 1);
-    if (is_orb) launch_orb(s->orb, s->feat_gray.as<uint8_t>(), kps, desc, cnt, capture, q);      // :557-559 / :604-612
-    else launch_sift(s->sift, s->feat_gray.as<uint8_t>(), kps, desc, cnt, q);                    // :572-574 / :614-621
+    if (is_orb) launch_orb(s->orb, feat_gray, kps, desc, cnt, capture, q);                       // :557-559 / :604-612
+    else launch_sift(s->sift, feat_gray, kps, desc, cnt, q);                                     // :572-574 / :614-621
     if (capture) {
-        launch_lock_update(Tfit, fitc, counts + 0, counts + 0, counts + 0, 1, s->lock_h.as<double>(), s->lock_tap.as<int>(), q);
+        launch_lock_update(Tfit, fitc, counts + 0, counts + 0, counts + 0, 1, lock_h, lock_tap, q);
         s->has_reference = true;
     } else {
         if (is_orb)
@@ -357,7 +369,7 @@ static vstab_status stream_feature_lock(vstab* s, long p) {
                             counts + 2, q);                                                        // :675-708, :711-716
         launch_fit_large(s->m_ref.as<float2>(), s->m_cur.as<float2>(), s->m_status.as<uint8_t>(), counts + 2, 5.0,
                          g.ww / 2.0, g.wh / 2.0, Tfit, Tfit + 9, fitc, q);                         // :734-758
-        launch_lock_update(Tfit, fitc, counts + 0, counts + 1, counts + 2, 0, s->lock_h.as<double>(), s->lock_tap.as<int>(), q);  // :784-787
+        launch_lock_update(Tfit, fitc, counts + 0, counts + 1, counts + 2, 0, lock_h, lock_tap, q);  // :784-787
     }
     CK(cudaGetLastError());
     return VSTAB_OK;
@@ -379,20 +391,39 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
     }
     const bool feature_lock = s->mode == VSTAB_ORB_FULL_LOCK || s->mode == VSTAB_SIFT_FULL_LOCK;
     if (feature_lock) {
-        vstab_status st = stream_feature_lock(s, p);
-        if (st != VSTAB_OK) return st;
+        const int slot = s->lock_slot ^ 1;
+        const bool ahead = s->feat_pending && s->feat_p == p && s->has_reference;
+        if (s->feat_pending) CK(cudaStreamWaitEvent(q, s->ev_feat, 0));     // look-ahead result, or just the scratch buffers
+        s->feat_pending = false;
+        if (!ahead) {
+            vstab_status st = stream_feature_lock(s, p, q, slot);
+            if (st != VSTAB_OK) return st;
+        }
+        s->lock_slot = slot;
     }
     SmoothArgs a{};
     a.T = s->T.as<double>(); a.t_mod = s->t_mod;
     a.P = (int)s->P; a.F = (int)s->F;
     a.mode = s->mode; a.lock_call = s->lock_call;
     a.acc = s->acc.as<double>(); a.acc_mod = 0;
-    a.lock_h = feature_lock ? s->lock_h.as<double>() : nullptr;
+    a.lock_h = feature_lock ? s->lock_h.as<double>() + 9 * s->lock_slot : nullptr;
     a.scale = g.scale;
     a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
     a.npix = (double)g.rows * (double)g.cols;
     launch_smooth(a, n, 1, s->wp.as<WarpParams>(), q);                                                 // :1234-1296
     s->mark(8, q);
+    static const bool lookahead = !(getenv("VSTAB_LOOKAHEAD") && atoi(getenv("VSTAB_LOOKAHEAD")) == 0);
+    if (feature_lock && lookahead && s->F >= 1 && s->has_reference) {
+        // registration of the next call's presentation frame, beside this call's warp and download
+        const long pn = n + 1 - (long)s->F > 0 ? n + 1 - (long)s->F : 0;
+        CK(cudaEventRecord(s->ev_reg, q));
+        CK(cudaStreamWaitEvent(s->feat_stream, s->ev_reg, 0));
+        vstab_status st = stream_feature_lock(s, pn, s->feat_stream, s->lock_slot ^ 1);
+        if (st != VSTAB_OK) return st;
+        CK(cudaEventRecord(s->ev_feat, s->feat_stream));
+        s->feat_p = pn;
+        s->feat_pending = true;
+    }
     launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
                 d_out, out_pitch, 0, q);                                                               // :1309-1313
     s->mark(9, q);
@@ -547,6 +578,9 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
         cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s->gftt_stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->feat_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_feat, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_reg, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_gftt, cudaEventDisableTiming) != cudaSuccess) {
         g_err = "cudaStreamCreate failed"; vstab_destroy(s); return VSTAB_ERR_CUDA;
@@ -577,6 +611,9 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_out) cudaEventDestroy(s->ev_out);
     if (s->gftt_stream) { cudaStreamSynchronize(s->gftt_stream); cudaStreamDestroy(s->gftt_stream); }
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->feat_stream) { cudaStreamSynchronize(s->feat_stream); cudaStreamDestroy(s->feat_stream); }
+    if (s->ev_feat) cudaEventDestroy(s->ev_feat);
+    if (s->ev_reg) cudaEventDestroy(s->ev_reg);
     if (s->ev_pyr) cudaEventDestroy(s->ev_pyr);
     if (s->ev_gftt) cudaEventDestroy(s->ev_gftt);
     if (s->orb) orb_plan_destroy(s->orb);
@@ -589,6 +626,7 @@ vstab_status vstab_set_mode(vstab_t* s, int mode) {
     if (mode < 0 || mode > 5) { s->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
     // stabilizer.cpp:55-70: reset reference + accumulator, keep window / prevGray_ / prevPoints_
     s->has_reference = false;
+    s->feat_p = -1;                      // a pending look-ahead registration belongs to the old reference: not consumed
     s->acc_valid = false;
     s->acc_to = -1;
     s->mode = mode;
@@ -608,6 +646,7 @@ vstab_status vstab_synchronize(vstab_t* s) {
     CK(cudaStreamSynchronize(s->out_stream));
     CK(cudaStreamSynchronize(s->gftt_stream));
     CK(cudaStreamSynchronize(s->copy_stream));
+    CK(cudaStreamSynchronize(s->feat_stream));
     return VSTAB_OK;
 }
 
@@ -695,9 +734,9 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
         case VSTAB_TAP_BORDER: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, border), 3, 3);
         case VSTAB_TAP_EIG: return copy(s->gws.eig, sizeof(float) * g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_INLIERS: if (last == 0) return 0; return copy(s->fitc.p, sizeof(int) * 2, 2);
-        case VSTAB_TAP_LOCK_H: if (!s->lock_h.p) return 0; return copy(s->lock_h.p, sizeof(double) * 9, 9);
-        case VSTAB_TAP_ORB_COUNTS: if (!s->lock_tap.p) return 0; return copy(s->lock_tap.p, sizeof(int) * 5, 5);
-        case VSTAB_TAP_FEAT_GRAY: if (!s->feat_gray.p) return 0; return copy(s->feat_gray.p, (size_t)g.ww * g.wh, (long)g.ww * g.wh);
+        case VSTAB_TAP_LOCK_H: if (!s->lock_h.p) return 0; return copy(s->lock_h.as<double>() + 9 * s->lock_slot, sizeof(double) * 9, 9);
+        case VSTAB_TAP_ORB_COUNTS: if (!s->lock_tap.p) return 0; return copy(s->lock_tap.as<int>() + 8 * s->lock_slot, sizeof(int) * 5, 5);
+        case VSTAB_TAP_FEAT_GRAY: if (!s->feat_gray.p) return 0; return copy(s->feat_gray.as<uint8_t>() + (size_t)s->lock_slot * g.ww * g.wh, (size_t)g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_CHANNEL_SUMS:
             return copy(s->sums.as<unsigned long long>() + (s->last_presented % s->W) * 3, sizeof(unsigned long long) * 3, 3);
     }
