@@ -21,7 +21,9 @@ PyrDesc make_pyr_desc(int w, int h) {
         if (d.nlev == kLkLevels && l + 1 < kLkLevels && (w <= kLkWin || h <= kLkWin)) d.nlev = l + 1;
     }
     for (int l = 0; l < kLkLevels; ++l) {
-        d.pitch[l] = (d.w[l] + 2 * kLkPad + 3) & ~3;
+        // one row pitch for all levels (that of level 0): the tracker addresses a column of taps as one pointer +
+        // immediate multiples of the pitch (lk.cu); rows beyond a level's own padded width are never touched
+        d.pitch[l] = (d.w[0] + 2 * kLkPad + 3) & ~3;
         const size_t px = (size_t)d.pitch[l] * (d.h[l] + 2 * kLkPad);
         d.poff[l] = 0;                              // (plain padded u8 levels are not materialised: the quads carry them)
         d.doff[l] = off;
@@ -96,6 +98,7 @@ constexpr int PTX = 32, PTY = 8, PPX = 4;            // threads x, threads y, pi
 constexpr int PTW = PTX * PPX;                        // 128
 struct PrepLevels {
     int w[kLkLevels], h[kLkLevels], pitch[kLkLevels];
+    int pw[kLkLevels];               // padded width of the level (multiple of 4, <= pitch)
     int tiles_x[kLkLevels];
     int first[kLkLevels + 1];        // first tile of each level
     unsigned off[kLkLevels], poff[kLkLevels], doff[kLkLevels], qoff[kLkLevels];
@@ -147,7 +150,7 @@ lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
     }
     __syncthreads();
     const int Y = Y0 + threadIdx.y, X = X0 + threadIdx.x * PPX;
-    if (Y >= h + 2 * kLkPad || X >= pitch) return;
+    if (Y >= h + 2 * kLkPad || X >= L.pw[l]) return;
     // staged bytes 4*tx .. 4*tx+5 of rows r-1, r, r+1 hold columns c-1 .. c+4 of this thread's 4 pixels
     const int r = threadIdx.y + 1;
     const unsigned* rm = reinterpret_cast<const unsigned*>(&t[r - 1][0]) + threadIdx.x;
@@ -191,7 +194,8 @@ void launch_pyramid(const PyrDesc& d, uint8_t* pyr, int nframes, cudaStream_t st
         L.w[l] = d.w[l]; L.h[l] = d.h[l]; L.pitch[l] = d.pitch[l];
         L.off[l] = (unsigned)d.off[l]; L.poff[l] = (unsigned)d.poff[l]; L.doff[l] = (unsigned)d.doff[l]; L.qoff[l] = (unsigned)d.qoff[l];
         L.first[l] = tiles;
-        L.tiles_x[l] = (d.pitch[l] + PTW - 1) / PTW;
+        L.pw[l] = (d.w[l] + 2 * kLkPad + 3) & ~3;
+        L.tiles_x[l] = (L.pw[l] + PTW - 1) / PTW;
         tiles += l < d.nlev ? L.tiles_x[l] * ((d.h[l] + 2 * kLkPad + PTY - 1) / PTY) : 0;
     }
     L.first[kLkLevels] = tiles;
