@@ -366,9 +366,10 @@ def run_ours(args):
                          f"(ping-pong), oracle.StabilizerRef over cv2 with {arm.cores} threads; host has "
                          f"{os.cpu_count()} logical cores"}
 
-    modes = None
+    modes, modes_offline = None, None
     if world == 1 and rank == 0 and not args.no_mode_probes:
         modes = run_mode_probes(args, torch, vs, lib, local)
+        modes_offline = run_4k_probe(args, torch, vs, local, peak)
 
     if rank == 0:
         line = {
@@ -382,7 +383,7 @@ def run_ours(args):
                        "l2_policy": f"inputs_exceed_l2 ({n_local * 3 * W * H / 1e6:.0f} MB of frames per GPU per step vs 126 MB L2)",
                        "parallelism": f"frame-sharded x{world}, one all-gather of 72 B/frame" if world > 1 else "single GPU"},
             "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "other_modes_streaming": modes,
+            "gpu_launches": int(launches), "clocks": clocks, "other_modes_streaming": modes, "other_modes_offline": modes_offline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -507,6 +508,56 @@ def run_mode_probes(args, torch, vs, lib, local):
                      "calls": n_timed, "keypoints_current": int(cnt[0]), "keypoints_reference": int(cnt[1]),
                      "matches": int(cnt[2]), "inliers": int(cnt[3])}
     return out
+
+
+def run_4k_probe(args, torch, vs, local, peak):
+    """Secondary figure: the LK + warp path on a 3840x2160 clip at working height 360 (the per-GPU shape of BASELINE
+    config 5), frames resident in HBM, same window / mode / camera path as the headline workload."""
+    from vstab_b200 import offline, synth
+    w, h, wh, n = 3840, 2160, 360, 96
+    dev = f"cuda:{local}"
+    tex = torch.from_numpy(synth.make_texture(2048)).to(dev)
+    frames = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    path = synth.camera_path(n, drift=PATH_DRIFT)
+    for s0 in range(0, n, 16):
+        offline.render_frames(tex, path[s0:s0 + 16], h, w, synth.focal_for_width(w), frames[s0:s0 + 16], device=local)
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    T = torch.zeros((n, 9), dtype=torch.float64, device=dev)
+    sums = torch.zeros((n, 3), dtype=torch.int64, device=dev)
+    off = offline.OfflineStabilizer(PAST, FUTURE, wh, h, w, n, device=local)
+    mode = vs.ACCUMULATED_FULL_LOCK
+
+    def step():
+        off.estimate(frames, 0, None, T, sums)
+        off.prepare(T, mode, LOCK_CALL)
+        off.render(frames, 0, 0, n, T, mode, LOCK_CALL, sums, out)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    off.set_timing(True)
+    off.stage_times()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(off.stream)
+    for _ in range(reps):
+        step()
+    e1.record(off.stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    stages = off.stage_times()
+    off.set_timing(False)
+    off.close()
+    B = 3 * w * h
+    warp_ms = stages["warp"][0] / reps
+    ingest_ms = stages["ingest"][0] / reps
+    return {"c5_lk_full_lock_4k_wh360": {
+        "value": n / (ms * 1e-3), "unit": UNIT, "frames": n, "ms_per_step": ms,
+        "api": "vstab_offline_estimate / _prepare / _render (frames resident in HBM, one launch per stage)",
+        "stages_ms": {k: v[0] / reps for k, v in stages.items() if v[1]},
+        "hbm_bound_stages": {
+            "ingest": {"achieved": (B + 640 * 360) * n / (ingest_ms * 1e-3) / 1e9, "frac": (B + 640 * 360) * n / (ingest_ms * 1e-3) / 1e9 / peak},
+            "warp": {"achieved": 2 * B * n / (warp_ms * 1e-3) / 1e9, "frac": 2 * B * n / (warp_ms * 1e-3) / 1e9 / peak}}}}
 
 
 def main():

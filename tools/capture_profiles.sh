@@ -10,7 +10,7 @@ python bench.py $ARGS > gpurun_out/plain_${TAG}.log 2>&1 || { echo "bench failed
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench_256f.csv \
     python bench.py $ARGS > gpurun_out/ncu_list_${TAG}.log 2>&1
 ncu --set full --import-source on --clock-control none \
-    -k regex:'ingest_kernel|pyrdown_kernel|lkprep_kernel|eig_kernel|topk_greedy_kernel|lk_kernel|fit_kernel|smooth_kernel|warp_tile_kernel|acc_chunk' \
+    -k regex:'ingest_kernel|pyrdown_kernel|lkprep_kernel|eig_kernel|topk_greedy_kernel|lk_strip_kernel|fit_kernel|smooth_kernel|warp_tile_kernel|acc_chunk' \
     -c 14 -o gpurun_out/${TAG}_full -f python bench.py $ARGS > gpurun_out/ncu_full_${TAG}.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_streaming.csv \
     python tools/stream_probe.py 56 > gpurun_out/stream_probe_${TAG}.log 2>&1

@@ -12,4 +12,4 @@ for l in sys.stdin:
         print('value %.0f ms/step %.3f' % (d['value'], d['ms_per_step']), ' '.join('%s %.3f' % (k, v['ms_per_step']) for k, v in s.items()))
 "
 }
-for w in 4 2 1; do for r in 96 80; do run VSTAB_LK_WARPS=$w VSTAB_LK_REGS=$r; done; done
+for r in 80 72 64; do run VSTAB_LK_WARPS=1 VSTAB_LK_REGS=$r; done

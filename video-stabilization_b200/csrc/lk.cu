@@ -284,7 +284,10 @@ void launch_lk(const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_str
     const int P = uniform ? d.pitch[0] : 0;
 #define VSTAB_LK_ARGS P, nframes, st, prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status
     // min blocks per SM = 65536 / (registers * threads per CTA)
-    if (wpb == 1) { if (regs == 80) launch_strip<1, 24>(VSTAB_LK_ARGS); else launch_strip<1, 20>(VSTAB_LK_ARGS); }
+    if (wpb == 1) {
+        if (regs == 64) launch_strip<1, 32>(VSTAB_LK_ARGS); else if (regs == 72) launch_strip<1, 28>(VSTAB_LK_ARGS);
+        else if (regs == 80) launch_strip<1, 24>(VSTAB_LK_ARGS); else launch_strip<1, 20>(VSTAB_LK_ARGS);
+    }
     else if (wpb == 2) { if (regs == 80) launch_strip<2, 12>(VSTAB_LK_ARGS); else launch_strip<2, 10>(VSTAB_LK_ARGS); }
     else { if (regs == 80) launch_strip<4, 6>(VSTAB_LK_ARGS); else launch_strip<4, 5>(VSTAB_LK_ARGS); }
 #undef VSTAB_LK_ARGS
