@@ -1,10 +1,16 @@
-cd /root/repo
-timeout 1500 python -m pytest tests/test_gpu_orb.py tests/test_gpu_pipeline.py tests/test_gpu_offline.py -q -m gpu -x 2>&1 | tail -3
-for g in 1 0; do
-VSTAB_LOOKAHEAD=$g timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --frames-per-gpu 128 > gpurun_out/exp.log 2>&1
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/exp.log").read().strip().splitlines()[-1])
-print("lookahead $g", {k: (round(v["value"],1), v["matches"], v["inliers"]) for k,v in d["other_modes_streaming"].items()})
-PY
-done
+#!/bin/bash
+# scratch experiment runner for the GPU box
+cd "$(dirname "$0")/.."
+ARGS="--steps 6 --warmup 3 --frames-per-gpu 256 --batch 256 --no-cpu-baseline --no-e2e --no-mode-probes"
+run() {
+  echo "== $*"
+  env "$@" python bench.py $ARGS 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); s=d['stages']
+        print('value %.0f ms/step %.3f' % (d['value'], d['ms_per_step']), ' '.join('%s %.3f' % (k, v['ms_per_step']) for k, v in s.items()))
+"
+}
+for pf in 0 4 8 16; do run VSTAB_EIG_PF=$pf; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pipeline.py tests/test_gpu_offline.py -q -m gpu -x 2>&1 | tail -3

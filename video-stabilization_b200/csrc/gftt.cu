@@ -38,7 +38,7 @@ struct D3 { double xx, xy, yy; };
 __global__ void __launch_bounds__(32 * kEigWarps, 8)
 eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, int nstrips, int nsegs, int seg_h, int idx_bits,
            float* __restrict__ eig_out, unsigned int* __restrict__ maxbits,
-           unsigned long long* __restrict__ keys, int* __restrict__ seg_end, int cap, double quality) {
+           unsigned long long* __restrict__ keys, int* __restrict__ seg_end, int cap, double quality, int pf) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kEigWarps + (threadIdx.x >> 5);
     const int frame = blockIdx.y;
@@ -109,6 +109,8 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
             if (yp <= p_hi) {
                 row_terms(ra, rb, rc, S[jB], R[jB]);                 // gray row yp+1
                 load_raw(reflect101(yp + 2, h), ra, rb, rc);         // (h + 1 at most: still a valid reflection)
+                // every row of the strip starts a new 128-byte line: ask for the line `pf` rows further down now
+                if (pf > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (min(yp + 2 + pf, h - 1) * w + xr)));
                 // Dx = fma(S[y-1] + S[y+1], k1, S[y]*k0),  Dy = R[y+1] - R[y-1]
                 const float dx = __fmaf_rn(__fadd_rn(S[j], S[jB]), k1, __fmul_rn(S[jA], k0));
                 const float dy = __fsub_rn(R[jB], R[j]);
@@ -527,8 +529,10 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
         const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + seg_h - 1) / seg_h;
         dim3 grid((nstrips * nsegs + kEigWarps - 1) / kEigWarps, nframes);
         count_launch(1);
+        static int pf = -1;
+        if (pf < 0) { const char* e = getenv("VSTAB_EIG_PF"); pf = e ? atoi(e) : 4; }
         eig_kernel<<<grid, 32 * kEigWarps, 0, st>>>(gray, gray_frame_stride, w, h, nstrips, nsegs, seg_h, ws.idx_bits, eig_out, ws.maxbits,
-                                                    ws.keys, ws.seg_end, ws.cap, quality);
+                                                    ws.keys, ws.seg_end, ws.cap, quality, pf);
     }
     if (fused) {
         count_launch(1);

@@ -100,6 +100,7 @@ struct PrepLevels {
     int w[kLkLevels], h[kLkLevels], pitch[kLkLevels];
     int pw[kLkLevels];               // padded width of the level (multiple of 4, <= pitch)
     int tiles_x[kLkLevels];
+    unsigned tiles_x_inv[kLkLevels]; // ceil(2^32 / tiles_x): tile / tiles_x == umulhi(tile, inv) for tile < 2^16
     int first[kLkLevels + 1];        // first tile of each level
     unsigned off[kLkLevels], poff[kLkLevels], doff[kLkLevels], qoff[kLkLevels];
 };
@@ -123,11 +124,42 @@ lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
     for (int i = 1; i < kLkLevels; ++i) l += (tile >= L.first[i]);
     const int w = L.w[l], h = L.h[l], pitch = L.pitch[l];
     const int ti = tile - L.first[l];
-    const int ty = ti / L.tiles_x[l], tx = ti - ty * L.tiles_x[l];
+    const int ty = L.tiles_x[l] == 1 ? ti : (int)__umulhi((unsigned)ti, L.tiles_x_inv[l]), tx = ti - ty * L.tiles_x[l];
     const int X0 = tx * PTW, Y0 = ty * PTY;                  // padded coordinates of the tile
     uint8_t* base = pyr + (size_t)blockIdx.y * frame_bytes;
     const uint8_t* src = base + L.off[l];
     const int tid = threadIdx.y * PTX + threadIdx.x;
+    // Interior tile (57 % of level 0 at 640 x 360): every tap of every pixel of the tile lies inside the image and the
+    // rows are word-aligned, so a thread takes its 3 x 6 bytes straight from global memory as 3 aligned words per row
+    // (x0 = X - kLkPad is a multiple of 4: bytes x0-1 .. x0+4 sit in the words at x0-4, x0, x0+4) -- no staging, no
+    // reflection tables, no barrier.
+    if ((w & 3) == 0 && X0 >= kLkPad + 4 && X0 + PTW - kLkPad <= w - 1 && Y0 >= kLkPad + 1 && Y0 + PTY - kLkPad <= h - 1) {
+        const int Y = Y0 + threadIdx.y, X = X0 + threadIdx.x * PPX;
+        const int wq = w >> 2;
+        const unsigned* rw = reinterpret_cast<const unsigned*>(src + (size_t)(Y - kLkPad - 1) * w + (X - kLkPad));
+        unsigned a[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            a[r][0] = __ldg(rw + r * wq - 1); a[r][1] = __ldg(rw + r * wq); a[r][2] = __ldg(rw + r * wq + 1);
+        }
+        int dq[PPX], qq[PPX];
+#pragma unroll
+        for (int k = 0; k < PPX; ++k) {
+            // columns (c-1, c, c+1, c+2) of the three rows, c = x0 + k
+            unsigned t3[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                t3[r] = k == 0 ? __funnelshift_r(a[r][0], a[r][1], 24) : k == 1 ? a[r][1] : __funnelshift_r(a[r][1], a[r][2], 8 * (k - 1));
+            const unsigned wm = t3[0], w0 = t3[1], wp = t3[2];
+            qq[k] = (int)__byte_perm(w0, wp, 0x6521);
+            const int dx = dp4a_us(wp, 0x000300fdu, dp4a_us(w0, 0x000a00f6u, dp4a_us(wm, 0x000300fdu, 0)));
+            const int dy = dp4a_us(wp, 0x00030a03u, dp4a_us(wm, 0x00fdf6fdu, 0));
+            dq[k] = (dx & 0xffff) | (dy << 16);
+        }
+        *reinterpret_cast<int4*>(base + L.doff[l] + ((size_t)Y * pitch + X) * 4) = make_int4(dq[0], dq[1], dq[2], dq[3]);
+        *reinterpret_cast<int4*>(base + L.qoff[l] + ((size_t)Y * pitch + X) * 4) = make_int4(qq[0], qq[1], qq[2], qq[3]);
+        return;
+    }
     if (tid < PTW + 2) sxs[tid] = reflect101_multi(X0 + tid - 1 - kLkPad, w);
     else if (tid < PTW + 2 + PTY + 2) sys[tid - (PTW + 2)] = reflect101_multi(Y0 + (tid - (PTW + 2)) - 1 - kLkPad, h) * w;
     __syncthreads();
@@ -196,6 +228,7 @@ void launch_pyramid(const PyrDesc& d, uint8_t* pyr, int nframes, cudaStream_t st
         L.first[l] = tiles;
         L.pw[l] = (d.w[l] + 2 * kLkPad + 3) & ~3;
         L.tiles_x[l] = (L.pw[l] + PTW - 1) / PTW;
+        L.tiles_x_inv[l] = (unsigned)(((1ull << 32) + L.tiles_x[l] - 1) / L.tiles_x[l]);
         tiles += l < d.nlev ? L.tiles_x[l] * ((d.h[l] + 2 * kLkPad + PTY - 1) / PTY) : 0;
     }
     L.first[kLkLevels] = tiles;
