@@ -261,3 +261,54 @@ def test_config5_shape_4k_wh360(texture):
     assert s["corners_differ"] == 0 and s["status"] == 0
     assert s["lk"] <= 0.05 and s["t"] <= H_TOL_PX and s["h"] <= H_TOL_PX
     assert s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
+
+
+# ---- size-independent properties at BASELINE's full frame sizes (no oracle run needed) ------------------------
+@pytest.mark.parametrize("W,H,wh", [(1920, 1080, 360), (3840, 2160, 360), (3840, 2160, 2160)])
+@pytest.mark.parametrize("mode", [None, vs.ACCUMULATED_FULL_LOCK])
+def test_static_clip_is_returned_unchanged(texture, W, H, wh, mode):
+    """Idempotence: a clip whose frames are all equal has identity motion, so every output frame equals the input
+    bit for bit (tracker converges with zero mismatch, the fit returns the identity, the warp of an identity
+    homography is a copy) -- in GLOBAL_SMOOTHING and in ACCUMULATED_FULL_LOCK."""
+    frame = render_clip(texture, W, H, 1)[0]
+    st = vs.Stabilizer(3, 2, wh)
+    for i in range(9):
+        if mode is not None and i == 4:
+            st.set_stabilization_mode(mode)
+        got = st.stabilize_frame(frame)
+        assert np.array_equal(got, frame), f"call {i}"
+        if i:
+            Hs = st.tap(vs.TAP_H_SCALED)
+            assert _corner_diff(Hs, np.eye(3), W, H) < 1e-6
+    st.close()
+
+
+@pytest.mark.parametrize("W,H,wh,k", [(1920, 1080, 360, 3), (3840, 2160, 360, 6)])
+def test_integer_shift_is_undone_by_full_lock(texture, W, H, wh, k):
+    """A camera that moves by whole working-resolution pixels (k source pixels = 1 working pixel) under
+    ACCUMULATED_FULL_LOCK: the stabilizing homography must be the pure translation back onto the anchor frame within
+    the north-star tolerance (0.1 px at the frame corners), and the output must show the anchor frame again wherever
+    the shifted frame still covers it (a residual of a few hundredths of a pixel moves Q5 coordinates by one or two
+    steps: small differences on edges, none on average)."""
+    big = render_clip(texture, W + 16 * k, H + 16 * k, 1)[0]
+    shifts = [(0, 0), (2, 1), (5, 3), (3, 6), (7, 2), (4, 4), (1, 5), (6, 0), (2, 2), (0, 3)]
+    frames = [np.ascontiguousarray(big[dy * k: dy * k + H, dx * k: dx * k + W]) for dx, dy in shifts]
+    P, F = 3, 2
+    st = vs.Stabilizer(P, F, wh)
+    lock_call = F + 1                      # presentation frame of that call = frame 1 -> anchor
+    a = lock_call - F
+    m = 8 * k                              # margin covering every shift
+    for i, f in enumerate(frames):
+        if i == lock_call:
+            st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
+        got = st.stabilize_frame(f)
+        if i < lock_call:
+            continue
+        j = i - F
+        want = np.eye(3)
+        want[0, 2] = (shifts[j][0] - shifts[a][0]) * k
+        want[1, 2] = (shifts[j][1] - shifts[a][1]) * k
+        assert _corner_diff(st.tap(vs.TAP_H_SCALED), want, W, H) <= H_TOL_PX, i
+        d = np.abs(got[m:H - m, m:W - m].astype(int) - frames[a][m:H - m, m:W - m])
+        assert d.mean() < 0.5 and d.max() <= 4 * MAX_Q5_STEP, (i, float(d.mean()), int(d.max()))
+    st.close()
