@@ -12,5 +12,5 @@ for l in sys.stdin:
         print('value %.0f ms/step %.3f' % (d['value'], d['ms_per_step']), ' '.join('%s %.3f' % (k, v['ms_per_step']) for k, v in s.items()))
 "
 }
-for pf in 0 4 8 16; do run VSTAB_EIG_PF=$pf; done
+for v in 0 1; do run VSTAB_TOPK_SMALL=$v; done
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pipeline.py tests/test_gpu_offline.py -q -m gpu -x 2>&1 | tail -3

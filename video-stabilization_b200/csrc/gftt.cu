@@ -332,19 +332,30 @@ greedy_kernel(const unsigned long long* __restrict__ keys, const int* __restrict
 //     significant bits) and handed to warp 0 for the greedy pass; the next chunk is only needed when fewer than
 //     max_corners points were accepted and candidates above the quality threshold remain (rare: 0.01 * max cuts the
 //     list to ~4.5 k keys at working height 360, ~16 k at 1080).
-constexpr int kTkThreads = 1024, kTkItems = 8, kTkCap = kTkThreads * kTkItems;
-typedef cub::BlockRadixSort<unsigned long long, kTkThreads, kTkItems> TkSort;
-union TkScratch {
-    typename TkSort::TempStorage sort;
-    unsigned long long keys[kTkCap];
+// Two shapes: 1024 threads x 8 keys (one CTA per SM: a lone frame in streaming wants every thread) and 512 threads x 8
+// keys (chunks of 4096; two CTAs per SM when the cell grid leaves room, so a batch of 256 frames is ONE wave over 148 SMs
+// instead of two).
+template <int kTkThreads, int kTkItems>
+struct TkShape {
+    static constexpr int kCap = kTkThreads * kTkItems;
+    typedef cub::BlockRadixSort<unsigned long long, kTkThreads, kTkItems> Sort;
+    union Scratch {
+        typename Sort::TempStorage sort;
+        unsigned long long keys[kCap];
+    };
 };
 
-__global__ void __launch_bounds__(kTkThreads)
+template <int kTkThreads, int kTkItems, int kMinBlocks>
+__global__ void __launch_bounds__(kTkThreads, kMinBlocks)
 topk_greedy_kernel(const unsigned long long* __restrict__ keys_all, const int* __restrict__ seg_begin,
                    int* __restrict__ seg_end, unsigned int* __restrict__ maxbits, double quality, int idx_bits, int cap,
                    int w, int min_distance, int cell, int grid_w, int grid_h, int max_corners,
                    float2* __restrict__ pts, int* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char tk_smem[];
+    typedef TkShape<kTkThreads, kTkItems> Shape;
+    typedef typename Shape::Scratch TkScratch;
+    typedef typename Shape::Sort TkSort;
+    constexpr int kTkCap = Shape::kCap;
     TkScratch& S = *reinterpret_cast<TkScratch*>(tk_smem);
     unsigned short* gfr = reinterpret_cast<unsigned short*>(tk_smem + sizeof(TkScratch));
     __shared__ unsigned hist[1024];
@@ -374,7 +385,7 @@ topk_greedy_kernel(const unsigned long long* __restrict__ keys_all, const int* _
             for (int top = key_bits; top > 0; top -= 10) {
                 const int shift = top > 10 ? top - 10 : 0;
                 const unsigned dmask = (1u << (top - shift)) - 1u;
-                hist[tid] = 0u;
+                for (int i = tid; i < 1024; i += kTkThreads) hist[i] = 0u;
                 __syncthreads();
                 for (int i0 = tid; i0 < n; i0 += 4 * kTkThreads) {         // 4 loads in flight per thread
                     unsigned long long kk[4];
@@ -507,14 +518,26 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     if (max_corners > kMaxCorners) max_corners = kMaxCorners;
     static const bool allow_fused = !(getenv("VSTAB_GFTT_FUSED") && atoi(getenv("VSTAB_GFTT_FUSED")) == 0);
     const size_t grid_bytes = (size_t)ws.ncells * kCellCap * sizeof(unsigned short);
-    const size_t fused_smem = sizeof(TkScratch) + grid_bytes;
+    typedef TkShape<1024, 8> Big;
+    typedef TkShape<512, 8> Small;
+    const size_t fused_smem = sizeof(Big::Scratch) + grid_bytes;
+    const size_t small_smem = sizeof(Small::Scratch) + grid_bytes;
     const bool fused = allow_fused && fused_smem <= (size_t)220 * 1024;
+    // batches larger than one wave of single-CTA SMs: the half-size shape when two of its CTAs fit an SM
+    // (227 KB shared memory per SM, 1 KB reserved per CTA, + the static histogram)
+    static int num_sms = 0, small_ok = 1;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
-        cudaFuncSetAttribute(topk_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(topk_greedy_kernel<1024, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(topk_greedy_kernel<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (const char* e = getenv("VSTAB_TOPK_SMALL")) small_ok = atoi(e);
         attr_set = true;
     }
+    const bool use_small = fused && small_ok && nframes > num_sms && small_smem <= (size_t)108 * 1024;
     const int key_bits = 31 + ws.idx_bits;
     // the fused kernel leaves the per-frame counters reset behind it
     if (!(fused && ws.counters_ready && nframes == 1)) {
@@ -536,9 +559,14 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     }
     if (fused) {
         count_launch(1);
-        topk_greedy_kernel<<<nframes, kTkThreads, fused_smem, st>>>(ws.keys, ws.seg_begin, ws.seg_end, ws.maxbits, quality,
-                                                                    ws.idx_bits, ws.cap, w, min_distance, ws.cell, ws.grid_w,
-                                                                    ws.grid_h, max_corners, pts, counts);
+        if (use_small)
+            topk_greedy_kernel<512, 8, 2><<<nframes, 512, small_smem, st>>>(ws.keys, ws.seg_begin, ws.seg_end, ws.maxbits, quality,
+                                                                           ws.idx_bits, ws.cap, w, min_distance, ws.cell, ws.grid_w,
+                                                                           ws.grid_h, max_corners, pts, counts);
+        else
+            topk_greedy_kernel<1024, 8, 1><<<nframes, 1024, fused_smem, st>>>(ws.keys, ws.seg_begin, ws.seg_end, ws.maxbits, quality,
+                                                                             ws.idx_bits, ws.cap, w, min_distance, ws.cell, ws.grid_w,
+                                                                             ws.grid_h, max_corners, pts, counts);
         return;
     }
     // unfused schedule: clamp, cub radix sort (its passes are not counted as launches of ours), greedy
