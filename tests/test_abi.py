@@ -113,3 +113,63 @@ def test_decompose_compose_host_functions(lib, golden):
 def test_status_strings(lib):
     assert lib.vstab_status_string(0) == b"ok"
     assert b"size" in lib.vstab_status_string(2)
+
+
+def _front_end():
+    exe = os.path.join(os.path.dirname(os.path.dirname(vs.LIB_PATH)), "bin", "vstab_file")
+    assert os.path.exists(exe), "video-stabilization_b200/bin/vstab_file is built by make (__graft_entry__.build())"
+    return exe
+
+
+def test_file_front_end_usage_and_argument_errors(tmp_path):
+    """examples/vstab_file.cpp (the reference's --file main loop over include/stabilizer.hpp): usage errors and the
+    constructor's std::invalid_argument (src/stabilizer.cpp:40-49) surface as exit status 1 before any device is used."""
+    import subprocess
+    exe = _front_end()
+    assert subprocess.run([exe], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--file", "-", "--width", "0", "--height", "4"], capture_output=True).returncode == 1
+    clip = tmp_path / "c.bgr"
+    clip.write_bytes(bytes(64 * 48 * 3))
+    r = subprocess.run([exe, "--file", str(clip), "--width", "64", "--height", "48", "--working-height", "90",
+                        "--out", str(tmp_path / "o.bgr")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error" in r.stderr          # workingHeight <= 90 is rejected
+    r = subprocess.run([exe, "--file", str(clip), "--width", "64", "--height", "48", "--past-window", "0",
+                        "--future-window", "0", "--out", str(tmp_path / "o.bgr")], capture_output=True, text=True)
+    assert r.returncode == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side_by_side", [False, True])
+def test_file_front_end_equals_streaming_api(tmp_path, side_by_side):
+    """The C++ front end on a raw BGR24 clip writes exactly what the per-frame C ABI returns (mode switched to the
+    full lock at call 5); --side-by-side pairs every stabilized frame with the original delayed by `future` frames."""
+    import subprocess
+    import numpy as np
+    from conftest import render_clip
+    from oracle import synth
+    W, H, n, P, F, wh = 320, 240, 14, 4, 3, 120
+    frames = render_clip(synth.make_texture(512), W, H, n)
+    clip = tmp_path / "in.bgr"
+    clip.write_bytes(b"".join(f.tobytes() for f in frames))
+    out = tmp_path / "out.bgr"
+    cmd = [_front_end(), "--file", str(clip), "--width", str(W), "--height", str(H), "--out", str(out),
+           "--past-window", str(P), "--future-window", str(F), "--working-height", str(wh), "--mode", "lock", "--mode-at", "5"]
+    r = subprocess.run(cmd + (["--side-by-side"] if side_by_side else []), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    st = vs.Stabilizer(P, F, wh)
+    want = []
+    for i, f in enumerate(frames):
+        if i == 5:
+            st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
+        want.append(st.stabilize_frame(f))
+    st.close()
+    got = np.frombuffer(out.read_bytes(), np.uint8)
+    if not side_by_side:
+        got = got.reshape(n, H, W, 3)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), i
+    else:
+        got = got.reshape(n - F, H, 2 * W, 3)
+        for j in range(n - F):
+            assert np.array_equal(got[j][:, :W], frames[j]), j            # delayed original = presentation frame
+            assert np.array_equal(got[j][:, W:], want[j + F]), j
