@@ -1,5 +1,7 @@
-"""Streaming calls on synthetic 1080p frames (for ncu launch lists of the per-frame kernels)."""
-import os, sys
+"""Streaming calls on synthetic 1080p frames through pinned host buffers (the bench's e2e.streaming path): for ncu launch
+lists of the per-frame kernels and for VSTAB_TRACE=1 (host split + device marks of a call, printed at destroy)."""
+import ctypes as C
+import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-stabilization_b200", "python")]
@@ -8,16 +10,27 @@ import vstab_b200 as vs
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 W, H = 1920, 1080
-dev = torch.device("cuda:0")
 from oracle import synth as osynth, camera_engine_ref as ce
 tex = osynth.make_texture(2048)
 path = osynth.camera_path(8)
 host = [ce.render_frame(tex, path[i], W, H, osynth.focal_for_width(W)) for i in range(8)]
 host = host + host[-2:0:-1]          # ping-pong
+lib = vs.load_library()
+lib.vstab_host_alloc.restype = C.c_void_p
+nbytes = W * H * 3
+hin = lib.vstab_host_alloc(len(host) * nbytes)
+hout = lib.vstab_host_alloc(nbytes)
+np.ctypeslib.as_array((C.c_uint8 * (len(host) * nbytes)).from_address(hin)).reshape(len(host), H, W, 3)[:] = np.stack(host)
 st = vs.Stabilizer(60, 45, 360, device=0)
+t0 = 0.0
 for i in range(n):
     if i == 46:
         st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
-    out = st.stabilize_frame(host[i % len(host)])
+    if i == 50:
+        st.synchronize(); t0 = time.perf_counter()
+    st.stabilize_frame_ptr(hin + (i % len(host)) * nbytes, H, W, W * 3, hout, W * 3)
 st.synchronize()
-print("done", out.shape)
+if n > 50:
+    print("calls/s", (n - 50) / (time.perf_counter() - t0))
+st.close()
+print("done")

@@ -214,6 +214,9 @@ struct SiftPlan {
     unsigned int *rkeys = nullptr, *rkeys_sorted = nullptr;
     uint8_t* alive = nullptr;
     void* cub_temp = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};          // octaves >= 1 run beside the tail of the octave above them
+    cudaEvent_t ev_g3[kSiftMaxOctaves] = {};           // Gaussian[kLayers] of octave o is ready (the next octave's base)
+    cudaEvent_t ev_join[2] = {nullptr, nullptr};
     GraphCache graphs;
 };
 SiftPlan* sift_plan_create(int w, int h, double size_ratio, int max_keypoints, std::string* err);

@@ -744,6 +744,9 @@ SiftPlan* sift_plan_create(int w, int h, double size_ratio, int max_keypoints, s
 
 void sift_plan_destroy(SiftPlan* P) {
     if (!P) return;
+    for (auto& a : P->aux) if (a) cudaStreamDestroy(a);
+    for (auto& e : P->ev_g3) if (e) cudaEventDestroy(e);
+    for (auto& e : P->ev_join) if (e) cudaEventDestroy(e);
     if (P->mem) cudaFree(P->mem);
     delete (SiftOctaves*)P->octaves;
     delete P;
@@ -764,7 +767,7 @@ static void launch_sift_body(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_
     const int max_smem = (int)(sizeof(float) * ((GBY + 2 * kMaxRadius) * (GBX + 2 * kMaxRadius) + (GBY + 2 * kMaxRadius) * GBX));
     if (!attr) { cudaFuncSetAttribute(sift_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); attr = true; }
     const int* hr = P->radii;
-    auto blur = [&](const float* src, float* dst, int w, int h, int ki) {
+    auto blur = [&](const float* src, float* dst, int w, int h, int ki, cudaStream_t st) {
         const int R = hr[ki];
         switch (R) {                       // the radii of SIFT's sigmas; anything else takes the generic kernel
             case 3: launch_blur_t<3>(src, dst, w, h, ki, st); return;
@@ -785,24 +788,47 @@ static void launch_sift_body(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_
     float* g0 = P->pyr + O.off[0];
     float* scratch = g0 + (size_t)O.w[0] * O.h[0];
     sift_upsample_kernel<<<dim3((O.w[0] + 255) / 256, O.h[0]), 256, 0, st>>>(gray, P->w, P->h, scratch);
-    blur(scratch, g0, O.w[0], O.h[0], 0);
+    blur(scratch, g0, O.w[0], O.h[0], 0, st);
     const int threshold = (int)std::floor(0.5 * 0.04 / kLayers * 255.0);
+    // Octave o + 1 starts from Gaussian[kLayers] of octave o, so it does not have to wait for the last two blurs and the
+    // extrema pass of octave o: octaves >= 1 alternate between two auxiliary streams (fork / join by events; inside a
+    // graph capture these become parallel branches).  The small octaves are ~40 launches of a few CTAs each, about
+    // 0.5 ms of pure latency per 4K frame when they run behind octave 0 instead of beside it.
+    static const bool fork = !(getenv("VSTAB_SIFT_FORK") && atoi(getenv("VSTAB_SIFT_FORK")) == 0);
+    if (fork && !P->aux[0]) {
+        // highest priority: their few CTAs are dispatched ahead of the thousands queued by the octave-0 kernels
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        for (auto& a : P->aux) cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, prio_hi);
+        for (auto& e : P->ev_g3) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        for (auto& e : P->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    bool used[2] = {false, false};
     for (int o = 0; o < O.n; ++o) {
         const int w = O.w[o], h = O.h[o];
         const size_t plane = (size_t)w * h;
         float* g = P->pyr + O.off[o];
+        const int lane = (o - 1) & 1;
+        cudaStream_t q = (fork && o > 0) ? P->aux[lane] : st;
         if (o > 0) {
+            if (fork) { cudaStreamWaitEvent(q, P->ev_g3[o - 1], 0); used[lane] = true; }
             const float* src = P->pyr + O.off[o - 1] + (size_t)kLayers * O.w[o - 1] * O.h[o - 1];
-            sift_decimate_kernel<<<dim3((w + 255) / 256, h), 256, 0, st>>>(src, O.w[o - 1], g, w, h);
+            sift_decimate_kernel<<<dim3((w + 255) / 256, h), 256, 0, q>>>(src, O.w[o - 1], g, w, h);
             ++launches;
         }
-        for (int i = 1; i < kGauss; ++i) { blur(g + (size_t)(i - 1) * plane, g + (size_t)i * plane, w, h, i); ++launches; }
+        for (int i = 1; i < kGauss; ++i) {
+            blur(g + (size_t)(i - 1) * plane, g + (size_t)i * plane, w, h, i, q);
+            ++launches;
+            if (fork && i == kLayers && o + 1 < O.n) cudaEventRecord(P->ev_g3[o], q);
+        }
         if (w > 2 * kBorder && h > 2 * kBorder) {
-            sift_extrema_tile_kernel<<<dim3((w - 2 * kBorder + EXW - 1) / EXW, (h - 2 * kBorder + EXH - 1) / EXH), 256, 0, st>>>(
+            sift_extrema_tile_kernel<<<dim3((w - 2 * kBorder + EXW - 1) / EXW, (h - 2 * kBorder + EXH - 1) / EXH), 256, 0, q>>>(
                 P->pyr, O, o, threshold, P->cand, P->counters + 0, P->cand_cap);
             ++launches;
         }
     }
+    for (int k = 0; k < 2; ++k)
+        if (used[k]) { cudaEventRecord(P->ev_join[k], P->aux[k]); cudaStreamWaitEvent(st, P->ev_join[k], 0); }
     SiftKp* kps = (SiftKp*)P->kps;
     sift_refine_kernel<<<std::min((P->cand_cap + 3) / 4, 148 * 16), 128, 0, st>>>(P->pyr, O, P->cand, P->counters + 0, P->cand_cap, kps, P->counters + 1,
                                                              P->kp_cap);
