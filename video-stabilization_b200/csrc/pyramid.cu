@@ -2,6 +2,7 @@
 // (/root/reference/src/stabilizer.cpp:192-195, maxLevel 3): level l+1 = pyrDown(level l),
 // separable [1 4 6 4 1], BORDER_REFLECT_101, out = (sum + 128) >> 8 at even sites,
 // dst size ((w+1)/2, (h+1)/2).  Bit-exact.
+#include <cstdlib>
 #include "kernels.h"
 
 namespace vstabk {
@@ -38,54 +39,52 @@ PyrDesc make_pyr_desc(int w, int h) {
 namespace {
 
 constexpr int TX = 32, TY = 8;                 // dst tile
-constexpr int SW = 2 * TX + 3, SH = 2 * TY + 3; // src footprint 67 x 19
 
+// pyrDown without shared memory: a thread owns one destination column and 4 destination rows.  The 11 source rows it
+// needs are filtered horizontally straight from global memory -- interior lanes read the 5 taps as two aligned words
+// (funnel shift + one dp4a with the weights {1, 4, 6, 4} + the fifth tap), the lanes at the left / right image edge read
+// 5 reflected bytes; row indices are reflected per row (warp-uniform) -- then combined vertically in registers.
+// ~27 instructions per destination pixel (a shared-memory tile version with byte staging through reflect indices and two
+// barriers needed ~140: 0.18 -> 0.12 ms per 256 frames for the three levels); integer arithmetic as in the header comment.
+constexpr int DRY = 4;                           // destination rows per thread
 __global__ void __launch_bounds__(TX * TY)
 pyrdown_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ pyr_out, size_t frame_bytes,
-               size_t src_off, size_t dst_off, int sw, int sh, int dw, int dh) {
-    __shared__ uint8_t tile[SH][SW + 1];
-    __shared__ unsigned short hsum[SH][TX];
+                      size_t src_off, size_t dst_off, int sw, int sh, int dw, int dh) {
     const int frame = blockIdx.z;
     const uint8_t* src = pyr + (size_t)frame * frame_bytes + src_off;
     uint8_t* dst = pyr_out + (size_t)frame * frame_bytes + dst_off;
-    const int dx0 = blockIdx.x * TX, dy0 = blockIdx.y * TY;
-    const int sx0 = 2 * dx0 - 2, sy0 = 2 * dy0 - 2;
-    const int tid = threadIdx.y * TX + threadIdx.x;
-    {
-        // all loads of a thread in flight together
-        constexpr int kN = (SH * SW + TX * TY - 1) / (TX * TY);
-        uint8_t v[kN];
+    const int x = blockIdx.x * TX + threadIdx.x;
+    const int y0 = (blockIdx.y * TY + threadIdx.y) * DRY;
+    if (x >= dw || y0 >= dh) return;
+    const int sx = 2 * x - 2;
+    const bool word_ok = (sw & 3) == 0 && sx >= 0 && sx + 4 <= sw - 1;
+    const int a = sx & ~3;                                       // aligned start of the two words holding taps 0..4
+    const unsigned sh16 = (unsigned)(sx & 2) * 8u;               // taps start at byte 0 or 2 of the first word
+    const unsigned sel4 = (sx & 2) ? 0x4442u : 0x4440u;          // the fifth tap: byte 2 or byte 0 of the second word
+    int xo[5];
 #pragma unroll
-        for (int k = 0; k < kN; ++k) {
-            const int i = tid + k * TX * TY;
-            const int r = i / SW, c = i - r * SW;
-            // rows/cols beyond what the clipped tile needs are still valid reflect indices
-            int yy = sy0 + r, xx = sx0 + c;
-            yy = reflect101(min(max(yy, -(sh - 1)), 2 * sh - 2), sh);
-            xx = reflect101(min(max(xx, -(sw - 1)), 2 * sw - 2), sw);
-            if (i < SH * SW) v[k] = src[yy * sw + xx];
-        }
+    for (int k = 0; k < 5; ++k) xo[k] = reflect101(min(max(sx + k, -(sw - 1)), 2 * sw - 2), sw);
+    int hs[2 * DRY + 3];
 #pragma unroll
-        for (int k = 0; k < kN; ++k) {
-            const int i = tid + k * TX * TY;
-            const int r = i / SW, c = i - r * SW;
-            if (i < SH * SW) tile[r][c] = v[k];
+    for (int j = 0; j < 2 * DRY + 3; ++j) {
+        const int ry = reflect101(min(max(2 * y0 - 2 + j, -(sh - 1)), 2 * sh - 2), sh);
+        const uint8_t* row = src + (size_t)ry * sw;
+        if (word_ok) {
+            const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(row + a));
+            const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(row + a + 4));
+            hs[j] = (int)__dp4a(__funnelshift_r(w0, w1, sh16), 0x04060401u, __byte_perm(w1, 0u, sel4));
+        } else {
+            hs[j] = (int)__ldg(row + xo[0]) + 4 * (int)__ldg(row + xo[1]) + 6 * (int)__ldg(row + xo[2]) + 4 * (int)__ldg(row + xo[3]) +
+                    (int)__ldg(row + xo[4]);
         }
     }
-    __syncthreads();
-    // horizontal pass: SH rows x TX dst columns
-    for (int i = tid; i < SH * TX; i += TX * TY) {
-        const int r = i / TX, c = i - r * TX;
-        const uint8_t* t = &tile[r][2 * c];
-        hsum[r][c] = (unsigned short)(t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
-    }
-    __syncthreads();
-    const int x = dx0 + threadIdx.x, y = dy0 + threadIdx.y;
-    if (x < dw && y < dh) {
-        const int r = 2 * threadIdx.y;
-        const int c = threadIdx.x;
-        const int s = hsum[r][c] + 4 * hsum[r + 1][c] + 6 * hsum[r + 2][c] + 4 * hsum[r + 3][c] + hsum[r + 4][c];
-        dst[(size_t)y * dw + x] = (uint8_t)((s + 128) >> 8);
+#pragma unroll
+    for (int i = 0; i < DRY; ++i) {
+        const int y = y0 + i;
+        if (y < dh) {
+            const int s = hs[2 * i] + 4 * hs[2 * i + 1] + 6 * hs[2 * i + 2] + 4 * hs[2 * i + 3] + hs[2 * i + 4];
+            dst[(size_t)y * dw + x] = (uint8_t)((s + 128) >> 8);
+        }
     }
 }
 
@@ -214,7 +213,7 @@ lkprep_kernel(uint8_t* __restrict__ pyr, size_t frame_bytes, PrepLevels L) {
 void launch_pyramid(const PyrDesc& d, uint8_t* pyr, int nframes, cudaStream_t st) {
     if (nframes <= 0) return;
     for (int l = 0; l + 1 < kLkLevels; ++l) {
-        dim3 grid((d.w[l + 1] + TX - 1) / TX, (d.h[l + 1] + TY - 1) / TY, nframes);
+        dim3 grid((d.w[l + 1] + TX - 1) / TX, (d.h[l + 1] + TY * DRY - 1) / (TY * DRY), nframes);
         dim3 block(TX, TY);
         count_launch(1);
         pyrdown_kernel<<<grid, block, 0, st>>>(pyr, pyr, d.frame_bytes, d.off[l], d.off[l + 1],
