@@ -450,17 +450,6 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
     if (trace && !s->tev[0][0])
         for (auto& set : s->tev) for (auto& e : set) cudaEventCreate(&e);
 
-    // The upload goes first: upload -> estimation -> the NEXT call's output is the critical cycle of the stream
-    // (period = (enqueue-before-upload + upload + estimation + output chain) / 2), so nothing is enqueued ahead of it.
-    // The ring slot being overwritten held frame n-W; its readers (the warp and the channel sums of an earlier
-    // call's output chain) are ordered before this copy by the previous call's ev_out.
-    // Host input: the upload runs on its own stream, beside the estimation of the previous frame.
-    cudaStream_t up = in_kind == cudaMemcpyHostToDevice ? s->copy_stream : s->stream;
-    if (s->n > 0) CK(cudaStreamWaitEvent(up, s->ev_out, 0));
-    s->mark(0, up);
-    CK(cudaMemcpy2DAsync(slot, g.pitch, in, step, row_bytes, rows, in_kind, up));
-    s->mark(1, up);
-    CK(cudaEventRecord(s->ev_in, up));
     if (out_first) {
         CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));          // T[n-1], sums of frames <= n-1
         vstab_status st = stream_output(s, warp_dst, warp_pitch);
@@ -469,7 +458,16 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
             CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
     }
     if (trace) tr1 = now_us();
-    // estimation chain (its input copy was enqueued first, above)
+    // estimation chain.  The ring slot being overwritten held frame n-W; its readers (the warp and the
+    // channel sums of an earlier call's output chain) are ordered before this copy by ev_out.
+    // Host input: the upload runs on its own stream, beside the estimation of the previous frame.
+    // (Enqueuing the upload ahead of the output chain was measured: no gain for LK, -4 % for ORB lock.)
+    cudaStream_t up = in_kind == cudaMemcpyHostToDevice ? s->copy_stream : s->stream;
+    if (s->n > 0) CK(cudaStreamWaitEvent(up, s->ev_out, 0));
+    s->mark(0, up);
+    CK(cudaMemcpy2DAsync(slot, g.pitch, in, step, row_bytes, rows, in_kind, up));
+    s->mark(1, up);
+    CK(cudaEventRecord(s->ev_in, up));
     if (up != s->stream) CK(cudaStreamWaitEvent(s->stream, s->ev_in, 0));
     vstab_status st = stream_estimate(s);
     if (st != VSTAB_OK) return st;
