@@ -766,6 +766,8 @@ struct vstab_offline {
     DevBuf clip, outbuf, clipT, clipSums;
     size_t clip_frames = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t gftt_stream = nullptr;           // corner detection beside the pyramid build (VSTAB_OVERLAP=1)
+    cudaEvent_t ev_ingest = nullptr, ev_corners = nullptr;
     // ORB / SIFT registration (offline): reference set, per-launch scratch, gathered registrations
     OrbPlan* orb = nullptr;
     SiftPlan* sift = nullptr;
@@ -941,6 +943,9 @@ void vstab_offline_destroy(vstab_offline_t* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->stream) { cudaStreamSynchronize(o->stream); cudaStreamDestroy(o->stream); }
+    if (o->gftt_stream) { cudaStreamSynchronize(o->gftt_stream); cudaStreamDestroy(o->gftt_stream); }
+    if (o->ev_ingest) cudaEventDestroy(o->ev_ingest);
+    if (o->ev_corners) cudaEventDestroy(o->ev_corners);
     if (o->copy_in) { cudaStreamSynchronize(o->copy_in); cudaStreamDestroy(o->copy_in); }
     if (o->copy_out) { cudaStreamSynchronize(o->copy_out); cudaStreamDestroy(o->copy_out); }
     if (o->orb) orb_plan_destroy(o->orb);
@@ -991,18 +996,44 @@ extern "C" vstab_status vstab_offline_estimate(vstab_offline_t* o, const uint8_t
     o->timer.end(ST_INGEST, q);
     const int s0 = has_halo ? 0 : 1;              // first pyramid slot in use
     const int nslots = has_halo ? n + 1 : n;
-    o->timer.begin(ST_PYRAMID, q);
-    launch_pyramid(g.pd, pyr + (size_t)s0 * g.pd.frame_bytes, nslots, q);
-    o->timer.end(ST_PYRAMID, q);
     // corners of every "previous" frame of a pair: slots s0 .. n-1
     const int npairs = nslots - 1;
     float2* corners = o->corners.as<float2>() + (size_t)s0 * kMaxCorners;
     int* ccount = o->ccount.as<int>() + s0;
-    if (npairs > 0) {
-        o->timer.begin(ST_GFTT, q);
+    // Corner detection only needs the gray level 0 that ingest wrote, the tracker needs corners AND pyramid: with
+    // VSTAB_OVERLAP=1 the two run side by side on two streams (the top-k / greedy kernel is one latency-bound CTA per
+    // frame and leaves most issue slots to the pyramid kernels); stage times then are overlapping wall intervals.
+    static const bool overlap = getenv("VSTAB_OVERLAP") && atoi(getenv("VSTAB_OVERLAP")) != 0;
+    cudaStream_t qg = q;
+    if (overlap && npairs > 0) {
+        if (!o->gftt_stream) {
+            CK(cudaStreamCreateWithFlags(&o->gftt_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&o->ev_ingest, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&o->ev_corners, cudaEventDisableTiming));
+        }
+        qg = o->gftt_stream;
+        CK(cudaEventRecord(o->ev_ingest, q));
+        CK(cudaStreamWaitEvent(qg, o->ev_ingest, 0));
+    }
+    if (npairs > 0 && qg != q) {
+        o->timer.begin(ST_GFTT, qg);
         launch_gftt(pyr + (size_t)s0 * g.pd.frame_bytes, g.pd.frame_bytes, g.ww, g.wh, npairs, 0.01, g.min_distance,
-                    kMaxCorners, o->gws, corners, ccount, nullptr, q);
-        o->timer.end(ST_GFTT, q);
+                    kMaxCorners, o->gws, corners, ccount, nullptr, qg);
+        o->timer.end(ST_GFTT, qg);
+        CK(cudaEventRecord(o->ev_corners, qg));
+    }
+    o->timer.begin(ST_PYRAMID, q);
+    launch_pyramid(g.pd, pyr + (size_t)s0 * g.pd.frame_bytes, nslots, q);
+    o->timer.end(ST_PYRAMID, q);
+    if (npairs > 0) {
+        if (qg != q) {
+            CK(cudaStreamWaitEvent(q, o->ev_corners, 0));
+        } else {
+            o->timer.begin(ST_GFTT, q);
+            launch_gftt(pyr + (size_t)s0 * g.pd.frame_bytes, g.pd.frame_bytes, g.ww, g.wh, npairs, 0.01, g.min_distance,
+                        kMaxCorners, o->gws, corners, ccount, nullptr, q);
+            o->timer.end(ST_GFTT, q);
+        }
         o->timer.begin(ST_LK, q);
         launch_lk(pyr + (size_t)s0 * g.pd.frame_bytes, pyr + (size_t)(s0 + 1) * g.pd.frame_bytes, g.pd.frame_bytes,
                   g.pd.frame_bytes, g.pd, corners, ccount, npairs, o->lkpts.as<float2>(), o->lkstat.as<uint8_t>(), q);
