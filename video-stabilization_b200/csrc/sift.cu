@@ -34,23 +34,28 @@ __constant__ float c_gk[kGauss + 1][2 * kMaxRadius + 1];   // [0] = initial blur
 __constant__ int c_gr[kGauss + 1];
 
 // ---------------------------------------------------------------- base image: u8 -> float, 2x INTER_LINEAR
+// cv::resize(INTER_LINEAR) by exactly 2: output 2i takes source columns (i-1, i) with weights (.25, .75), output 2i+1 takes
+// (i, i+1) with (.75, .25), clamped at the borders; the same along y.  All products and sums of u8 values with these weights
+// are exact in fp32, so the order of evaluation does not matter.  One thread per SOURCE pixel: 9 bytes in, a 2 x 2 block out.
 __global__ void __launch_bounds__(256)
 sift_upsample_kernel(const uint8_t* __restrict__ gray, int w, int h, float* __restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= w) return;
+    const int il = max(i - 1, 0), ir = min(i + 1, w - 1);
+    const int jr[3] = {max(j - 1, 0), j, min(j + 1, h - 1)};
+    float hl[3], hr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint8_t* row = gray + (size_t)jr[r] * w;
+        const float a = (float)__ldg(row + il), b = (float)__ldg(row + i), c = (float)__ldg(row + ir);
+        hl[r] = a * 0.25f + b * 0.75f;
+        hr[r] = b * 0.75f + c * 0.25f;
+    }
     const int W = 2 * w;
-    if (x >= W) return;
-    float fx = (x + 0.5f) * 0.5f - 0.5f, fy = (y + 0.5f) * 0.5f - 0.5f;
-    int sx = (int)floorf(fx), sy = (int)floorf(fy);
-    fx -= sx; fy -= sy;
-    if (sx < 0) { sx = 0; fx = 0.f; }
-    if (sx >= w - 1) { sx = w - 1; fx = 0.f; }
-    if (sy < 0) { sy = 0; fy = 0.f; }
-    if (sy >= h - 1) { sy = h - 1; fy = 0.f; }
-    const int sx1 = min(sx + 1, w - 1), sy1 = min(sy + 1, h - 1);
-    const float a = gray[(size_t)sy * w + sx], b = gray[(size_t)sy * w + sx1];
-    const float c = gray[(size_t)sy1 * w + sx], d = gray[(size_t)sy1 * w + sx1];
-    const float top = a * (1.f - fx) + b * fx, bot = c * (1.f - fx) + d * fx;
-    out[(size_t)y * W + x] = top * (1.f - fy) + bot * fy;
+    float2* o0 = reinterpret_cast<float2*>(out + (size_t)(2 * j) * W + 2 * i);
+    float2* o1 = reinterpret_cast<float2*>(out + (size_t)(2 * j + 1) * W + 2 * i);
+    *o0 = make_float2(hl[0] * 0.25f + hl[1] * 0.75f, hr[0] * 0.25f + hr[1] * 0.75f);
+    *o1 = make_float2(hl[1] * 0.75f + hl[2] * 0.25f, hr[1] * 0.75f + hr[2] * 0.25f);
 }
 
 // ---------------------------------------------------------------- separable Gaussian blur (float), REFLECT_101
@@ -238,31 +243,45 @@ constexpr int EXW = 64, EXH = 16;
 __global__ void __launch_bounds__(256)
 sift_extrema_tile_kernel(const float* __restrict__ pyr, SiftOctaves O, int o, int threshold,
                          unsigned long long* __restrict__ cand, int* __restrict__ ncand, int cap) {
-    constexpr int TW = EXW + 2, TH = EXH + 2, NE = (TW * TH + 255) / 256;
-    __shared__ float D[kGauss - 1][TH][TW];
+    // tile rows start at x0 - 1 = kBorder - 1 + 64 bx, a multiple of 4 floats: staged as float4 (17 per row, row stride 68)
+    constexpr int TH = EXH + 2, TWV = (EXW + 2 + 3) / 4, TWP = 4 * TWV, NE = (TWV * TH + 255) / 256;
+    static_assert((kBorder - 1) % 4 == 0, "tile rows must start on a 16-byte boundary");
+    __shared__ __align__(16) float D[kGauss - 1][TH][TWP];
     const int w = O.w[o], h = O.h[o];
     const size_t plane = (size_t)w * h;
     const float* g = pyr + O.off[o];
     const int x0 = kBorder + blockIdx.x * EXW, y0 = kBorder + blockIdx.y * EXH;
     const int tid = threadIdx.x;
     {
-        float prev[NE];
+        const bool vec_ok = (w & 3) == 0;
+        float4 prev[NE];
 #pragma unroll
         for (int l = 0; l < kGauss; ++l) {
-            float cur[NE];
+            float4 cur[NE];
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 const int i = tid + e * 256;
-                const int r = i / TW, c = i - r * TW;
-                const int yy = min(y0 - 1 + r, h - 1), xx = min(x0 - 1 + c, w - 1);
-                cur[e] = i < TW * TH ? __ldg(g + (size_t)l * plane + (size_t)yy * w + xx) : 0.f;
+                const int r = i / TWV, c4 = i - r * TWV;
+                cur[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < TWV * TH) {
+                    const int yy = min(y0 - 1 + r, h - 1), xb = x0 - 1 + 4 * c4;
+                    const float* rowp = g + (size_t)l * plane + (size_t)yy * w;
+                    if (vec_ok && xb + 3 <= w - 1) {
+                        cur[e] = __ldg(reinterpret_cast<const float4*>(rowp + xb));
+                    } else {
+                        cur[e].x = __ldg(rowp + min(xb, w - 1)); cur[e].y = __ldg(rowp + min(xb + 1, w - 1));
+                        cur[e].z = __ldg(rowp + min(xb + 2, w - 1)); cur[e].w = __ldg(rowp + min(xb + 3, w - 1));
+                    }
+                }
             }
             if (l > 0) {
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     const int i = tid + e * 256;
-                    const int r = i / TW, c = i - r * TW;
-                    if (i < TW * TH) D[l - 1][r][c] = cur[e] - prev[e];
+                    const int r = i / TWV, c4 = i - r * TWV;
+                    if (i < TWV * TH)
+                        *reinterpret_cast<float4*>(&D[l - 1][r][4 * c4]) =
+                            make_float4(cur[e].x - prev[e].x, cur[e].y - prev[e].y, cur[e].z - prev[e].z, cur[e].w - prev[e].w);
                 }
             }
 #pragma unroll
@@ -787,7 +806,7 @@ static void launch_sift_body(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_
     // base image: upsample into the Gaussian-1 slot of octave 0 (scratch), blur into Gaussian 0
     float* g0 = P->pyr + O.off[0];
     float* scratch = g0 + (size_t)O.w[0] * O.h[0];
-    sift_upsample_kernel<<<dim3((O.w[0] + 255) / 256, O.h[0]), 256, 0, st>>>(gray, P->w, P->h, scratch);
+    sift_upsample_kernel<<<dim3((P->w + 255) / 256, P->h), 256, 0, st>>>(gray, P->w, P->h, scratch);
     blur(scratch, g0, O.w[0], O.h[0], 0, st);
     const int threshold = (int)std::floor(0.5 * 0.04 / kLayers * 255.0);
     // Octave o + 1 starts from Gaussian[kLayers] of octave o, so it does not have to wait for the last two blurs and the
