@@ -302,17 +302,28 @@ sift_extrema_tile_kernel(const float* __restrict__ pyr, SiftOctaves O, int o, in
             if (x < w - kBorder && y < h - kBorder) {
                 const float val = D[layer][r][c];
                 if (fabsf(val) > (float)threshold) {
+                    // own layer first: few samples are 2-D extrema, the two neighbouring layers are only read for those
                     bool mx = val > 0.f, mn = val < 0.f;
 #pragma unroll
-                    for (int dl = -1; dl <= 1; ++dl)
+                    for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const float v = D[layer][r + dy][c + dx];
+                            mx = mx && val >= v;
+                            mn = mn && val <= v;
+                        }
+                    if (mx || mn) {
 #pragma unroll
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const float v = D[layer + dl][r + dy][c + dx];
-                                mx = mx && val >= v;
-                                mn = mn && val <= v;
-                            }
+                        for (int dl = -1; dl <= 1; dl += 2)
+#pragma unroll
+                            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                                for (int dx = -1; dx <= 1; ++dx) {
+                                    const float v = D[layer + dl][r + dy][c + dx];
+                                    mx = mx && val >= v;
+                                    mn = mn && val <= v;
+                                }
+                    }
                     is_ext = mx || mn;
                 }
             }
