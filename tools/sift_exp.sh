@@ -1,7 +1,7 @@
 #!/bin/bash
 # SIFT / ORB streaming figures + the SIFT parity tests (GPU box)
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests/test_gpu_orb.py tests/test_gpu_pipeline.py tests/test_gpu_offline.py -q -m gpu -x -k "sift or feature_lock" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_orb.py tests/test_gpu_pipeline.py tests/test_gpu_offline.py -q -m gpu -x -k "sift or feature_lock or featprep or orb" 2>&1 | tail -3
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --frames-per-gpu 128 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:

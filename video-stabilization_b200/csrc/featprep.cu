@@ -16,10 +16,14 @@
 namespace vstabk {
 namespace {
 
-constexpr int MTX = 32, MTY = 8;
+constexpr int MTX = 32, MTY = 8, MPX = 4;     // threads x, threads y, pixels per thread along x
+constexpr int MTW = MTX * MPX;                 // 128-pixel tile rows
+constexpr int MSW = MTW + 8;                   // staged row: columns x0-4 .. x0+MTW+3 (word-aligned start), 34 words
 
-VSTAB_D int median25(int* v) {
-#define CS(a, b) { const int lo_ = min(v[a], v[b]); v[b] = max(v[a], v[b]); v[a] = lo_; }
+// 25-element median selection network on TWO pixels at once: every register holds the same window position of two
+// horizontally adjacent pixels as u16x2, and a comparator is one VIMNMX.U16x2 pair.
+VSTAB_D unsigned median25x2(unsigned* v) {
+#define CS(a, b) { const unsigned lo_ = __vminu2(v[a], v[b]); v[b] = __vmaxu2(v[a], v[b]); v[a] = lo_; }
 #include "median25.inc"
 #undef CS
     return v[12];
@@ -34,26 +38,55 @@ nn_gray_kernel(const uint8_t* __restrict__ frame, size_t pitch, const int* __res
     out[(size_t)y * w + x] = (uint8_t)luma_q15(p[0], p[1], p[2]);
 }
 
-// 5x5 median, BORDER_REPLICATE
+// 5x5 median, BORDER_REPLICATE.  A CTA stages a (8+4) x (128+8) tile as words (aligned loads where the word lies inside
+// the row, clamped bytes at the image edges); a thread produces 4 pixels of a row as two u16x2 pairs: per source row three
+// words + two funnel shifts give the 8 bytes its windows span, five PRMT per pair spread them into u16x2 lanes.
 __global__ void __launch_bounds__(MTX * MTY)
 median5_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int w, int h) {
-    __shared__ uint8_t t[MTY + 4][MTX + 4];
-    const int x0 = blockIdx.x * MTX, y0 = blockIdx.y * MTY;
+    __shared__ __align__(16) unsigned t[MTY + 4][MSW / 4];
+    const int x0 = blockIdx.x * MTW, y0 = blockIdx.y * MTY;
     const int tid = threadIdx.y * MTX + threadIdx.x;
-    for (int i = tid; i < (MTY + 4) * (MTX + 4); i += MTX * MTY) {
-        const int r = i / (MTX + 4), c = i - r * (MTX + 4);
-        const int yy = min(max(y0 + r - 2, 0), h - 1), xx = min(max(x0 + c - 2, 0), w - 1);
-        t[r][c] = in[(size_t)yy * w + xx];
+    const bool words_ok = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) & 3) == 0);
+    for (int i = tid; i < (MTY + 4) * (MSW / 4); i += MTX * MTY) {
+        const int r = i / (MSW / 4), c = i - r * (MSW / 4);
+        const int yy = min(max(y0 + r - 2, 0), h - 1), xb = x0 - 4 + 4 * c;
+        const uint8_t* row = in + (size_t)yy * w;
+        unsigned v;
+        if (words_ok && xb >= 0 && xb + 3 <= w - 1) {
+            v = __ldg(reinterpret_cast<const unsigned*>(row + xb));
+        } else {
+            v = (unsigned)row[min(max(xb, 0), w - 1)] | ((unsigned)row[min(max(xb + 1, 0), w - 1)] << 8) |
+                ((unsigned)row[min(max(xb + 2, 0), w - 1)] << 16) | ((unsigned)row[min(max(xb + 3, 0), w - 1)] << 24);
+        }
+        t[r][c] = v;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int x = x0 + threadIdx.x * MPX, y = y0 + threadIdx.y;
     if (x >= w || y >= h) return;
-    int v[25];
+    // the windows of pixels x .. x+3 span columns x-2 .. x+5 = staged bytes 4 tx + 2 .. 4 tx + 9
+    unsigned va[25], vb[25];
 #pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) v[dy * 5 + dx] = t[threadIdx.y + dy][threadIdx.x + dx];
-    out[(size_t)y * w + x] = (uint8_t)median25(v);
+    for (int dy = 0; dy < 5; ++dy) {
+        const unsigned* rp = &t[threadIdx.y + dy][threadIdx.x];
+        const unsigned q0 = rp[0], q1 = rp[1], q2 = rp[2];
+        const unsigned w0 = __funnelshift_r(q0, q1, 16), w1 = __funnelshift_r(q1, q2, 16);   // bytes 0..3, 4..7 of the span
+        const unsigned wm = __funnelshift_r(w0, w1, 16);                                        // bytes 2..5
+        // pair A = pixels (x, x+1): window position dx holds span bytes (dx, dx+1); pair B = (x+2, x+3): bytes (dx+2, dx+3)
+        va[dy * 5 + 0] = __byte_perm(w0, 0u, 0x4140); va[dy * 5 + 1] = __byte_perm(w0, 0u, 0x4241);
+        va[dy * 5 + 2] = __byte_perm(w0, 0u, 0x4342); va[dy * 5 + 3] = __byte_perm(wm, 0u, 0x4241);
+        va[dy * 5 + 4] = __byte_perm(w1, 0u, 0x4140);
+        vb[dy * 5 + 0] = __byte_perm(w0, 0u, 0x4342); vb[dy * 5 + 1] = __byte_perm(wm, 0u, 0x4241);
+        vb[dy * 5 + 2] = __byte_perm(w1, 0u, 0x4140); vb[dy * 5 + 3] = __byte_perm(w1, 0u, 0x4241);
+        vb[dy * 5 + 4] = __byte_perm(w1, 0u, 0x4342);
+    }
+    const unsigned ma = median25x2(va), mb = median25x2(vb);
+    const unsigned res = __byte_perm(ma, mb, 0x6420);          // {A.lo, A.hi, B.lo, B.hi} low bytes
+    uint8_t* o = out + (size_t)y * w + x;
+    if (x + 3 < w && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+        *reinterpret_cast<unsigned*>(o) = res;
+    } else {
+        for (int k = 0; k < 4 && x + k < w; ++k) o[k] = (uint8_t)(res >> (8 * k));
+    }
 }
 
 // sharpen at (x, y) of the median image `m` (BORDER_REFLECT_101), saturated to u8
@@ -189,7 +222,7 @@ void launch_featprep(const uint8_t* frame, size_t pitch, const int* xofs, const 
     if (clip < 1) clip = 1;
     count_launch(6);
     nn_gray_kernel<<<dim3((w + 255) / 256, h), 256, 0, st>>>(frame, pitch, xofs, yofs, w, h, a);
-    dim3 mg((w + MTX - 1) / MTX, (h + MTY - 1) / MTY), mb(MTX, MTY);
+    dim3 mg((w + MTW - 1) / MTW, (h + MTY - 1) / MTY), mb(MTX, MTY);
     median5_kernel<<<mg, mb, 0, st>>>(a, b, w, h);
     cudaMemsetAsync(hist, 0, 64 * 256 * 4, st);
     clahe_hist_kernel<<<dim3(64, 8), 256, 0, st>>>(b, w, h, tw, th, tiles, hist);
