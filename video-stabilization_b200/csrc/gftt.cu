@@ -13,6 +13,7 @@
 //           memory, one warp per frame, 32 candidates per step with ballot/shuffle conflict
 //           resolution -- the accepted set and its order equal the sequential OpenCV loop.
 #include <cstdlib>
+#include <type_traits>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include "kernels.h"
@@ -99,75 +100,97 @@ eig_kernel(const uint8_t* __restrict__ gray, size_t gray_stride, int w, int h, i
     __shared__ unsigned long long queue_all[kEigWarps][64];
     unsigned long long* queue = queue_all[threadIdx.x >> 5];
     int qn = 0;
-    bool done = false;
-    for (int yp0 = p_lo; !done; yp0 += 3) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int yp = yp0 + j;
-            if (yp > p_hi + 1 || (yp > p_hi && p_hi != h - 1)) { done = true; break; }
-            const int jA = (j + 1) % 3, jB = (j + 2) % 3;           // slots of rows yp-2, yp-1
-            if (yp <= p_hi) {
-                row_terms(ra, rb, rc, S[jB], R[jB]);                 // gray row yp+1
-                load_raw(reflect101(yp + 2, h), ra, rb, rc);         // (h + 1 at most: still a valid reflection)
-                // every row of the strip starts a new 128-byte line: ask for the line `pf` rows further down now
-                if (pf > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (min(yp + 2 + pf, h - 1) * w + xr)));
-                // Dx = fma(S[y-1] + S[y+1], k1, S[y]*k0),  Dy = R[y+1] - R[y-1]
-                const float dx = __fmaf_rn(__fadd_rn(S[j], S[jB]), k1, __fmul_rn(S[jA], k0));
-                const float dy = __fsub_rn(R[jB], R[j]);
-                const double pxx = (double)__fmul_rn(dx, dx), pxy = (double)__fmul_rn(dx, dy), pyy = (double)__fmul_rn(dy, dy);
-                RS[j].xx = __dadd_rn(__dadd_rn(pxx, __shfl_down_sync(0xffffffffu, pxx, 1)), __shfl_down_sync(0xffffffffu, pxx, 2));
-                RS[j].xy = __dadd_rn(__dadd_rn(pxy, __shfl_down_sync(0xffffffffu, pxy, 1)), __shfl_down_sync(0xffffffffu, pxy, 2));
-                RS[j].yy = __dadd_rn(__dadd_rn(pyy, __shfl_down_sync(0xffffffffu, pyy, 1)), __shfl_down_sync(0xffffffffu, pyy, 2));
-            } else {
-                RS[j] = RS[jA];                                     // below the last image row: product row h == row h-2
+    // One row of the stream.  kSteady: a row away from every boundary of the segment and of the image -- all the range tests
+    // below are known true at compile time, the next gray row needs no reflection -- which is every row but the first and last
+    // few of a segment; the generic instance keeps the tests.  j: the compile-time slot of product row yp.
+    auto step = [&](auto steady_c, auto j_c, const int yp) {
+        constexpr bool kSteady = decltype(steady_c)::value;
+        constexpr int j = decltype(j_c)::value, jA = (j + 1) % 3, jB = (j + 2) % 3;   // slots of rows yp, yp-2, yp-1
+        if (kSteady || yp <= p_hi) {
+            row_terms(ra, rb, rc, S[jB], R[jB]);                 // gray row yp+1
+            load_raw(kSteady ? yp + 2 : reflect101(yp + 2, h), ra, rb, rc);   // (h + 1 at most: still a valid reflection)
+            // every row of the strip starts a new 128-byte line: ask for the line `pf` rows further down now
+            if (pf > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (min(yp + 2 + pf, h - 1) * w + xr)));
+            // Dx = fma(S[y-1] + S[y+1], k1, S[y]*k0),  Dy = R[y+1] - R[y-1]
+            const float dx = __fmaf_rn(__fadd_rn(S[j], S[jB]), k1, __fmul_rn(S[jA], k0));
+            const float dy = __fsub_rn(R[jB], R[j]);
+            const double pxx = (double)__fmul_rn(dx, dx), pxy = (double)__fmul_rn(dx, dy), pyy = (double)__fmul_rn(dy, dy);
+            RS[j].xx = __dadd_rn(__dadd_rn(pxx, __shfl_down_sync(0xffffffffu, pxx, 1)), __shfl_down_sync(0xffffffffu, pxx, 2));
+            RS[j].xy = __dadd_rn(__dadd_rn(pxy, __shfl_down_sync(0xffffffffu, pxy, 1)), __shfl_down_sync(0xffffffffu, pxy, 2));
+            RS[j].yy = __dadd_rn(__dadd_rn(pyy, __shfl_down_sync(0xffffffffu, pyy, 1)), __shfl_down_sync(0xffffffffu, pyy, 2));
+        } else {
+            RS[j] = RS[jA];                                     // below the last image row: product row h == row h-2
+        }
+        const int ye = yp - 1;
+        if (kSteady || (ye >= ye_lo && ye <= ye_hi)) {
+            const D3 U = (!kSteady && ye == 0) ? RS[j] : RS[jA];   // above the first image row: product row -1 == row 1
+            const double sxx = __dadd_rn(__dadd_rn(U.xx, RS[jB].xx), RS[j].xx);
+            const double sxy = __dadd_rn(__dadd_rn(U.xy, RS[jB].xy), RS[j].xy);
+            const double syy = __dadd_rn(__dadd_rn(U.yy, RS[jB].yy), RS[j].yy);
+            const float a = __fmul_rn((float)sxx, 0.5f);
+            const float b = (float)sxy;
+            const float cc = __fmul_rn((float)syy, 0.5f);
+            const float d = __fsub_rn(a, cc);
+            const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b)));
+            const float e = e_valid ? __fsub_rn(__fadd_rn(a, cc), rad) : 0.f;
+            if (own_col && (kSteady || (ye >= ya && ye < yb))) {
+                vmax = fmaxf(vmax, e);
+                if (eig_out) eig_out[(size_t)frame * w * h + (size_t)ye * w + xe] = e;
             }
-            const int ye = yp - 1;
-            if (ye >= ye_lo && ye <= ye_hi) {
-                const D3 U = ye == 0 ? RS[j] : RS[jA];              // above the first image row: product row -1 == row 1
-                const double sxx = __dadd_rn(__dadd_rn(U.xx, RS[jB].xx), RS[j].xx);
-                const double sxy = __dadd_rn(__dadd_rn(U.xy, RS[jB].xy), RS[j].xy);
-                const double syy = __dadd_rn(__dadd_rn(U.yy, RS[jB].yy), RS[j].yy);
-                const float a = __fmul_rn((float)sxx, 0.5f);
-                const float b = (float)sxy;
-                const float cc = __fmul_rn((float)syy, 0.5f);
-                const float d = __fsub_rn(a, cc);
-                const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b)));
-                const float e = e_valid ? __fsub_rn(__fadd_rn(a, cc), rad) : 0.f;
-                if (own_col && ye >= ya && ye < yb) {
-                    vmax = fmaxf(vmax, e);
-                    if (eig_out) eig_out[(size_t)frame * w * h + (size_t)ye * w + xe] = e;
-                }
-                const float hm = fmaxf(__shfl_up_sync(0xffffffffu, e, 1), __shfl_down_sync(0xffffffffu, e, 1));
-                E[j] = e; HM[j] = hm; H3[j] = fmaxf(hm, e);
-                // 3x3 local maxima of row yc = ye - 1 (ties kept, like eig == dilate(eig)) inside the 1-px image border
-                const int yc = ye - 1;
-                if (yc >= yc_lo && yc < yc_hi) {
-                    const float v = E[jB];
-                    // conservative early cut: the running maximum only grows, so anything at or below
-                    // 0.01 * (maximum seen so far) is certainly below the final threshold
-                    const bool is_cand = cand_col && v > cut && v >= HM[jB] && v >= H3[jA] && v >= H3[j];
-                    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-                    if (ball) {
-                        // append to this warp's queue; 32 keys leave with one atomic and one coalesced 256-byte store
-                        if (is_cand)
-                            queue[qn + __popc(ball & ((1u << lane) - 1u))] =
-                                ((unsigned long long)__float_as_uint(v) << idx_bits) | (unsigned long long)(unsigned)(yc * w + xe);
-                        qn += __popc(ball);
+            const float hm = fmaxf(__shfl_up_sync(0xffffffffu, e, 1), __shfl_down_sync(0xffffffffu, e, 1));
+            E[j] = e; HM[j] = hm; H3[j] = fmaxf(hm, e);
+            // 3x3 local maxima of row yc = ye - 1 (ties kept, like eig == dilate(eig)) inside the 1-px image border
+            const int yc = ye - 1;
+            if (kSteady || (yc >= yc_lo && yc < yc_hi)) {
+                const float v = E[jB];
+                // conservative early cut: the running maximum only grows, so anything at or below
+                // 0.01 * (maximum seen so far) is certainly below the final threshold
+                const bool is_cand = cand_col && v > cut && v >= HM[jB] && v >= H3[jA] && v >= H3[j];
+                const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+                if (ball) {
+                    // append to this warp's queue; 32 keys leave with one atomic and one coalesced 256-byte store
+                    if (is_cand)
+                        queue[qn + __popc(ball & ((1u << lane) - 1u))] =
+                            ((unsigned long long)__float_as_uint(v) << idx_bits) | (unsigned long long)(unsigned)(yc * w + xe);
+                    qn += __popc(ball);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        int pos0 = 0;
+                        if (lane == 0) pos0 = atomicAdd(seg_end + frame, 32);
+                        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                        const unsigned long long k0 = queue[lane], k1 = queue[32 + lane];
+                        if (pos0 + lane < (frame + 1) * cap) keys[pos0 + lane] = k0;
                         __syncwarp();
-                        if (qn >= 32) {
-                            int pos0 = 0;
-                            if (lane == 0) pos0 = atomicAdd(seg_end + frame, 32);
-                            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                            const unsigned long long k0 = queue[lane], k1 = queue[32 + lane];
-                            if (pos0 + lane < (frame + 1) * cap) keys[pos0 + lane] = k0;
-                            __syncwarp();
-                            queue[lane] = k1;
-                            qn -= 32;
-                            __syncwarp();
-                        }
+                        queue[lane] = k1;
+                        qn -= 32;
+                        __syncwarp();
                     }
                 }
             }
+        }
+    };
+    // generic row with the end-of-segment test; returns true when the segment is finished
+    auto edge = [&](auto j_c, const int yp) -> bool {
+        if (yp > p_hi + 1 || (yp > p_hi && p_hi != h - 1)) return true;
+        step(std::false_type{}, j_c, yp);
+        return false;
+    };
+    const std::integral_constant<int, 0> J0{};
+    const std::integral_constant<int, 1> J1{};
+    const std::integral_constant<int, 2> J2{};
+    // steady rows: yp <= p_hi, yp + 2 <= h - 1, ye = yp - 1 in [max(ye_lo, 1), ye_hi] and in [ya, yb), yc = yp - 2 in [yc_lo, yc_hi)
+    const int ys_lo = max(max(ye_lo + 1, 2), max(ya + 1, yc_lo + 2));
+    const int ys_hi = min(min(p_hi, h - 3), min(min(ye_hi + 1, yb), yc_hi + 1));
+    bool done = false;
+    for (int yp0 = p_lo; !done; yp0 += 3) {
+        if (yp0 >= ys_lo && yp0 + 2 <= ys_hi) {
+            step(std::true_type{}, J0, yp0);
+            step(std::true_type{}, J1, yp0 + 1);
+            step(std::true_type{}, J2, yp0 + 2);
+        } else {
+            done = edge(J0, yp0);
+            if (!done) done = edge(J1, yp0 + 1);
+            if (!done) done = edge(J2, yp0 + 2);
         }
         // publish the running maximum every 12 rows (and at the end), and refresh the early cut from the frame's
         // maximum so far
