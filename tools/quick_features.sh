@@ -1,5 +1,5 @@
 #!/bin/bash
-# SIFT / ORB streaming figures + the SIFT parity tests (GPU box)
+# Quick check on the GPU box: ORB / SIFT parity tests and the streaming frames/s of BASELINE configs 3 and 4.
 cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests/test_gpu_orb.py tests/test_gpu_pipeline.py tests/test_gpu_offline.py -q -m gpu -x -k "sift or feature_lock or featprep or orb" 2>&1 | tail -3
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --frames-per-gpu 128 2>/dev/null | python -c "
