@@ -32,7 +32,7 @@ constexpr int kGreedySmemMax = 200 * 1024;
 // order of OpenCV's row/column sums), the eigenvalue row from those, and the 3x3 local-maximum test from the last
 // three eigenvalue rows (horizontal neighbours by shuffle).  Each gray row is read once per strip (+4 halo
 // columns, +4 halo rows per segment); every f32 product is converted to f64 once.
-constexpr int kStripW = 28, kSegH = 60, kEigWarps = 4;
+constexpr int kStripW = 28, kSegH = 90, kEigWarps = 4;   // (segment height 45 / 60 / 90 / 120 / 180: 0.663 / 0.655 / 0.646 / 0.658 / 0.670 ms)
 
 struct D3 { double xx, xy, yy; };
 
@@ -571,7 +571,9 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     {
         // rows per warp: long segments amortise the 4 halo rows; a few frames alone (streaming) want more, shorter
         // warps instead (latency)
-        const int seg_h = nframes >= 8 ? kSegH : kSegH / 4;
+        static int seg_env = -1;
+        if (seg_env < 0) { const char* e = getenv("VSTAB_EIG_SEGH"); seg_env = e ? atoi(e) : 0; }
+        const int seg_h = seg_env > 0 ? seg_env : (nframes >= 8 ? kSegH : 15);
         const int nstrips = (w + kStripW - 1) / kStripW, nsegs = (h + seg_h - 1) / seg_h;
         dim3 grid((nstrips * nsegs + kEigWarps - 1) / kEigWarps, nframes);
         count_launch(1);
