@@ -370,6 +370,7 @@ def run_ours(args):
     if world == 1 and rank == 0 and not args.no_mode_probes:
         modes = run_mode_probes(args, torch, vs, lib, local)
         modes_offline = run_4k_probe(args, torch, vs, local, peak)
+        modes_offline.update(run_feature_offline_probes(args, torch, vs, local))
 
     if rank == 0:
         line = {
@@ -558,6 +559,54 @@ def run_4k_probe(args, torch, vs, local, peak):
         "hbm_bound_stages": {
             "ingest": {"achieved": (B + 640 * 360) * n / (ingest_ms * 1e-3) / 1e9, "frac": (B + 640 * 360) * n / (ingest_ms * 1e-3) / 1e9 / peak},
             "warp": {"achieved": 2 * B * n / (warp_ms * 1e-3) / 1e9, "frac": 2 * B * n / (warp_ms * 1e-3) / 1e9 / peak}}}}
+
+
+def run_feature_offline_probes(args, torch, vs, local):
+    """Secondary figures: a complete offline pass in the ORB / SIFT lock modes (BASELINE configs 3 and 4) with the frames resident
+    in HBM -- LK-path estimation of the window transforms, per-frame registration against the reference set (conditioning,
+    detect + describe, match, RANSAC fit; frames dealt round-robin to registration lanes), carry scan + warp."""
+    from vstab_b200 import offline, synth
+    out = {}
+    dev = f"cuda:{local}"
+    tex = torch.from_numpy(synth.make_texture(2048)).to(dev)
+    for name, w, h, wh, mode, n in (("c3_orb_full_lock_1080p_wh1080", 1920, 1080, 1080, vs.ORB_FULL_LOCK, 64),
+                                    ("c4_sift_full_lock_4k_wh2160", 3840, 2160, 2160, vs.SIFT_FULL_LOCK, 16)):
+        frames = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        path = synth.camera_path(n, drift=PATH_DRIFT)
+        for s0 in range(0, n, 16):
+            offline.render_frames(tex, path[s0:s0 + 16], h, w, synth.focal_for_width(w), frames[s0:s0 + 16], device=local)
+        res = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        T = torch.zeros((n, 9), dtype=torch.float64, device=dev)
+        sums = torch.zeros((n, 3), dtype=torch.int64, device=dev)
+        reg = torch.zeros((n, 10), dtype=torch.float64, device=dev)
+        off = offline.OfflineStabilizer(PAST, FUTURE, wh, h, w, n, device=local)
+        lock_call = FUTURE + 1                       # anchor = frame 1
+        off.capture_reference(frames[lock_call - FUTURE], mode)
+
+        def step():
+            off.estimate(frames, 0, None, T, sums)
+            off.register(frames, reg)
+            off.set_registrations(reg)
+            off.prepare(T, mode, lock_call)
+            off.render(frames, 0, 0, n, T, mode, lock_call, sums, res)
+
+        for _ in range(3):                           # the third pass replays the front ends as CUDA graphs
+            step()
+        torch.cuda.synchronize()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(off.stream)
+        for _ in range(reps):
+            step()
+        e1.record(off.stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        valid = int(reg[:, 9].sum().item())
+        off.close()
+        del frames, res
+        out[name] = {"value": n / (ms * 1e-3), "unit": UNIT, "frames": n, "ms_per_step": ms, "registrations_valid": valid,
+                     "api": "vstab_offline_estimate / _register / _prepare / _render (frames resident in HBM)"}
+    return out
 
 
 def main():

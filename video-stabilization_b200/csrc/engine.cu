@@ -779,6 +779,17 @@ struct vstab_offline {
         m_status, lock_fit;
     const double* reg_all = nullptr;
     long reg_n = 0;
+    // extra registration lanes: frames of a shard are independent units, so vstab_offline_register deals them round-robin
+    // to lanes with their own stream, plan and scratch (lane 0 = the members above on `stream`)
+    struct RegLane {
+        cudaStream_t q = nullptr;
+        cudaEvent_t done = nullptr;
+        OrbPlan* orb = nullptr;
+        SiftPlan* sift = nullptr;
+        DevBuf feat_ws, feat_gray, cur_kps, cur_desc, f_counts, m_idx, m_d0, m_d1, m_good, m_ref, m_cur, m_status, lock_fit;
+    };
+    std::vector<RegLane*> lanes;
+    cudaEvent_t ev_reg_fork = nullptr;
     std::string err;
     void set_err(const std::string& e) { err = e; }
 };
@@ -875,26 +886,72 @@ vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames,
     const int* nref = (const int*)pack;
     const OrbKeypoint* ref_kps = (const OrbKeypoint*)(pack + kRefPackKps);
     const uint8_t* ref_desc = (const uint8_t*)(pack + kRefPackDesc);
-    int* counts = o->f_counts.as<int>();
-    double* Tfit = o->lock_fit.as<double>();
-    int* fitc = reinterpret_cast<int*>(Tfit + 16);
+    const bool is_orb = o->ref_mode == VSTAB_ORB_FULL_LOCK;
+    // lanes: the ORB front end is ~44 small dependent launches per frame (4 lanes), SIFT at 4K mostly large ones (2 lanes)
+    static const int lanes_env = getenv("VSTAB_REG_LANES") ? atoi(getenv("VSTAB_REG_LANES")) : 0;
+    int K = lanes_env > 0 ? lanes_env : (is_orb ? 4 : 2);
+    if (K > n) K = n;
+    if (K > 8) K = 8;
+    while ((int)o->lanes.size() < K - 1) {
+        auto* L = new (std::nothrow) vstab_offline::RegLane();
+        if (!L) { o->err = "out of memory"; return VSTAB_ERR_CUDA; }
+        o->lanes.push_back(L);
+        CK(cudaStreamCreateWithFlags(&L->q, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming));
+        CK(L->feat_ws.alloc(featprep_workspace_bytes(g.ww, g.wh)));
+        CK(L->feat_gray.alloc((size_t)g.ww * g.wh));
+        CK(L->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(L->cur_desc.alloc(128 * kOrbMaxKp));
+        CK(L->f_counts.alloc(sizeof(int) * 4));
+        CK(L->m_idx.alloc(4 * kOrbMaxKp)); CK(L->m_d0.alloc(4 * kOrbMaxKp)); CK(L->m_d1.alloc(4 * kOrbMaxKp));
+        CK(L->m_good.alloc(kOrbMaxKp)); CK(L->m_status.alloc(kOrbMaxKp));
+        CK(L->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(L->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
+        CK(L->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));
+    }
+    for (int k = 1; k < K; ++k) {
+        auto* L = o->lanes[k - 1];
+        if (is_orb && !L->orb) { L->orb = orb_plan_create(g.ww, g.wh, 0.10, kOrbMaxKp, &o->err); if (!L->orb) return VSTAB_ERR_CUDA; }
+        if (!is_orb && !L->sift) { L->sift = sift_plan_create(g.ww, g.wh, 0.05, kOrbMaxKp, &o->err); if (!L->sift) return VSTAB_ERR_CUDA; }
+    }
+    if (K > 1) {
+        if (!o->ev_reg_fork) CK(cudaEventCreateWithFlags(&o->ev_reg_fork, cudaEventDisableTiming));
+        CK(cudaEventRecord(o->ev_reg_fork, q));                       // reference set, frames: ordered before every lane
+        for (int k = 1; k < K; ++k) CK(cudaStreamWaitEvent(o->lanes[k - 1]->q, o->ev_reg_fork, 0));
+    }
     for (int i = 0; i < n; ++i) {
+        const int k = i % K;
+        vstab_offline::RegLane* L = k ? o->lanes[k - 1] : nullptr;
+        cudaStream_t ql = L ? L->q : q;
+        void* feat_ws = L ? L->feat_ws.p : o->feat_ws.p;
+        uint8_t* feat_gray = (L ? L->feat_gray : o->feat_gray).as<uint8_t>();
+        OrbKeypoint* cur_kps = (L ? L->cur_kps : o->cur_kps).as<OrbKeypoint>();
+        uint8_t* cur_desc = (L ? L->cur_desc : o->cur_desc).as<uint8_t>();
+        int* counts = (L ? L->f_counts : o->f_counts).as<int>();
+        int* m_idx = (L ? L->m_idx : o->m_idx).as<int>();
+        int* m_d0 = (L ? L->m_d0 : o->m_d0).as<int>();
+        int* m_d1 = (L ? L->m_d1 : o->m_d1).as<int>();
+        uint8_t* m_good = (L ? L->m_good : o->m_good).as<uint8_t>();
+        float2* m_ref = (L ? L->m_ref : o->m_ref).as<float2>();
+        float2* m_cur = (L ? L->m_cur : o->m_cur).as<float2>();
+        uint8_t* m_status = (L ? L->m_status : o->m_status).as<uint8_t>();
+        double* Tfit = (L ? L->lock_fit : o->lock_fit).as<double>();
+        int* fitc = reinterpret_cast<int*>(Tfit + 16);
         const uint8_t* frame = d_frames + (size_t)i * frame_stride;
-        launch_featprep(frame, step, o->nn_x.as<int>(), o->nn_y.as<int>(), g.ww, g.wh, o->feat_ws.p, o->feat_gray.as<uint8_t>(), q);
-        if (o->ref_mode == VSTAB_ORB_FULL_LOCK) {
-            launch_orb(o->orb, o->feat_gray.as<uint8_t>(), o->cur_kps.as<OrbKeypoint>(), o->cur_desc.as<uint8_t>(), counts + 1, false, q);
-            launch_hamming_match(ref_desc, nref, ref_kps, o->cur_desc.as<uint8_t>(), counts + 1, o->cur_kps.as<OrbKeypoint>(), kOrbMaxKp,
-                                 0.6f, o->m_idx.as<int>(), o->m_d0.as<int>(), o->m_d1.as<int>(), o->m_good.as<uint8_t>(),
-                                 o->m_ref.as<float2>(), o->m_cur.as<float2>(), o->m_status.as<uint8_t>(), counts + 2, q);
+        launch_featprep(frame, step, o->nn_x.as<int>(), o->nn_y.as<int>(), g.ww, g.wh, feat_ws, feat_gray, ql);
+        if (is_orb) {
+            launch_orb(L ? L->orb : o->orb, feat_gray, cur_kps, cur_desc, counts + 1, false, ql);
+            launch_hamming_match(ref_desc, nref, ref_kps, cur_desc, counts + 1, cur_kps, kOrbMaxKp, 0.6f, m_idx, m_d0, m_d1, m_good,
+                                 m_ref, m_cur, m_status, counts + 2, ql);
         } else {
-            launch_sift(o->sift, o->feat_gray.as<uint8_t>(), o->cur_kps.as<OrbKeypoint>(), o->cur_desc.as<uint8_t>(), counts + 1, q);
-            launch_l2_match(ref_desc, nref, ref_kps, o->cur_desc.as<uint8_t>(), counts + 1, o->cur_kps.as<OrbKeypoint>(), kOrbMaxKp,
-                            o->m_idx.as<int>(), o->m_d0.as<int>(), o->m_good.as<uint8_t>(), o->m_ref.as<float2>(),
-                            o->m_cur.as<float2>(), o->m_status.as<uint8_t>(), counts + 2, q);
+            launch_sift(L ? L->sift : o->sift, feat_gray, cur_kps, cur_desc, counts + 1, ql);
+            launch_l2_match(ref_desc, nref, ref_kps, cur_desc, counts + 1, cur_kps, kOrbMaxKp, m_idx, m_d0, m_good, m_ref, m_cur,
+                            m_status, counts + 2, ql);
         }
-        launch_fit_large(o->m_ref.as<float2>(), o->m_cur.as<float2>(), o->m_status.as<uint8_t>(), counts + 2, 5.0, g.ww / 2.0,
-                         g.wh / 2.0, Tfit, Tfit + 9, fitc, q);
-        launch_reg_store(Tfit, fitc, nref, counts + 1, counts + 2, d_reg + (size_t)i * 10, q);
+        launch_fit_large(m_ref, m_cur, m_status, counts + 2, 5.0, g.ww / 2.0, g.wh / 2.0, Tfit, Tfit + 9, fitc, ql);
+        launch_reg_store(Tfit, fitc, nref, counts + 1, counts + 2, d_reg + (size_t)i * 10, ql);
+    }
+    for (int k = 1; k < K; ++k) {
+        CK(cudaEventRecord(o->lanes[k - 1]->done, o->lanes[k - 1]->q));
+        CK(cudaStreamWaitEvent(q, o->lanes[k - 1]->done, 0));
     }
     CK(cudaGetLastError());
     return VSTAB_OK;
@@ -953,6 +1010,14 @@ void vstab_offline_destroy(vstab_offline_t* o) {
     if (o->copy_out) { cudaStreamSynchronize(o->copy_out); cudaStreamDestroy(o->copy_out); }
     if (o->orb) orb_plan_destroy(o->orb);
     if (o->sift) sift_plan_destroy(o->sift);
+    for (auto* L : o->lanes) {
+        if (L->q) { cudaStreamSynchronize(L->q); cudaStreamDestroy(L->q); }
+        if (L->done) cudaEventDestroy(L->done);
+        if (L->orb) orb_plan_destroy(L->orb);
+        if (L->sift) sift_plan_destroy(L->sift);
+        delete L;
+    }
+    if (o->ev_reg_fork) cudaEventDestroy(o->ev_reg_fork);
     delete o;
 }
 
