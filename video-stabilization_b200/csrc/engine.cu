@@ -887,9 +887,11 @@ vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames,
     const OrbKeypoint* ref_kps = (const OrbKeypoint*)(pack + kRefPackKps);
     const uint8_t* ref_desc = (const uint8_t*)(pack + kRefPackDesc);
     const bool is_orb = o->ref_mode == VSTAB_ORB_FULL_LOCK;
-    // lanes: the ORB front end is ~44 small dependent launches per frame (4 lanes), SIFT at 4K mostly large ones (2 lanes)
+    // lanes: the ORB front end is ~44 small dependent launches per frame, SIFT at 4K mostly large ones (and 1.1 GB of pyramid per
+    // lane).  Measured on B200, complete offline pass, frames/s with 1 / 2 / 3 / 4 / 8 lanes: ORB 1080p 1950 / - / 2834 / 2981 / 3117,
+    // SIFT 4K 442 / 511 / 531 / - / 563.
     static const int lanes_env = getenv("VSTAB_REG_LANES") ? atoi(getenv("VSTAB_REG_LANES")) : 0;
-    int K = lanes_env > 0 ? lanes_env : (is_orb ? 4 : 2);
+    int K = lanes_env > 0 ? lanes_env : (is_orb ? 8 : 4);
     if (K > n) K = n;
     if (K > 8) K = 8;
     while ((int)o->lanes.size() < K - 1) {
