@@ -1,7 +1,7 @@
 """T1: each CUDA kernel, called through the C ABI (vstab_k_*), against cv2 4.13.0 on the same
 seeded inputs and against the committed golden vectors.  Bit-exact for the integer stages
-(ingest, pyramid, warp), identical corner list for GFTT, <= 0.05 px for LK (north-star
-tolerance; observed <= 1e-3), identical consensus set and <= 1e-6 px for the similarity fit."""
+(ingest, pyramid, warp), identical corner list for GFTT, bit-identical points for LK (north-star
+tolerance 0.05 px), identical consensus set and <= 1e-6 px for the similarity fit."""
 import cv2
 import numpy as np
 import pytest
@@ -116,15 +116,16 @@ def test_lk_parity(texture):
         mine, mst = vs.k_lk(gs[a], gs[b], pts)
         assert np.array_equal(st, mst)
         ok = st == 1
-        assert np.abs(mine[ok] - cur[ok]).max() <= LK_TOL_PX
-        assert np.abs(mine[ok] - cur[ok]).max() <= 2e-3       # what the kernel actually achieves
+        assert np.abs(mine[ok] - cur[ok]).max() <= LK_TOL_PX   # the north-star tolerance ...
+        # ... and what the kernel achieves: the same float32 bits (OpenCV's five-chain float accumulation order is replayed)
+        assert np.array_equal(mine[ok].view(np.uint32), cur[ok].view(np.uint32))
 
 
 def test_lk_golden_and_edge_cases(golden):
     mine, mst = vs.k_lk(golden["g0"], golden["g1"], golden["corners0"])
     assert np.array_equal(mst, golden["lk_status"])
     ok = mst == 1
-    assert np.abs(mine[ok] - golden["lk_pts"][ok]).max() <= 2e-3
+    assert np.array_equal(mine[ok], golden["lk_pts"][ok])        # bit-exact
     # empty point list and a textureless image (min-eigenvalue gate => status 0)
     out, st = vs.k_lk(golden["g0"], golden["g1"], np.zeros((0, 2), np.float32))
     assert len(out) == 0 and len(st) == 0
@@ -140,7 +141,7 @@ def test_lk_golden_and_edge_cases(golden):
     out, st = vs.k_lk(g0, g1, pts)
     cur, ref = _cv_lk(g0, g1, pts)
     assert np.array_equal(st, ref) and (ref == 0).any() and (ref == 1).any()
-    assert np.abs(out[ref == 1] - cur[ref == 1]).max() <= 2e-3
+    assert np.array_equal(out[ref == 1], cur[ref == 1])
 
 
 def test_lk_small_image_drops_pyramid_levels(golden):
@@ -153,7 +154,7 @@ def test_lk_small_image_drops_pyramid_levels(golden):
         cur, ref = _cv_lk(a, b, pts)
         out, st = vs.k_lk(a, b, pts)
         assert np.array_equal(st, ref)
-        assert np.abs(out[ref == 1] - cur[ref == 1]).max() <= 2e-3
+        assert np.array_equal(out[ref == 1], cur[ref == 1])
 
 
 # ------------------------------------------------------------------ K5 fit

@@ -5,20 +5,30 @@
 // float operation order follow OpenCV's LKTrackerInvoker: Q14 bilinear
 // weights, Q5 intensity patches, Scharr derivatives (zero outside the image, intensity
 // reflect-101 padded), float 2x2 normal equations, eps^2 = 1e-4, oscillation damping.
-// Differences from OpenCV are confined to the summation order of the 441-term sums
-// (exact 64-bit integer sums here) => <= 1e-3 px against the 0.05 px tolerance.
+//
+// BIT-EXACT with OpenCV 4.x (SSE2/universal-intrinsics build), including the float rounding of the
+// 441-term sums.  OpenCV accumulates each sum in FIVE float chains, row-major over the window:
+//   chain k = 0..3 : the four lanes of a v_float32x4 over the columns x < 16 with x % 4 == k
+//                    (A sums: one term per pixel, product then add; b sums: the int32 pair
+//                    P(y,x) + P(y,x+4) of an 8-column block converted to float, then added),
+//   chain 4        : the scalar tail over the columns 16..20 (float(int product) added one by one),
+//   result         = chain4 + ((chain0 + chain2) + (chain1 + chain3))         (v_reduce_sum, SSE order).
+// Every term is an integer, so a chain is exact -- and therefore order-free -- as long as the absolute
+// values of its terms sum to less than 2^24.  The kernel keeps OpenCV's value in three tiers:
+//   tier 0: the bound holds for the whole window          -> one exact warp sum,
+//   tier 1: the bound holds for every chain                -> five exact chain sums, OpenCV's four adds,
+//   tier 2: otherwise the terms go through shared memory in chain order and 10 (b) / 15 (A) lanes
+//           replay the sequential float additions.
+// The A sums (once per level) always take the replay; the b sums (every iteration) take the tiers.
 //
 // The 21x21 template (I, Ix, Iy) of a level lives in registers: the window is cut into 63 vertical
-// strips of 7 pixels (3 strip rows x 21 columns) and lane l owns strips l and l + 32 (lane 31 has one).
+// strips of 7 pixels (3 strip rows x 21 columns), two per lane, both of the same chain: lanes 0..23
+// own the column pair (x, x + 4) of an 8-column block (x = 0..3, 8..11) in strip row lane / 8 -- the
+// pair whose products OpenCV adds as integers -- and lanes 24..31 the 15 strips of the columns 16..20.
 // Every level of a frame's pyramid block has the same row pitch, so with the pitch as a template
-// argument the 7 taps of a strip are ONE pointer + immediate offsets: two address computations per
-// iteration instead of fourteen, no per-tap offset registers, all 14 loads of an iteration issued
-// back to back.  A request touches two image rows (lanes 0..20 one row, lanes 21..31 the row seven
-// below).  Intensities come from the padded u8 level (reflect-101 border) and derivatives from the
-// padded Scharr level (zero border) that K2 prepares, so no tap ever needs border logic; both are
-// tiny and L1/L2-resident.  The 2x2 system and the mismatch vector are reduced exactly with
-// redux.sync.  (Round-1 history: pixel-major mapping, lane owns pixels l + 32 s with 14 offset
-// register pairs and a divergent last slot: 2.62 ms per 256 frames; this mapping: 1.84 ms.)
+// argument the 7 taps of a strip are ONE pointer + immediate offsets.  Intensities come from the padded
+// u8 level (reflect-101 border) and derivatives from the padded Scharr level (zero border) that K2
+// prepares, so no tap ever needs border logic; both are tiny and L1/L2-resident.
 #include <cstdlib>
 #include "kernels.h"
 
@@ -46,37 +56,69 @@ VSTAB_D const unsigned* pin(const unsigned* p) {
 }
 VSTAB_D unsigned pack_w(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 
-// (float)(exact 64-bit warp sum of v) * 2^-20 without 64-bit integers: the sum is hi * 2^16 + lo with the two redux.sync
-// results lo < 2^21 and |hi| <= 2^20, which convert exactly; the products by powers of two are exact and the fma rounds
-// the exact sum once -- the same float as an int64 -> float conversion followed by the scaling.
-VSTAB_D float warp_sum_scaled(int v) {
-    const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
-    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
-    return __fmaf_rn((float)hi, 0.0625f, __fmul_rn((float)lo, 1.f / (float)(1 << 20)));
+// exact int -> float for |v| < 2^22 without the conversion pipe: 1.5 * 2^23 + v is representable
+VSTAB_D float small_int_to_float(int v) { return __fsub_rn(__int_as_float(0x4B400000 + v), 12582912.f); }
+
+// OpenCV's final reduction of the five chain sums (v_reduce_sum of the SSE build: (q0 + q2) + (q1 + q3), then the scalar tail)
+VSTAB_D float combine_chains(float c0, float c1, float c2, float c3, float c4) {
+    return __fadd_rn(c4, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
 }
 
-// kP = 0: run-time pitch (any working width); kP > 0: the tap offsets are immediates.
-constexpr int kStripLen = 7, kStrips = 63;
+constexpr int kStripLen = 7;
+// shared memory per warp, in floats.  A planes (Ix, Iy in chain order): chains 0..3 at 84 c (84 terms: row * 4 + x / 4), chain 4
+// at 336 (105 terms: row * 5 + x - 16), 3 zero pads.  b planes (terms of b1, b2 in chain order) alias them: chains 0..3 at 44 c
+// (42 pair terms: row * 2 + block, 2 zero pads), chain 4 at 176 (105 terms, 3 zero pads).
+constexpr int kPlaneA = 444, kPlaneB = 284;
+constexpr int kLkSmemFloats = 2 * kPlaneA;
+constexpr float kExactBound = 16760000.f;      // < 2^24 by more than the rounding of the float bound itself
 
+// kP = 0: run-time pitch (any working width); kP > 0: the tap offsets are immediates.
 template <int kWarpsPerBlock, int kMinBlocks, int kP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks)
-lk_strip_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
+lk_chain_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
                 size_t prev_stride, size_t next_stride, PyrDesc d,
                 const float2* __restrict__ pts, const int* __restrict__ counts,
                 float2* __restrict__ out_pts, uint8_t* __restrict__ status) {
+    __shared__ __align__(16) float smem_all[kWarpsPerBlock][kLkSmemFloats];
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fi = blockIdx.x * kWarpsPerBlock + warp;
     if (fi >= counts[frame]) return;
+    float* sm = smem_all[warp];
+    const unsigned full = 0xffffffffu;
     const uint8_t* pI = prev_pyr + (size_t)frame * prev_stride;
     const uint8_t* pJ = next_pyr + (size_t)frame * next_stride;
     const float2 pt = pts[(size_t)frame * kMaxCorners + fi];
 
-    // the two strips of this lane: strip i covers rows 7 (i / 21) .. + 6 of column i % 21
-    const bool v1 = lane + 32 < kStrips;                       // lane 31: its second strip aliases strip 62 with zero derivatives
-    const int i1 = v1 ? lane + 32 : kStrips - 1;
-    const int q0 = (lane * 3121) >> 16, q1 = (i1 * 3121) >> 16;   // i / 21 for i < 448
-    const int c0 = lane - kLkWin * q0, c1 = i1 - kLkWin * q1;
+    // ---- the two strips of this lane (strip = 7 rows of one window column) ------------------------
+    const bool isP = lane < 24;
+    int q0, c0, q1, c1, chain, oa, ob, sa, ta, tb, sb;
+    bool v1 = true;                                            // lane 31: its second strip aliases strip (2, 20) with zero derivatives
+    if (isP) {
+        const int r = lane & 7;
+        q0 = q1 = lane >> 3;
+        c0 = (r & 3) + 2 * (r & 4);                            // 0..3, 8..11
+        c1 = c0 + 4;
+        chain = r & 3;
+        oa = 84 * chain + 28 * q0 + (c0 >> 2); ob = oa + 1; sa = 4;
+        ta = tb = 44 * chain + 14 * q0 + (r >> 2); sb = 2;
+    } else {
+        const int i0 = 2 * (lane - 24);
+        int i1 = i0 + 1;
+        v1 = i1 < 15;
+        if (!v1) i1 = 14;
+        q0 = i0 / 5; c0 = 16 + i0 % 5;
+        q1 = i1 / 5; c1 = 16 + i1 % 5;
+        chain = 4;
+        oa = 336 + 35 * q0 + (c0 - 16); ob = 336 + 35 * q1 + (c1 - 16); sa = 5;
+        ta = 176 + 35 * q0 + (c0 - 16); tb = 176 + 35 * q1 + (c1 - 16); sb = 5;
+    }
+    // replay lanes: lane = 5 * sum + chain (A: sums A11, A12, A22 on lanes 0..14; b: b1, b2 on lanes 0..9)
+    const int rs = lane / 5, rc = lane - 5 * rs;
+    const float* rdA0 = sm + (rs == 2 ? kPlaneA : 0) + (rc < 4 ? 84 * rc : 336);
+    const float* rdA1 = sm + (rs == 0 ? 0 : kPlaneA) + (rc < 4 ? 84 * rc : 336);
+    float* rdB = sm + (rs & 1) * kPlaneB + (rc < 4 ? 44 * rc : 176);
+    const int nA4 = rc < 4 ? 21 : 27, nB4 = rc < 4 ? 11 : 27;
 
     float outx = 0.f, outy = 0.f;
     int st = 1;
@@ -114,9 +156,8 @@ lk_strip_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
         }
         const unsigned wt01 = pack_w(w00, w01), wt23 = pack_w(w10, w11);
 
-        // ---- template patch (I in Q5, Ix/Iy) into registers, 2x2 normal matrix ---------------
-        int Iw[2 * kStripLen], Ix[2 * kStripLen], Iy[2 * kStripLen];
-        int sA11 = 0, sA12 = 0, sA22 = 0;          // per lane <= 14 * 4080^2 < 2^31
+        // ---- template patch into registers: 2^23 + I (Q5), Ix, Iy as floats (all exact integers) ------
+        float Iw[2 * kStripLen], Ix[2 * kStripLen], Iy[2 * kStripLen];
         {
             const int wo = iy * P + ix;
 #pragma unroll
@@ -132,9 +173,9 @@ lk_strip_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
                         const int s = b * kStripLen + t;
                         const unsigned qi = __ldg(Ip + t * P);
                         const unsigned d00 = __ldg(Dp + t * P);
-                        Iw[s] = (int)(qi & 0xffu) << 5;
-                        Ix[s] = (int)(short)(d00 & 0xffffu);
-                        Iy[s] = (int)d00 >> 16;
+                        Iw[s] = __int_as_float(0x4B000000 + ((int)(qi & 0xffu) << 5));
+                        Ix[s] = small_int_to_float((int)(short)(d00 & 0xffffu));
+                        Iy[s] = small_int_to_float((int)d00 >> 16);
                     }
                 } else {
                     // derivative rows 0..7 of the strip, two columns: the lower taps of row t are the upper taps of row t + 1
@@ -151,26 +192,58 @@ lk_strip_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
                         const int xv = (int)(short)(d00 & 0xffffu) * w00 + (int)(short)(d01 & 0xffffu) * w01 +
                                        (int)(short)(d10 & 0xffffu) * w10 + (int)(short)(d11 & 0xffffu) * w11;
                         const int yv = ((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 + ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11;
-                        Iw[s] = iv >> 9;
-                        Ix[s] = (xv + (1 << 13)) >> 14;
-                        Iy[s] = (yv + (1 << 13)) >> 14;
+                        Iw[s] = __int_as_float(0x4B000000 + (iv >> 9));
+                        Ix[s] = small_int_to_float((xv + (1 << 13)) >> 14);
+                        Iy[s] = small_int_to_float((yv + (1 << 13)) >> 14);
                     }
                 }
             }
             if (!v1) {
 #pragma unroll
-                for (int t = 0; t < kStripLen; ++t) { Ix[kStripLen + t] = 0; Iy[kStripLen + t] = 0; }
-            }
-#pragma unroll
-            for (int s = 0; s < 2 * kStripLen; ++s) {
-                sA11 += Ix[s] * Ix[s];
-                sA12 += Ix[s] * Iy[s];
-                sA22 += Iy[s] * Iy[s];
+                for (int t = 0; t < kStripLen; ++t) { Ix[kStripLen + t] = 0.f; Iy[kStripLen + t] = 0.f; }
             }
         }
-        const float A11 = warp_sum_scaled(sA11);
-        const float A12 = warp_sum_scaled(sA12);
-        const float A22 = warp_sum_scaled(sA22);
+        // ---- 2x2 normal matrix: OpenCV's five float chains per sum, replayed by lanes 0..14 -----------
+        float A11, A12, A22;
+        {
+#pragma unroll
+            for (int t = 0; t < kStripLen; ++t) {
+                sm[oa + t * sa] = Ix[t];
+                sm[kPlaneA + oa + t * sa] = Iy[t];
+            }
+            if (v1) {
+#pragma unroll
+                for (int t = 0; t < kStripLen; ++t) {
+                    sm[ob + t * sa] = Ix[kStripLen + t];
+                    sm[kPlaneA + ob + t * sa] = Iy[kStripLen + t];
+                }
+            }
+            if (lane < 3) { sm[441 + lane] = 0.f; sm[kPlaneA + 441 + lane] = 0.f; }
+            __syncwarp();
+            float acc = 0.f;
+            if (lane < 15) {
+                const float4* a4 = reinterpret_cast<const float4*>(rdA0);
+                const float4* b4 = reinterpret_cast<const float4*>(rdA1);
+#pragma unroll 3
+                for (int i = 0; i < nA4; ++i) {
+                    const float4 a = a4[i], b = b4[i];
+                    // the products are exact (< 2^24), so fma(a, b, acc) == acc + a * b as OpenCV's mul + add computes it
+                    acc = __fmaf_rn(a.x, b.x, acc);
+                    acc = __fmaf_rn(a.y, b.y, acc);
+                    acc = __fmaf_rn(a.z, b.z, acc);
+                    acc = __fmaf_rn(a.w, b.w, acc);
+                }
+            }
+            __syncwarp();
+            float s[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float e0 = __shfl_sync(full, acc, 5 * k), e1 = __shfl_sync(full, acc, 5 * k + 1), e2 = __shfl_sync(full, acc, 5 * k + 2),
+                            e3 = __shfl_sync(full, acc, 5 * k + 3), e4 = __shfl_sync(full, acc, 5 * k + 4);
+                s[k] = __fmul_rn(combine_chains(e0, e1, e2, e3, e4), 1.f / (float)(1 << 20));
+            }
+            A11 = s[0]; A12 = s[1]; A22 = s[2];
+        }
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         {
             const float dd = __fsub_rn(A11, A22);
@@ -201,22 +274,88 @@ lk_strip_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
                 const int v11 = 16384 - v00 - v01 - v10;
                 vt01 = pack_w(v00, v01); vt23 = pack_w(v10, v11);
             }
-            int sb1 = 0, sb2 = 0;                   // per lane <= 14 * 8160 * 4080 < 2^31
             const int jo = jy * P + jx;
             const unsigned* Jp0 = pin(J + (jo + so0));
             const unsigned* Jp1 = pin(J + (jo + so1));
             unsigned q[2 * kStripLen];
 #pragma unroll
             for (int t = 0; t < kStripLen; ++t) { q[t] = __ldg(Jp0 + t * P); q[kStripLen + t] = __ldg(Jp1 + t * P); }
+            // mismatch I_t = J - I (exact, |.| <= 8160) and the lane's share of b1 = sum I_t Ix, b2 = sum I_t Iy in float: exact
+            // while the bound (sum of |terms|, same instruction with the free |.| modifiers) stays below 2^24
+            float fd[2 * kStripLen];
+            float acc1 = 0.f, acc2 = 0.f, bn1 = 0.f, bn2 = 0.f;
 #pragma unroll
             for (int s = 0; s < 2 * kStripLen; ++s) {
                 const int jv = dp2a_lo_su(vt01, q[s], dp2a_hi_su(vt23, q[s], 1 << 8)) >> 9;
-                const int diff = jv - Iw[s];
-                sb1 += diff * Ix[s];
-                sb2 += diff * Iy[s];
+                fd[s] = __fsub_rn(__int_as_float(0x4B000000 + jv), Iw[s]);
+                acc1 = __fmaf_rn(fd[s], Ix[s], acc1);
+                acc2 = __fmaf_rn(fd[s], Iy[s], acc2);
+                bn1 = __fmaf_rn(fabsf(fd[s]), fabsf(Ix[s]), bn1);
+                bn2 = __fmaf_rn(fabsf(fd[s]), fabsf(Iy[s]), bn2);
             }
-            const float b1 = warp_sum_scaled(sb1);
-            const float b2 = warp_sum_scaled(sb2);
+            float b1, b2;
+            {
+                const float bl = fmaxf(bn1, bn2);
+                const int bi = bl < kExactBound ? __float2int_ru(bl) : (1 << 24);
+                if (__reduce_add_sync(full, bi) < (int)kExactBound) {
+                    // tier 0: no partial sum of any order reaches 2^24
+                    b1 = (float)__reduce_add_sync(full, __float2int_rn(acc1));
+                    b2 = (float)__reduce_add_sync(full, __float2int_rn(acc2));
+                } else {
+                    bool ok = true;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) ok = ok && __reduce_add_sync(full, chain == c ? bi : 0) < (int)kExactBound;
+                    float e1[5], e2[5];
+                    if (ok) {
+                        // tier 1: every chain is exact; OpenCV's four float additions on top
+                        const int a1 = __float2int_rn(acc1), a2 = __float2int_rn(acc2);
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            e1[c] = (float)__reduce_add_sync(full, chain == c ? a1 : 0);
+                            e2[c] = (float)__reduce_add_sync(full, chain == c ? a2 : 0);
+                        }
+                    } else {
+                        // tier 2: terms in chain order through shared memory (the integer pair sums of OpenCV's v_dotprod for the
+                        // SIMD chains), then lanes 0..9 replay the sequential float additions
+                        if (lane < 10) {
+                            if (rc < 4) { rdB[42] = 0.f; rdB[43] = 0.f; }
+                            else { rdB[105] = 0.f; rdB[106] = 0.f; rdB[107] = 0.f; }
+                        }
+#pragma unroll
+                        for (int t = 0; t < kStripLen; ++t) {
+                            const int d0 = __float2int_rn(fd[t]), d1 = __float2int_rn(fd[kStripLen + t]);
+                            const int u1 = d0 * __float2int_rn(Ix[t]), u2 = d0 * __float2int_rn(Iy[t]);
+                            const int g1 = d1 * __float2int_rn(Ix[kStripLen + t]), g2 = d1 * __float2int_rn(Iy[kStripLen + t]);
+                            sm[ta + t * sb] = (float)(isP ? u1 + g1 : u1);
+                            sm[kPlaneB + ta + t * sb] = (float)(isP ? u2 + g2 : u2);
+                            if (!isP && v1) {
+                                sm[tb + t * sb] = (float)g1;
+                                sm[kPlaneB + tb + t * sb] = (float)g2;
+                            }
+                        }
+                        __syncwarp();
+                        float acc = 0.f;
+                        if (lane < 10) {
+                            const float4* p4 = reinterpret_cast<const float4*>(rdB);
+#pragma unroll 3
+                            for (int i = 0; i < nB4; ++i) {
+                                const float4 v = p4[i];
+                                acc = __fadd_rn(acc, v.x);
+                                acc = __fadd_rn(acc, v.y);
+                                acc = __fadd_rn(acc, v.z);
+                                acc = __fadd_rn(acc, v.w);
+                            }
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) { e1[c] = __shfl_sync(full, acc, c); e2[c] = __shfl_sync(full, acc, 5 + c); }
+                    }
+                    b1 = combine_chains(e1[0], e1[1], e1[2], e1[3], e1[4]);
+                    b2 = combine_chains(e2[0], e2[1], e2[2], e2[3], e2[4]);
+                }
+            }
+            b1 = __fmul_rn(b1, 1.f / (float)(1 << 20));
+            b2 = __fmul_rn(b2, 1.f / (float)(1 << 20));
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
@@ -252,15 +391,15 @@ lk_strip_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
 }
 
 template <int kWarpsPerBlock, int kMinBlocks>
-void launch_strip(int P, int nframes, cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_stride,
+void launch_chain(int P, int nframes, cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_stride,
                   size_t next_stride, const PyrDesc& d, const float2* pts, const int* counts, float2* out_pts, uint8_t* status) {
     const int T = kWarpsPerBlock * 32;
     const dim3 grid((kMaxCorners + kWarpsPerBlock - 1) / kWarpsPerBlock, nframes);
     // working widths 640 (wh 360 of 16:9 input), 1920, 3840 (+ 2 * kLkPad) get immediate tap offsets
-    if (P == 688) lk_strip_kernel<kWarpsPerBlock, kMinBlocks, 688><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
-    else if (P == 1968) lk_strip_kernel<kWarpsPerBlock, kMinBlocks, 1968><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
-    else if (P == 3888) lk_strip_kernel<kWarpsPerBlock, kMinBlocks, 3888><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
-    else lk_strip_kernel<kWarpsPerBlock, kMinBlocks, 0><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
+    if (P == 688) lk_chain_kernel<kWarpsPerBlock, kMinBlocks, 688><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
+    else if (P == 1968) lk_chain_kernel<kWarpsPerBlock, kMinBlocks, 1968><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
+    else if (P == 3888) lk_chain_kernel<kWarpsPerBlock, kMinBlocks, 3888><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
+    else lk_chain_kernel<kWarpsPerBlock, kMinBlocks, 0><<<grid, T, 0, st>>>(prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status);
 }
 
 }  // namespace
@@ -270,26 +409,16 @@ void launch_lk(const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_str
                float2* out_pts, uint8_t* status, cudaStream_t st) {
     if (nframes <= 0) return;
     count_launch(1);
-    // VSTAB_LK_WARPS: features (warps) per CTA -- a CTA's registers are held until its slowest feature converges, so
-    // one-warp CTAs refill soonest; VSTAB_LK_REGS: 96 or 80 registers per thread.  Measured on B200, ms per 256 frames
-    // (warps per CTA / registers): 4/96 1.73, 4/80 1.91, 2/96 1.71, 2/80 1.88, 1/96 1.66, 1/80 1.62 (default).
-    // An L1 prefetch (CCTL.PF1) of the next level's windows cost +0.1 ms and was not kept.
-    static int wpb = 0, regs = 80;
-    if (wpb == 0) {
-        const char* e = getenv("VSTAB_LK_WARPS"); wpb = e ? atoi(e) : 1;
-        if (const char* r = getenv("VSTAB_LK_REGS")) regs = atoi(r);
-    }
+    // One warp per CTA: a CTA's registers and shared memory are held until its slowest feature converges, so one-warp
+    // CTAs refill soonest (round 1: 4 / 2 / 1 warps per CTA 1.73 / 1.71 / 1.66 ms per 256 frames).
+    // VSTAB_LK_REGS: 128 (16 CTAs per SM) or 96 (20 CTAs per SM) registers per thread.
+    static const int regs = [] { const char* r = getenv("VSTAB_LK_REGS"); return r ? atoi(r) : 128; }();
     bool uniform = true;
     for (int l = 1; l < d.nlev; ++l) uniform = uniform && d.pitch[l] == d.pitch[0];
     const int P = uniform ? d.pitch[0] : 0;
 #define VSTAB_LK_ARGS P, nframes, st, prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status
     // min blocks per SM = 65536 / (registers * threads per CTA)
-    if (wpb == 1) {
-        if (regs == 64) launch_strip<1, 32>(VSTAB_LK_ARGS); else if (regs == 72) launch_strip<1, 28>(VSTAB_LK_ARGS);
-        else if (regs == 80) launch_strip<1, 24>(VSTAB_LK_ARGS); else launch_strip<1, 20>(VSTAB_LK_ARGS);
-    }
-    else if (wpb == 2) { if (regs == 80) launch_strip<2, 12>(VSTAB_LK_ARGS); else launch_strip<2, 10>(VSTAB_LK_ARGS); }
-    else { if (regs == 80) launch_strip<4, 6>(VSTAB_LK_ARGS); else launch_strip<4, 5>(VSTAB_LK_ARGS); }
+    if (regs == 96) launch_chain<1, 20>(VSTAB_LK_ARGS); else launch_chain<1, 16>(VSTAB_LK_ARGS);
 #undef VSTAB_LK_ARGS
 }
 
