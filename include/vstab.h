@@ -42,7 +42,8 @@ typedef enum vstab_status {
     VSTAB_ERR_SIZE_CHANGED = 2,     /* "Frame size has changed" (:110-112)      */
     VSTAB_ERR_CUDA = 3,             /* no device / CUDA runtime failure          */
     VSTAB_ERR_UNSUPPORTED = 4,      /* mode not built yet        */
-    VSTAB_ERR_STATE = 5             /* call order the reference asserts against  */
+    VSTAB_ERR_STATE = 5,            /* call order the reference asserts against  */
+    VSTAB_ERR_NCCL = 6              /* NCCL missing / a collective failed (sharded offline jobs only) */
 } vstab_status;
 
 /* struct HomographyParameters -- include/stabilizer.hpp:44-57 */
@@ -139,8 +140,9 @@ long vstab_presentation_index(const vstab_t* s);    /* absolute index of the fra
 /* ---- offline (frame-sharded) mode ---------------------------------------------------
  * BASELINE.json north_star: a clip is sharded by contiguous frame ranges with a halo
  * frame; each GPU estimates its frame-pair transforms, the per-frame 3x3 are
- * all-gathered (by the caller, e.g. ncclAllGather on `d_T`), then each GPU smooths and
- * warps its own frames.  Index algebra: SURVEY.md Appendix C; results equal the
+ * all-gathered, then each GPU smooths and warps its own frames.  vstab_offline_run (below) is
+ * that whole job behind one call; the functions here are its building blocks (device pointers,
+ * caller-driven).  Index algebra: SURVEY.md Appendix C; results equal the
  * streaming calls above for every call index.  All pointers are DEVICE pointers. */
 typedef struct vstab_offline vstab_offline_t;
 
@@ -197,6 +199,7 @@ vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames,
                                     int n, double* d_reg);
 vstab_status vstab_offline_set_registrations(vstab_offline_t* o, const double* d_reg_all, long n_total);
 vstab_status vstab_offline_synchronize(vstab_offline_t* o);
+const char* vstab_offline_last_error(const vstab_offline_t* o);   /* message of the last non-OK status of an offline instance */
 /* per-stage device time (CUDA events on the instance stream) accumulated since the last call:
  * ms[8]/counts[8] = ingest, pyramid, gftt, lk, fit, smooth, warp, acc-scan */
 void vstab_offline_set_timing(vstab_offline_t* o, int enable);
@@ -207,6 +210,52 @@ long long vstab_launch_count(void);
 long vstab_offline_read_h(vstab_offline_t* o, double* dst, size_t n_calls);
 /* cudaStream_t of the instance, as an integer handle, so callers can order NCCL work after it */
 uintptr_t vstab_offline_stream(vstab_offline_t* o);
+
+/* ---- sharded offline job: the whole multi-GPU path behind one call (BASELINE config 5) ------------
+ * One process per GPU.  Every rank creates a vstab_offline_t on its device, the ranks join one NCCL communicator
+ * (rank 0 makes the id, the host program ships its 128 bytes to the others any way it likes), and every rank calls
+ * vstab_offline_run with the same n_total / mode / lock_call:
+ *   pass 1   rank r estimates T[f] for its contiguous range [first, last) (+ the halo frame first-1), chunk by chunk:
+ *            at most max_batch + 1 frames are resident at any time (the reference's window bound, stabilizer.cpp:160-167);
+ *   exchange ONE ncclAllGather of 72 bytes per frame (ORB / SIFT lock: + one ncclBroadcast of the packed reference set
+ *            and one all-gather of 80 bytes per frame {H, valid});
+ *   pass 2   global prefix / window average for the calls whose presentation frame the rank owns, warp, sink.
+ * Frames come from host memory (this rank's shard; re-read in pass 2) or from the simulator (K13 renders each
+ * chunk on the device from `poses`, in both passes: nothing of the clip is ever stored).  Outputs go to host memory
+ * and / or are reduced to one 64-bit checksum per call (see vstab_frame_checksum).  With no communicator the
+ * instance is a world of one.  Replaces the reference's --file / --simulator loop around stabilizeFrame
+ * (src/main_utils.cpp:397-417, 459-493) for clips that are sharded over GPUs. */
+typedef struct vstab_nccl_id { char bytes[128]; } vstab_nccl_id;
+vstab_status vstab_nccl_get_unique_id(vstab_nccl_id* out);                 /* rank 0 */
+vstab_status vstab_offline_comm_init(vstab_offline_t* o, const vstab_nccl_id* id, int rank, int world);
+/* frame range [first, last) and call range [call_first, call_last) of `rank` (balanced contiguous split; the owner of
+ * frame 0 also produces the `future` warm-up calls; the last `future` frames are never presented) */
+typedef struct vstab_shard_plan { long first, last, call_first, call_last; } vstab_shard_plan;
+vstab_status vstab_offline_plan(long n_total, int world, int rank, size_t future_frames, vstab_shard_plan* out);
+
+typedef enum vstab_frame_source { VSTAB_SRC_HOST = 0, VSTAB_SRC_SIMULATOR = 1 } vstab_frame_source;
+typedef struct vstab_offline_cfg {
+    long n_total;                   /* frames of the whole clip                                                  */
+    int mode;                       /* vstab_mode; lock modes: lock_call = call index of setStabilizationMode      */
+    long lock_call;
+    int source;                     /* vstab_frame_source                                                          */
+    /* VSTAB_SRC_HOST: this rank's frames [first, last) (pinned memory recommended) and frame first-1 (NULL on rank 0) */
+    const uint8_t* host_frames; size_t frame_stride, step;
+    const uint8_t* host_halo;
+    /* VSTAB_SRC_SIMULATOR: device-resident BGR texture and the host array poses[n_total][6] = x y z pan tilt roll   */
+    const uint8_t* d_texture; int tex_rows, tex_cols; const double* poses; double focal;
+    /* sinks (each may be NULL): outputs of this rank's calls in call order, their checksums, all transforms         */
+    uint8_t* host_out; size_t out_frame_stride, out_step;
+    uint64_t* checksums;            /* [call_last - call_first]                                                    */
+    double* T_all;                  /* [n_total][9] host copy of the gathered transforms                           */
+} vstab_offline_cfg;
+typedef struct vstab_offline_report {   /* device time per phase on this rank, milliseconds (CUDA events)         */
+    float source_ms, estimate_ms, exchange_ms, render_ms, total_ms;
+    long frames, calls;
+} vstab_offline_report;
+vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offline_cfg* cfg, vstab_offline_report* report /* or NULL */);
+/* the checksum the warp kernel accumulates, of a host frame (tests) */
+uint64_t vstab_frame_checksum(const uint8_t* bgr, int rows, int cols, size_t step);
 
 /* ---- simulator frame source (CameraEngine::renderFrame, src/camera_engine.cpp:158-172) --
  * Renders `n` frames on the device from a device-resident BGR texture; poses are

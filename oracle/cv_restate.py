@@ -251,11 +251,44 @@ def _pad_reflect(img, pad):
     return img[yy][:, xx]
 
 
+def _lk_chain_sum(terms: np.ndarray) -> np.ndarray:
+    """float32 sums of k 21x21 term windows (k, 21, 21) in the accumulation order of OpenCV's
+    LKTrackerInvoker (lkpyramid.cpp, CV_SIMD128 build: SSE2 baseline of the cv2 wheels): rows top to
+    bottom; in a row the columns 0..15 go four at a time into the four lanes of a v_float32x4 (lane
+    k takes the columns x % 4 == k, one float add per term), the columns 16..20 one by one into a
+    scalar float; the result is scalar + ((lane0 + lane2) + (lane1 + lane3)) (v_reduce_sum, SSE).
+    Pinned against cv2.calcOpticalFlowPyrLK: identical float32 bits (tests/test_oracle_restate.py).
+    The CUDA tracker (csrc/lk.cu) replays exactly this order."""
+    t = np.asarray(terms, np.float32)
+    q = np.zeros((t.shape[0], 4), np.float32)
+    tail = np.zeros(t.shape[0], np.float32)
+    for y in range(t.shape[1]):
+        for x0 in range(0, 16, 4):
+            q = q + t[:, y, x0:x0 + 4]
+        for x in range(16, t.shape[2]):
+            tail = tail + t[:, y, x]
+    return tail + ((q[:, 0] + q[:, 2]) + (q[:, 1] + q[:, 3]))
+
+
+def _lk_b_terms(prod: np.ndarray) -> np.ndarray:
+    """The float terms of the mismatch sums b1, b2 from the exact integer products I_t * Ix (or Iy),
+    (k, 21, 21): in each 8-column block v_dotprod adds the products of the columns x and x + 4 as
+    int32 before the conversion to float; `_lk_chain_sum` then sees that pair term in column x and a
+    zero in column x + 4 (adding +0.0 changes nothing).  Columns 16..20: float(int product) each."""
+    p = np.asarray(prod, np.int64)
+    t = np.zeros(p.shape, np.float32)
+    for b in (0, 8):
+        t[:, :, b:b + 4] = (p[:, :, b:b + 4] + p[:, :, b + 4:b + 8]).astype(np.float32)
+    t[:, :, 16:] = p[:, :, 16:].astype(np.float32)
+    return t
+
+
 def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
                              win: int = 21, max_level: int = 3, max_iter: int = 50,
                              eps: float = 0.01, min_eig: float = 1e-4):
-    """Sparse pyramidal LK, control flow and fixed-point formats of OpenCV's
-    LKTrackerInvoker.  Returns (next_pts float32 (N,2), status u8)."""
+    """Sparse pyramidal LK, control flow, fixed-point formats and float accumulation order of
+    OpenCV's LKTrackerInvoker (`_lk_chain_sum`): bit-identical to
+    cv2.calcOpticalFlowPyrLK.  Returns (next_pts float32 (N,2), status u8)."""
     half = (win - 1) * 0.5
     # buildOpticalFlowPyramid drops every level that is not larger than the window in both
     # dimensions ([probe] 128x96 with win 21 keeps levels 0..2), lowering the effective maxLevel
@@ -315,9 +348,10 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
             Iw = interp(Ipad, 1 << (W_BITS - 5 - 1), W_BITS - 5)
             Ix = interp(dxpad, 1 << (W_BITS - 1), W_BITS)
             Iy = interp(dypad, 1 << (W_BITS - 1), W_BITS)
-            A11 = F32(F32(np.sum(Ix.astype(np.float32) * Ix.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
-            A12 = F32(F32(np.sum(Ix.astype(np.float32) * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
-            A22 = F32(F32(np.sum(Iy.astype(np.float32) * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+            fx, fy = Ix.astype(np.float32), Iy.astype(np.float32)
+            A11 = F32(_lk_chain_sum((fx * fx)[None])[0] * FLT_SCALE)
+            A12 = F32(_lk_chain_sum((fx * fy)[None])[0] * FLT_SCALE)
+            A22 = F32(_lk_chain_sum((fy * fy)[None])[0] * FLT_SCALE)
             D = F32(A11 * A22 - A12 * A12)
             mineig = F32((A22 + A11 - np.sqrt(F32((A11 - A22) * (A11 - A22) + F32(4.0) * A12 * A12))) / F32(2 * win * win))
             if float(mineig) < min_eig or D < np.finfo(np.float32).eps:   # OpenCV compares in double
@@ -342,9 +376,10 @@ def calc_optical_flow_pyr_lk(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray,
                 w10 = int(np.rint((one - a) * b * s))
                 w11 = (1 << W_BITS) - w00 - w01 - w10
                 Jw = interp(Jpad, 1 << (W_BITS - 5 - 1), W_BITS - 5, iny + PAD, inx + PAD, (w00, w01, w10, w11))
-                diff = (Jw - Iw).astype(np.float32)
-                b1 = F32(F32(np.sum(diff * Ix.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
-                b2 = F32(F32(np.sum(diff * Iy.astype(np.float32), dtype=np.float32)) * FLT_SCALE)
+                diff = (Jw - Iw).astype(np.int64)
+                bb = _lk_chain_sum(_lk_b_terms(np.stack([diff * Ix, diff * Iy])))
+                b1 = F32(bb[0] * FLT_SCALE)
+                b2 = F32(bb[1] * FLT_SCALE)
                 ddx = F32((A12 * b2 - A22 * b1) * D)
                 ddy = F32((A12 * b1 - A11 * b2) * D)
                 nx = F32(nx + ddx)

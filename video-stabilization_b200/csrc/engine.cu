@@ -10,6 +10,9 @@
 // and the accumulated transform (:444).  The host keeps only integer indices, so a call
 // enqueues kernels and copies without ever reading a result back except the output frame.
 #include <atomic>
+#include <dlfcn.h>
+#include <mutex>
+#include <utility>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
@@ -28,6 +31,17 @@ namespace vstabk {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        cache[dev & 63].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 bool graphs_enabled() {
     static const bool on = !(getenv("VSTAB_GRAPHS") && atoi(getenv("VSTAB_GRAPHS")) == 0);
     return on;
@@ -85,6 +99,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
     } while (0)
 
 thread_local std::string g_err;   // for entry points without an instance
+void nccl_comm_destroy(void* comm);
 
 struct DevBuf {
     void* p = nullptr;
@@ -416,8 +431,10 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
     launch_smooth(a, n, 1, s->wp.as<WarpParams>(), q);                                                 // :1234-1296
     s->mark(8, q);
     static const bool lookahead = !(getenv("VSTAB_LOOKAHEAD") && atoi(getenv("VSTAB_LOOKAHEAD")) == 0);
-    if (feature_lock && lookahead && s->F >= 1 && s->has_reference) {
-        // registration of the next call's presentation frame, beside this call's warp and download
+    if (feature_lock && lookahead && s->F >= 2 && s->has_reference) {
+        // registration of the next call's presentation frame, beside this call's warp and download.  Only with
+        // future >= 2: that frame (n + 1 - F <= n - 1) is then already in the ring; with future == 1 it is the frame
+        // this very call uploads AFTER its output chain was enqueued, so its registration stays inside call n + 1
         const long pn = n + 1 - (long)s->F > 0 ? n + 1 - (long)s->F : 0;
         CK(cudaEventRecord(s->ev_reg, q));
         CK(cudaStreamWaitEvent(s->feat_stream, s->ev_reg, 0));
@@ -555,6 +572,7 @@ const char* vstab_status_string(vstab_status st) {
         case VSTAB_ERR_SIZE_CHANGED: return "frame size changed";
         case VSTAB_ERR_CUDA: return "CUDA error";
         case VSTAB_ERR_UNSUPPORTED: return "unsupported";
+        case VSTAB_ERR_NCCL: return "NCCL error";
         case VSTAB_ERR_STATE: return "invalid state";
     }
     return "?";
@@ -622,6 +640,7 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_gftt) cudaEventDestroy(s->ev_gftt);
     if (s->orb) orb_plan_destroy(s->orb);
     if (s->sift) sift_plan_destroy(s->sift);
+    for (auto& set : s->tev) for (auto& e : set) if (e) cudaEventDestroy(e);     // VSTAB_TRACE marks
     delete s;
 }
 
@@ -790,6 +809,11 @@ struct vstab_offline {
     };
     std::vector<RegLane*> lanes;
     cudaEvent_t ev_reg_fork = nullptr;
+    // sharded job (vstab_offline_run): NCCL communicator of this rank, chunk buffers kept between runs
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    DevBuf job_chunk, job_out;
+    size_t job_chunk_frames = 0;
     std::string err;
     void set_err(const std::string& e) { err = e; }
 };
@@ -977,11 +1001,11 @@ vstab_status vstab_offline_create(size_t past_frames, size_t future_frames, int 
     if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
     vstab_offline* o = new (std::nothrow) vstab_offline();
     if (!o) return VSTAB_ERR_CUDA;
-    auto fail = [&](vstab_status st, const std::string& m) { g_err = m; delete o; return st; };
+    auto fail = [&](vstab_status st, const std::string& m) { g_err = m; vstab_offline_destroy(o); return st; };
     o->device = device; o->P = past_frames; o->F = future_frames; o->max_batch = max_batch;
     if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VSTAB_ERR_CUDA, "cudaStreamCreate failed");
     vstab_status st = o->g.init(rows, cols, working_height, g_err);
-    if (st != VSTAB_OK) { delete o; return st; }
+    if (st != VSTAB_OK) { vstab_offline_destroy(o); return st; }
     Geometry& g = o->g;
     const size_t nb = (size_t)max_batch + 1;   // + halo
     bool ok = o->pyr.alloc(g.pd.frame_bytes * nb) == cudaSuccess &&
@@ -1020,6 +1044,7 @@ void vstab_offline_destroy(vstab_offline_t* o) {
         delete L;
     }
     if (o->ev_reg_fork) cudaEventDestroy(o->ev_reg_fork);
+    if (o->comm) nccl_comm_destroy(o->comm);
     delete o;
 }
 
@@ -1124,11 +1149,12 @@ extern "C" vstab_status vstab_offline_estimate(vstab_offline_t* o, const uint8_t
 }
 
 // d_sums: [.][3] u64 indexed like d_frames (frame - frame_base)
-extern "C" vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
-                                              size_t step, long frame_base, int n, long call_first,
-                                              const double* d_T_all, long n_total, int mode, long lock_call,
-                                              const unsigned long long* d_sums,
-                                              uint8_t* d_out, size_t out_frame_stride, size_t out_step) {
+static vstab_status offline_render_impl(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
+                                        size_t step, long frame_base, int n, long call_first,
+                                        const double* d_T_all, long n_total, int mode, long lock_call,
+                                        const unsigned long long* d_sums,
+                                        uint8_t* d_out, size_t out_frame_stride, size_t out_step,
+                                        unsigned long long* d_check /* [n] pre-zeroed, or null */) {
     if (!o || !d_frames || !d_T_all || !d_out || !d_sums || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
     auto set_err = [&](const std::string& e) { o->err = e; };
     if (n > o->max_batch + 1) { o->err = "n exceeds max_batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
@@ -1166,11 +1192,20 @@ extern "C" vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* 
     o->timer.end(ST_SMOOTH, q);
     o->timer.begin(ST_WARP, q);
     launch_warp(d_frames, step, frame_stride, 0, o->wp.as<WarpParams>(), n, g.cols, g.rows, d_out, out_step,
-                out_frame_stride, q);
+                out_frame_stride, q, d_check);
     o->timer.end(ST_WARP, q);
     CK(cudaGetLastError());
     o->last_ncalls = n;
     return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_offline_render(vstab_offline_t* o, const uint8_t* d_frames, size_t frame_stride,
+                                              size_t step, long frame_base, int n, long call_first,
+                                              const double* d_T_all, long n_total, int mode, long lock_call,
+                                              const unsigned long long* d_sums,
+                                              uint8_t* d_out, size_t out_frame_stride, size_t out_step) {
+    return offline_render_impl(o, d_frames, frame_stride, step, frame_base, n, call_first, d_T_all, n_total, mode, lock_call,
+                               d_sums, d_out, out_frame_stride, out_step, nullptr);
 }
 
 // The "segmented prefix/scan over 3x3 transforms" of the north star: accumulated products
@@ -1319,19 +1354,311 @@ extern "C" long vstab_offline_read_h(vstab_offline_t* o, double* dst, size_t n_c
 }
 
 // =====================================================================================
+// sharded offline job: NCCL (resolved at run time) + vstab_offline_run
+// =====================================================================================
+// NCCL is bound with dlopen so that single-GPU users of libvstab.so need no NCCL at all and a host process that already
+// carries one (torch's bundled libnccl.so.2) shares it.  Only the six entry points below are used; their signatures are
+// those of nccl.h 2.x (ncclResult_t = int, ncclDataType_t: ncclUint8 = 1, ncclDouble = 8).
+static void poses_to_render(const double* poses, long n, RenderPose* hp);
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, vstab_nccl_id, int) = nullptr;     // ncclUniqueId is a 128-byte struct passed by value
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (lib) break; }   // one already in the process
+        if (!lib) for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : ""); return false; }
+        auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) err = std::string("NCCL symbol missing: ") + n; return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        Broadcast = (decltype(Broadcast))sym("ncclBroadcast");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !Broadcast || !GetErrorString) { lib = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+constexpr int kNcclUint8 = 1, kNcclDouble = 8;
+
+struct PhaseClock {          // device time of the phases of one vstab_offline_run (events on the instance stream)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() { cudaEvent_t e = nullptr; cudaEventCreate(&e); pool.push_back(e); return e; }
+    void begin(int phase, cudaStream_t q) { cudaEvent_t e = get(); cudaEventRecord(e, q); spans.push_back({phase, {e, nullptr}}); }
+    void end(cudaStream_t q) { cudaEvent_t e = get(); cudaEventRecord(e, q); spans.back().second.second = e; }
+    void collect(float* ms4) {
+        for (auto& sp : spans) { float ms = 0.f; if (sp.second.second && cudaEventElapsedTime(&ms, sp.second.first, sp.second.second) == cudaSuccess) ms4[sp.first] += ms; }
+    }
+    ~PhaseClock() { for (auto e : pool) cudaEventDestroy(e); }
+};
+}  // namespace
+
+namespace { void nccl_comm_destroy(void* comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); } }
+
+extern "C" const char* vstab_offline_last_error(const vstab_offline_t* o) { return o ? o->err.c_str() : g_err.c_str(); }
+
+extern "C" vstab_status vstab_nccl_get_unique_id(vstab_nccl_id* out) {
+    if (!out) return VSTAB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (!g_nccl.load()) { g_err = g_nccl.err; return VSTAB_ERR_NCCL; }
+    const int r = g_nccl.GetUniqueId(out);
+    if (r != 0) { g_err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return VSTAB_ERR_NCCL; }
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_offline_comm_init(vstab_offline_t* o, const vstab_nccl_id* id, int rank, int world) {
+    if (!o || !id || world < 1 || rank < 0 || rank >= world) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    {
+        std::lock_guard<std::mutex> lock(g_nccl_mu);
+        if (!g_nccl.load()) { o->err = g_nccl.err; return VSTAB_ERR_NCCL; }
+    }
+    CK(cudaSetDevice(o->device));
+    if (o->comm) { g_nccl.CommDestroy(o->comm); o->comm = nullptr; }
+    const int r = g_nccl.CommInitRank(&o->comm, world, *id, rank);
+    if (r != 0) { o->comm = nullptr; o->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return VSTAB_ERR_NCCL; }
+    o->rank = rank; o->world = world;
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_offline_plan(long n_total, int world, int rank, size_t future_frames, vstab_shard_plan* out) {
+    if (!out || n_total < 1 || world < 1 || rank < 0 || rank >= world) return VSTAB_ERR_INVALID_ARGUMENT;
+    const long base = n_total / world, rem = n_total % world;
+    const long first = rank * base + (rank < rem ? rank : rem);
+    const long last = first + base + (rank < rem ? 1 : 0);
+    out->first = first; out->last = last;
+    if (last <= first) { out->call_first = out->call_last = 0; return VSTAB_OK; }
+    const long F = (long)future_frames;
+    const long c0 = first == 0 ? 0 : first + F;
+    const long c1 = last + F < n_total ? last + F : n_total;
+    out->call_first = c0; out->call_last = c1 > c0 ? c1 : c0;
+    return VSTAB_OK;
+}
+
+extern "C" uint64_t vstab_frame_checksum(const uint8_t* bgr, int rows, int cols, size_t step) {
+    uint64_t sum = 0;
+    const int groups = (cols + 3) / 4;
+    for (int y = 0; y < rows; ++y) {
+        const uint8_t* row = bgr + (size_t)y * step;
+        for (int g = 0; g < groups; ++g) {
+            uint8_t b[12] = {0};
+            const int nb = 3 * ((cols - 4 * g) < 4 ? (cols - 4 * g) : 4);
+            memcpy(b, row + (size_t)12 * g, (size_t)nb);
+            uint32_t w[3];
+            for (int k = 0; k < 3; ++k) w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
+            sum += (uint64_t)(y + 1) * (uint64_t)(g + 1) * ((uint64_t)w[0] + 3ull * w[1] + 5ull * w[2]);
+        }
+    }
+    return sum;
+}
+
+extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offline_cfg* cfg, vstab_offline_report* rep) {
+    if (!o || !cfg || cfg->n_total < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    auto set_err = [&](const std::string& e) { o->err = e; };
+    Geometry& g = o->g;
+    const long N = cfg->n_total;
+    const int mode = cfg->mode;
+    const bool sim = cfg->source == VSTAB_SRC_SIMULATOR;
+    const bool feature_lock = mode == VSTAB_ORB_FULL_LOCK || mode == VSTAB_SIFT_FULL_LOCK;
+    if (mode < 0 || mode > 5) { o->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (sim && (!cfg->d_texture || !cfg->poses || cfg->tex_rows < 1 || cfg->tex_cols < 1)) { o->err = "simulator source needs d_texture and poses"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    const size_t row_bytes = (size_t)g.cols * 3;
+    if (!sim && (!cfg->host_frames || cfg->step < row_bytes)) { o->err = "host source needs host_frames with step >= 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (cfg->host_out && cfg->out_step < row_bytes) { o->err = "out_step smaller than 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if ((mode == VSTAB_ACCUMULATED_FULL_LOCK || feature_lock) && cfg->lock_call < (long)o->F) {
+        o->err = "lock modes must be set at a call index >= future (SURVEY B.6)"; return VSTAB_ERR_STATE;
+    }
+    CK(cudaSetDevice(o->device));
+    const int world = o->comm ? o->world : 1, rank = o->comm ? o->rank : 0;
+    vstab_shard_plan pl;
+    vstab_offline_plan(N, world, rank, o->F, &pl);
+    if (!sim && pl.first > 0 && !cfg->host_halo) { o->err = "host source: host_halo (frame first-1) required on ranks > 0"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    const long n_local = pl.last - pl.first, n_calls = pl.call_last - pl.call_first;
+    const long L = (N + world - 1) / world;                        // padded shard length of the all-gather
+    const int B = o->max_batch;
+    const long F = (long)o->F;
+    cudaStream_t q = o->stream;
+    PhaseClock clock;
+    enum { PH_SOURCE = 0, PH_ESTIMATE = 1, PH_EXCHANGE = 2, PH_RENDER = 3 };
+
+    // ---- buffers: one chunk of frames (+ halo), one chunk of outputs, transforms, sums, checksums -----------------
+    DevBuf& chunk = o->job_chunk; DevBuf& outc = o->job_out;
+    if (o->job_chunk_frames < (size_t)B + 1) {
+        CK(chunk.alloc(g.frame_bytes * ((size_t)B + 1) + 64));
+        CK(outc.alloc(g.frame_bytes * (size_t)B + 64));
+        o->job_chunk_frames = (size_t)B + 1;
+    }
+    DevBuf T_local, T_gather, T_all, sums, checks, poses_d, reg_local, reg_gather, reg_all;
+    CK(T_local.alloc(sizeof(double) * 9 * (size_t)L));
+    CK(T_all.alloc(sizeof(double) * 9 * (size_t)N));
+    if (world > 1) CK(T_gather.alloc(sizeof(double) * 9 * (size_t)L * world));
+    CK(sums.alloc(sizeof(unsigned long long) * 3 * (size_t)(n_local > 0 ? n_local : 1)));
+    CK(checks.alloc(sizeof(unsigned long long) * (size_t)(n_calls > 0 ? n_calls : 1)));
+    CK(cudaMemsetAsync(T_local.p, 0, sizeof(double) * 9 * (size_t)L, q));
+    CK(cudaMemsetAsync(checks.p, 0, sizeof(unsigned long long) * (size_t)(n_calls > 0 ? n_calls : 1), q));
+    uint8_t* cb = chunk.as<uint8_t>();
+    const size_t fb = g.frame_bytes;
+    // simulator: poses of the frames this rank may touch (first-1 .. last-1, the anchor frame), as renderer poses
+    if (sim) {
+        std::vector<RenderPose> hp((size_t)N);
+        poses_to_render(cfg->poses, N, hp.data());                  // all N (72 + 24 bytes each): the anchor frame may be anyone's
+        CK(poses_d.alloc(sizeof(RenderPose) * (size_t)N));
+        CK(cudaMemcpyAsync(poses_d.p, hp.data(), sizeof(RenderPose) * (size_t)N, cudaMemcpyHostToDevice, q));
+        CK(cudaStreamSynchronize(q));                               // hp goes out of scope
+    }
+    // frames [f0, f0 + n) of the clip -> chunk slots [slot, slot + n)
+    auto fetch = [&](long f0, long n, int slot) -> vstab_status {
+        if (n <= 0) return VSTAB_OK;
+        clock.begin(PH_SOURCE, q);
+        if (sim) {
+            launch_render(cfg->d_texture, cfg->tex_rows, cfg->tex_cols, poses_d.as<RenderPose>() + f0, (int)n, g.cols, g.rows, cfg->focal,
+                          cb + (size_t)slot * fb, g.pitch, fb, q);
+        } else {
+            for (long i = 0; i < n; ++i) {
+                const long f = f0 + i;
+                if (f < pl.first - 1 || f >= pl.last) { o->err = "internal: frame outside the rank's shard"; return VSTAB_ERR_STATE; }
+                const uint8_t* src = f == pl.first - 1 ? cfg->host_halo : cfg->host_frames + (size_t)(f - pl.first) * cfg->frame_stride;
+                CK(cudaMemcpy2DAsync(cb + (size_t)(slot + i) * fb, g.pitch, src, cfg->step, row_bytes, g.rows, cudaMemcpyHostToDevice, q));
+            }
+        }
+        clock.end(q);
+        CK(cudaGetLastError());
+        return VSTAB_OK;
+    };
+    cudaEvent_t ev_t0 = clock.get(), ev_t1 = clock.get();
+    CK(cudaEventRecord(ev_t0, q));
+    vstab_status st = VSTAB_OK;
+
+    // ---- ORB / SIFT lock: reference set from the anchor frame, broadcast from its owner --------------------------
+    if (feature_lock) {
+        const long anchor = cfg->lock_call - F > 0 ? cfg->lock_call - F : 0;       // presentation frame of the call that set the mode
+        int owner = 0;
+        for (int r = 0; r < world; ++r) { vstab_shard_plan q2; vstab_offline_plan(N, world, r, o->F, &q2); if (anchor >= q2.first && anchor < q2.last) owner = r; }
+        st = offline_feature_setup(o, mode);
+        if (st != VSTAB_OK) return st;
+        DevBuf pack;
+        CK(pack.alloc(vstab_offline_reference_bytes()));
+        if (rank == owner) {
+            if ((st = fetch(anchor, 1, 0)) != VSTAB_OK) return st;
+            if ((st = vstab_offline_reference_capture(o, cb, g.pitch, mode)) != VSTAB_OK) return st;
+            if ((st = vstab_offline_reference_export(o, pack.p)) != VSTAB_OK) return st;
+        }
+        if (world > 1) {
+            clock.begin(PH_EXCHANGE, q);
+            const int r = g_nccl.Broadcast(pack.p, pack.p, vstab_offline_reference_bytes(), kNcclUint8, owner, o->comm, q);
+            clock.end(q);
+            if (r != 0) { o->err = std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r); return VSTAB_ERR_NCCL; }
+            if (rank != owner && (st = vstab_offline_reference_import(o, pack.p, mode)) != VSTAB_OK) return st;
+        }
+        CK(cudaStreamSynchronize(q));                               // `pack` is released here
+        CK(reg_local.alloc(sizeof(double) * 10 * (size_t)L));
+        CK(reg_all.alloc(sizeof(double) * 10 * (size_t)N));
+        if (world > 1) CK(reg_gather.alloc(sizeof(double) * 10 * (size_t)L * world));
+        CK(cudaMemsetAsync(reg_local.p, 0, sizeof(double) * 10 * (size_t)L, q));
+    }
+
+    // ---- pass 1: estimate T[f] for f in [first, last), chunk by chunk ----------------------------------------------
+    for (long f0 = pl.first; f0 < pl.last; f0 += B) {
+        const long n = pl.last - f0 < B ? pl.last - f0 : B;
+        if (f0 == pl.first) {
+            if (f0 > 0 && (st = fetch(f0 - 1, 1, 0)) != VSTAB_OK) return st;        // halo frame
+        } else {
+            // the last frame of the previous chunk is this chunk's halo
+            CK(cudaMemcpyAsync(cb, cb + (size_t)B * fb, fb, cudaMemcpyDeviceToDevice, q));
+        }
+        if ((st = fetch(f0, n, 1)) != VSTAB_OK) return st;
+        clock.begin(PH_ESTIMATE, q);
+        st = vstab_offline_estimate(o, cb + fb, fb, g.pitch, (int)n, f0, f0 > 0 ? cb : nullptr,
+                                    T_local.as<double>() + (size_t)(f0 - pl.first) * 9,
+                                    sums.as<unsigned long long>() + (size_t)(f0 - pl.first) * 3);
+        if (st == VSTAB_OK && feature_lock)
+            st = vstab_offline_register(o, cb + fb, fb, g.pitch, (int)n, reg_local.as<double>() + (size_t)(f0 - pl.first) * 10);
+        clock.end(q);
+        if (st != VSTAB_OK) return st;
+    }
+
+    // ---- the exchange: one all-gather of 72 bytes per frame (+ 80 bytes per frame of registrations) ----------------
+    clock.begin(PH_EXCHANGE, q);
+    auto gather = [&](DevBuf& local, DevBuf& gathered, DevBuf& all, size_t per_frame) -> vstab_status {
+        if (world == 1) {
+            CK(cudaMemcpyAsync(all.p, local.p, sizeof(double) * per_frame * (size_t)N, cudaMemcpyDeviceToDevice, q));
+            return VSTAB_OK;
+        }
+        const int r = g_nccl.AllGather(local.p, gathered.p, per_frame * (size_t)L, kNcclDouble, o->comm, q);
+        if (r != 0) { o->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return VSTAB_ERR_NCCL; }
+        for (int rr = 0; rr < world; ++rr) {                       // drop the padding of the shorter shards
+            vstab_shard_plan q2; vstab_offline_plan(N, world, rr, o->F, &q2);
+            if (q2.last > q2.first)
+                CK(cudaMemcpyAsync(all.as<double>() + (size_t)q2.first * per_frame, gathered.as<double>() + (size_t)rr * L * per_frame,
+                                   sizeof(double) * per_frame * (size_t)(q2.last - q2.first), cudaMemcpyDeviceToDevice, q));
+        }
+        return VSTAB_OK;
+    };
+    if ((st = gather(T_local, T_gather, T_all, 9)) != VSTAB_OK) return st;
+    if (feature_lock) {
+        if ((st = gather(reg_local, reg_gather, reg_all, 10)) != VSTAB_OK) return st;
+        if ((st = vstab_offline_set_registrations(o, reg_all.as<double>(), N)) != VSTAB_OK) return st;
+    }
+    if ((st = vstab_offline_prepare(o, T_all.as<double>(), N, mode, cfg->lock_call)) != VSTAB_OK) return st;
+    clock.end(q);
+
+    // ---- pass 2: the calls whose presentation frame this rank owns -------------------------------------------------
+    for (long c0 = pl.call_first; c0 < pl.call_last; c0 += B) {
+        const long n = pl.call_last - c0 < B ? pl.call_last - c0 : B;
+        const long p_lo = c0 - F > 0 ? c0 - F : 0, p_hi = c0 + n - 1 - F > 0 ? c0 + n - 1 - F : 0;
+        if ((st = fetch(p_lo, p_hi - p_lo + 1, 0)) != VSTAB_OK) return st;
+        clock.begin(PH_RENDER, q);
+        st = offline_render_impl(o, cb, fb, g.pitch, p_lo, (int)n, c0, T_all.as<double>(), N, mode, cfg->lock_call,
+                                 sums.as<unsigned long long>() + (size_t)(p_lo - pl.first) * 3, outc.as<uint8_t>(), fb, g.pitch,
+                                 cfg->checksums ? checks.as<unsigned long long>() + (c0 - pl.call_first) : nullptr);
+        clock.end(q);
+        if (st != VSTAB_OK) return st;
+        if (cfg->host_out) {
+            for (long i = 0; i < n; ++i)
+                CK(cudaMemcpy2DAsync(cfg->host_out + (size_t)(c0 - pl.call_first + i) * cfg->out_frame_stride, cfg->out_step,
+                                     outc.as<uint8_t>() + (size_t)i * fb, g.pitch, row_bytes, g.rows, cudaMemcpyDeviceToHost, q));
+        }
+    }
+    if (cfg->checksums && n_calls > 0)
+        CK(cudaMemcpyAsync(cfg->checksums, checks.p, sizeof(unsigned long long) * (size_t)n_calls, cudaMemcpyDeviceToHost, q));
+    if (cfg->T_all) CK(cudaMemcpyAsync(cfg->T_all, T_all.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, q));
+    CK(cudaEventRecord(ev_t1, q));
+    CK(cudaStreamSynchronize(q));
+    o->acc_T = nullptr;                                            // T_all dies with this call
+    o->reg_all = nullptr; o->reg_n = 0;
+    if (rep) {
+        float ms[4] = {0, 0, 0, 0};
+        clock.collect(ms);
+        rep->source_ms = ms[PH_SOURCE]; rep->estimate_ms = ms[PH_ESTIMATE]; rep->exchange_ms = ms[PH_EXCHANGE]; rep->render_ms = ms[PH_RENDER];
+        rep->total_ms = 0.f;
+        cudaEventElapsedTime(&rep->total_ms, ev_t0, ev_t1);
+        rep->frames = n_local; rep->calls = n_calls;
+    }
+    CK(cudaGetLastError());
+    return VSTAB_OK;
+}
+
+// =====================================================================================
 // simulator render + single-kernel entry points (host buffers)
 // =====================================================================================
-extern "C" vstab_status vstab_render_frames(int device, const uint8_t* d_texture, int tex_rows, int tex_cols,
-                                            const double* poses, int n, int rows, int cols, double focal,
-                                            uint8_t* d_out, size_t frame_stride, size_t step) {
-    auto set_err = [&](const std::string& e) { g_err = e; };
-    if (!d_texture || !poses || !d_out || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
-    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
-    std::vector<RenderPose> hp(n);
-    for (int i = 0; i < n; ++i) {
+// CameraParams (x y z pan tilt roll, include/camera_engine.hpp:44-74) -> the rotation the renderer uses:
+// rotationMatrix = Rz(roll) * Rx(tilt) * Ry(pan), camera_engine.cpp:36-61 (products individually rounded, as cv::Mat's)
+static void poses_to_render(const double* poses, long n, RenderPose* hp) {
+    for (long i = 0; i < n; ++i) {
         const double* p = poses + (size_t)i * 6;
         const double pan = p[3] * M_PI / 180.0, tilt = p[4] * M_PI / 180.0, roll = p[5] * M_PI / 180.0;
-        // rotationMatrix: Rz(roll) * Rx(tilt) * Ry(pan), camera_engine.cpp:36-61
         const double ry[9] = {cos(pan), 0, sin(pan), 0, 1, 0, -sin(pan), 0, cos(pan)};
         const double rx[9] = {1, 0, 0, 0, cos(tilt), -sin(tilt), 0, sin(tilt), cos(tilt)};
         const double rz[9] = {cos(roll), -sin(roll), 0, sin(roll), cos(roll), 0, 0, 0, 1};
@@ -1348,6 +1675,17 @@ extern "C" vstab_status vstab_render_frames(int device, const uint8_t* d_texture
         mm(t, ry, hp[i].R);
         hp[i].cam[0] = p[0]; hp[i].cam[1] = p[1]; hp[i].cam[2] = p[2];
     }
+}
+
+
+extern "C" vstab_status vstab_render_frames(int device, const uint8_t* d_texture, int tex_rows, int tex_cols,
+                                            const double* poses, int n, int rows, int cols, double focal,
+                                            uint8_t* d_out, size_t frame_stride, size_t step) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!d_texture || !poses || !d_out || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    std::vector<RenderPose> hp(n);
+    poses_to_render(poses, n, hp.data());
     DevBuf dp;
     CK(dp.alloc(sizeof(RenderPose) * n));
     CK(cudaMemcpy(dp.p, hp.data(), sizeof(RenderPose) * n, cudaMemcpyHostToDevice));
@@ -1356,7 +1694,6 @@ extern "C" vstab_status vstab_render_frames(int device, const uint8_t* d_texture
     CK(cudaDeviceSynchronize());
     return VSTAB_OK;
 }
-
 extern "C" vstab_status vstab_k_ingest(int device, const uint8_t* bgr, int rows, int cols, size_t step,
                                        int working_height, uint8_t* gray_out, uint64_t sums_out[3]) {
     auto set_err = [&](const std::string& e) { g_err = e; };

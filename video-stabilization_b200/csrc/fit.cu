@@ -247,11 +247,8 @@ void launch_fit(const float2* prev_pts, const float2* next_pts, const uint8_t* s
 
 void launch_fit_large(const float2* ref_pts, const float2* cur_pts, const uint8_t* status, const int* count,
                       double thresh, double cx, double cy, double* T, double* M, int* fit_counts, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(fit_kernel<kOrbMaxKp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 4 * kOrbMaxKp));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    once.run([] { cudaFuncSetAttribute(fit_kernel<kOrbMaxKp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 4 * kOrbMaxKp)); });
     count_launch(1);
     fit_kernel<kOrbMaxKp><<<1, kFitThreads, sizeof(float) * 4 * kOrbMaxKp, st>>>(ref_pts, cur_pts, status, count, thresh, cx,
                                                                                  cy, T, M, fit_counts, 0);

@@ -548,18 +548,14 @@ void launch_gftt(const uint8_t* gray, size_t gray_frame_stride, int w, int h, in
     const bool fused = allow_fused && fused_smem <= (size_t)220 * 1024;
     // batches larger than one wave of single-CTA SMs: the half-size shape when two of its CTAs fit an SM
     // (227 KB shared memory per SM, 1 KB reserved per CTA, + the static histogram)
-    static int num_sms = 0, small_ok = 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static const int small_ok = getenv("VSTAB_TOPK_SMALL") ? atoi(getenv("VSTAB_TOPK_SMALL")) : 1;
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGreedySmemMax);
         cudaFuncSetAttribute(topk_greedy_kernel<1024, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(topk_greedy_kernel<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (const char* e = getenv("VSTAB_TOPK_SMALL")) small_ok = atoi(e);
-        attr_set = true;
-    }
+    });
+    const int num_sms = device_sm_count();
     const bool use_small = fused && small_ok && nframes > num_sms && small_smem <= (size_t)108 * 1024;
     const int key_bits = 31 + ws.idx_bits;
     // the fused kernel leaves the per-frame counters reset behind it

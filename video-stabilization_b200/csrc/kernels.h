@@ -5,6 +5,7 @@
 //   * corners / LK points: float2 [frame][kMaxCorners]; counts int [frame].
 //   * transforms: double [frame][9] row-major.
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -14,6 +15,22 @@ namespace vstabk {
 // number of kernels of this library launched so far (bench.py reports the delta per timed region)
 void count_launch(int n);
 long long launch_count();
+
+// Function attributes (opt-in dynamic shared memory) and the SM count belong to a DEVICE, the C ABI takes a device per
+// instance, and instances may live on several host threads: one-time setup is keyed by the current device and serialised.
+struct PerDeviceOnce {
+    std::mutex mu;
+    unsigned long long done = 0;            // bit d: setup ran on device d
+    template <class F>
+    void run(F&& setup) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        std::lock_guard<std::mutex> lock(mu);
+        if (!(done & bit)) { setup(); done |= bit; }
+    }
+};
+int device_sm_count();                      // of the current device (cached per device)
 
 // ---------------------------------------------------------------- K1 ingest
 struct IngestPlan {
@@ -112,7 +129,8 @@ void launch_acc_scan(const double* T, long n_total, long anchor, double* acc, cu
 // ---------------------------------------------------------------- K7 warpPerspective + border
 void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long slot_mod,
                  const WarpParams* wp, int nout, int w, int h,
-                 uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st);
+                 uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st,
+                 unsigned long long* check = nullptr /* [nout], pre-zeroed: per-frame output checksum (warp.cu) */);
 
 // ---------------------------------------------------------------- K8 feature-path preprocessing
 void build_nn_table(int src, int dst, int* host_tab);                       // cv::resize INTER_NEAREST offsets

@@ -231,12 +231,9 @@ l2_filter_kernel(const int* __restrict__ best_idx, const int* __restrict__ best_
 void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,
                      const int* ncur, const OrbKeypoint* cur_kps, int max_kp, int* best_idx, int* best_d2, uint8_t* good,
                      float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch, cudaStream_t st) {
-    static bool attr = false;
     const int smem = 4 * kTileBytes + 1024;
-    if (!attr) {
-        cudaFuncSetAttribute(l2_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    once.run([&] { cudaFuncSetAttribute(l2_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     count_launch(2);
     l2_nn_kernel<<<(max_kp + TM - 1) / TM, 128, smem, st>>>(ref_desc, nref, max_kp, cur_desc, ncur, max_kp, best_idx, best_d2);
     l2_filter_kernel<<<1, 256, 0, st>>>(best_idx, best_d2, nref, max_kp, ncur, ref_kps, cur_kps, good, ref_pts, cur_pts, status,

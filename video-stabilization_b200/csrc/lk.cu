@@ -64,6 +64,31 @@ VSTAB_D float combine_chains(float c0, float c1, float c2, float c3, float c4) {
     return __fadd_rn(c4, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
 }
 
+
+// Shared-memory geometry of a lane, recomputed where it is used (a handful of integer instructions) instead of
+// being held in registers across the whole kernel: `l` is an opaque copy of the lane index, so nothing is hoisted.
+struct LaneGeo { int oa, ob, sa, ta, tb, sb; };
+VSTAB_D LaneGeo lane_geo(int l) {
+    asm volatile("" : "+r"(l));
+    LaneGeo g;
+    if (l < 24) {
+        const int r = l & 7, q = l >> 3, ch = r & 3;
+        g.oa = 84 * ch + 28 * q + (r >> 2) * 2; g.ob = g.oa + 1; g.sa = 4;      // column c0 = ch + 8 (r >> 2): c0 >> 2 = 2 (r >> 2)
+        g.ta = g.tb = 44 * ch + 14 * q + (r >> 2); g.sb = 2;
+    } else {
+        const int i0 = 2 * (l - 24), i1 = i0 + 1 < 15 ? i0 + 1 : 14;
+        g.oa = 336 + 7 * i0 - 6 * (i0 % 5) + 0 * i1; g.ob = 0; g.sa = 5;       // 35 (i / 5) + i % 5 = 7 i - 6 (i % 5)
+        g.ob = 336 + 7 * i1 - 6 * (i1 % 5);
+        g.ta = g.oa - 160; g.tb = g.ob - 160; g.sb = 5;                          // 176 + ... = 336 + ... - 160
+    }
+    return g;
+}
+// replay lanes: lane = 5 * sum + chain (A: sums A11, A12, A22 on lanes 0..14; b: b1, b2 on lanes 0..9)
+VSTAB_D void replay_geo(int l, int& rs, int& rc) {
+    asm volatile("" : "+r"(l));
+    rs = l / 5; rc = l - 5 * rs;
+}
+
 constexpr int kStripLen = 7;
 // shared memory per warp, in floats.  A planes (Ix, Iy in chain order): chains 0..3 at 84 c (84 terms: row * 4 + x / 4), chain 4
 // at 336 (105 terms: row * 5 + x - 16), 3 zero pads.  b planes (terms of b1, b2 in chain order) alias them: chains 0..3 at 44 c
@@ -92,16 +117,13 @@ lk_chain_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
 
     // ---- the two strips of this lane (strip = 7 rows of one window column) ------------------------
     const bool isP = lane < 24;
-    int q0, c0, q1, c1, chain, oa, ob, sa, ta, tb, sb;
+    int q0, c0, q1, c1;
     bool v1 = true;                                            // lane 31: its second strip aliases strip (2, 20) with zero derivatives
     if (isP) {
         const int r = lane & 7;
         q0 = q1 = lane >> 3;
         c0 = (r & 3) + 2 * (r & 4);                            // 0..3, 8..11
         c1 = c0 + 4;
-        chain = r & 3;
-        oa = 84 * chain + 28 * q0 + (c0 >> 2); ob = oa + 1; sa = 4;
-        ta = tb = 44 * chain + 14 * q0 + (r >> 2); sb = 2;
     } else {
         const int i0 = 2 * (lane - 24);
         int i1 = i0 + 1;
@@ -109,16 +131,8 @@ lk_chain_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
         if (!v1) i1 = 14;
         q0 = i0 / 5; c0 = 16 + i0 % 5;
         q1 = i1 / 5; c1 = 16 + i1 % 5;
-        chain = 4;
-        oa = 336 + 35 * q0 + (c0 - 16); ob = 336 + 35 * q1 + (c1 - 16); sa = 5;
-        ta = 176 + 35 * q0 + (c0 - 16); tb = 176 + 35 * q1 + (c1 - 16); sb = 5;
     }
-    // replay lanes: lane = 5 * sum + chain (A: sums A11, A12, A22 on lanes 0..14; b: b1, b2 on lanes 0..9)
-    const int rs = lane / 5, rc = lane - 5 * rs;
-    const float* rdA0 = sm + (rs == 2 ? kPlaneA : 0) + (rc < 4 ? 84 * rc : 336);
-    const float* rdA1 = sm + (rs == 0 ? 0 : kPlaneA) + (rc < 4 ? 84 * rc : 336);
-    float* rdB = sm + (rs & 1) * kPlaneB + (rc < 4 ? 44 * rc : 176);
-    const int nA4 = rc < 4 ? 21 : 27, nB4 = rc < 4 ? 11 : 27;
+    const int chain = isP ? lane & 3 : 4;
 
     float outx = 0.f, outy = 0.f;
     int st = 1;
@@ -206,33 +220,42 @@ lk_chain_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
         // ---- 2x2 normal matrix: OpenCV's five float chains per sum, replayed by lanes 0..14 -----------
         float A11, A12, A22;
         {
-#pragma unroll
-            for (int t = 0; t < kStripLen; ++t) {
-                sm[oa + t * sa] = Ix[t];
-                sm[kPlaneA + oa + t * sa] = Iy[t];
-            }
-            if (v1) {
+            {
+                const LaneGeo g = lane_geo(lane);
+                float* wx = sm + g.oa;
 #pragma unroll
                 for (int t = 0; t < kStripLen; ++t) {
-                    sm[ob + t * sa] = Ix[kStripLen + t];
-                    sm[kPlaneA + ob + t * sa] = Iy[kStripLen + t];
+                    wx[t * g.sa] = Ix[t];
+                    wx[kPlaneA + t * g.sa] = Iy[t];
                 }
+                if (v1) {
+                    float* wy = sm + g.ob;
+#pragma unroll
+                    for (int t = 0; t < kStripLen; ++t) {
+                        wy[t * g.sa] = Ix[kStripLen + t];
+                        wy[kPlaneA + t * g.sa] = Iy[kStripLen + t];
+                    }
+                }
+                if (lane < 3) { sm[441 + lane] = 0.f; sm[kPlaneA + 441 + lane] = 0.f; }
             }
-            if (lane < 3) { sm[441 + lane] = 0.f; sm[kPlaneA + 441 + lane] = 0.f; }
             __syncwarp();
             float acc = 0.f;
             if (lane < 15) {
-                const float4* a4 = reinterpret_cast<const float4*>(rdA0);
-                const float4* b4 = reinterpret_cast<const float4*>(rdA1);
+                int rs, rc;
+                replay_geo(lane, rs, rc);
+                const int cb = rc < 4 ? 84 * rc : 336;
+                const float4* a4 = reinterpret_cast<const float4*>(sm + (rs == 2 ? kPlaneA : 0) + cb);
+                const float4* b4 = reinterpret_cast<const float4*>(sm + (rs == 0 ? 0 : kPlaneA) + cb);
+                // the products are exact (< 2^24), so fma(a, b, acc) == acc + a * b as OpenCV's mul + add computes it
+#define VSTAB_LK_A_STEP(i) { const float4 a = a4[i], b = b4[i]; acc = __fmaf_rn(a.x, b.x, acc); acc = __fmaf_rn(a.y, b.y, acc); \
+                             acc = __fmaf_rn(a.z, b.z, acc); acc = __fmaf_rn(a.w, b.w, acc); }
 #pragma unroll 3
-                for (int i = 0; i < nA4; ++i) {
-                    const float4 a = a4[i], b = b4[i];
-                    // the products are exact (< 2^24), so fma(a, b, acc) == acc + a * b as OpenCV's mul + add computes it
-                    acc = __fmaf_rn(a.x, b.x, acc);
-                    acc = __fmaf_rn(a.y, b.y, acc);
-                    acc = __fmaf_rn(a.z, b.z, acc);
-                    acc = __fmaf_rn(a.w, b.w, acc);
+                for (int i = 0; i < 21; ++i) VSTAB_LK_A_STEP(i)          // 84 terms: all chains
+                if (rc == 4) {
+#pragma unroll 3
+                    for (int i = 21; i < 27; ++i) VSTAB_LK_A_STEP(i)     // the scalar chain has 105 (+ 3 zero pads)
                 }
+#undef VSTAB_LK_A_STEP
             }
             __syncwarp();
             float s[3];
@@ -282,29 +305,42 @@ lk_chain_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
             for (int t = 0; t < kStripLen; ++t) { q[t] = __ldg(Jp0 + t * P); q[kStripLen + t] = __ldg(Jp1 + t * P); }
             // mismatch I_t = J - I (exact, |.| <= 8160) and the lane's share of b1 = sum I_t Ix, b2 = sum I_t Iy in float: exact
             // while the bound (sum of |terms|, same instruction with the free |.| modifiers) stays below 2^24
-            float fd[2 * kStripLen];
             float acc1 = 0.f, acc2 = 0.f, bn1 = 0.f, bn2 = 0.f;
 #pragma unroll
             for (int s = 0; s < 2 * kStripLen; ++s) {
                 const int jv = dp2a_lo_su(vt01, q[s], dp2a_hi_su(vt23, q[s], 1 << 8)) >> 9;
-                fd[s] = __fsub_rn(__int_as_float(0x4B000000 + jv), Iw[s]);
-                acc1 = __fmaf_rn(fd[s], Ix[s], acc1);
-                acc2 = __fmaf_rn(fd[s], Iy[s], acc2);
-                bn1 = __fmaf_rn(fabsf(fd[s]), fabsf(Ix[s]), bn1);
-                bn2 = __fmaf_rn(fabsf(fd[s]), fabsf(Iy[s]), bn2);
+                const float fd = __fsub_rn(__int_as_float(0x4B000000 + jv), Iw[s]);
+                acc1 = __fmaf_rn(fd, Ix[s], acc1);
+                acc2 = __fmaf_rn(fd, Iy[s], acc2);
+                bn1 = __fmaf_rn(fabsf(fd), fabsf(Ix[s]), bn1);
+                bn2 = __fmaf_rn(fabsf(fd), fabsf(Iy[s]), bn2);
             }
             float b1, b2;
             {
-                const float bl = fmaxf(bn1, bn2);
-                const int bi = bl < kExactBound ? __float2int_ru(bl) : (1 << 24);
-                if (__reduce_add_sync(full, bi) < (int)kExactBound) {
-                    // tier 0: no partial sum of any order reaches 2^24
+                // Every partial sum of a set of terms lies in [-P-, P+] (P+ / P- = sum of its positive / |negative| terms), and the
+                // lane has both for free: P+ = (bound + sum) / 2, P- = (bound - sum) / 2.  Quantised upwards, the larger of b1's and
+                // b2's, packed as two 16-bit fields so that one redux.sync adds both over the warp or over a chain.
+                const bool lane_exact = fmaxf(bn1, bn2) < kExactBound;            // else the lane's own float sums may have rounded
+                const float pp = fmaxf(__fadd_rn(bn1, acc1), __fadd_rn(bn2, acc2));   // 2 P+
+                const float pm = fmaxf(__fsub_rn(bn1, acc1), __fsub_rn(bn2, acc2));   // 2 P-
+                // warp-wide fields in units of 2^15 (<= 513 per lane), chain fields in units of 2^13 (<= 2049 per lane, <= 8 lanes)
+                const int wp = lane_exact ? __float2int_rz(__fmul_rn(pp, 1.f / 65536.f)) + 1 : 600;
+                const int wm = lane_exact ? __float2int_rz(__fmul_rn(pm, 1.f / 65536.f)) + 1 : 600;
+                const unsigned tot = __reduce_add_sync(full, (unsigned)wp | ((unsigned)wm << 16));
+                if ((tot & 0xffffu) <= 511u && (tot >> 16) <= 511u) {
+                    // tier 0: no partial sum of any order reaches 2^24 (511 * 2^15 < 2^24)
                     b1 = (float)__reduce_add_sync(full, __float2int_rn(acc1));
                     b2 = (float)__reduce_add_sync(full, __float2int_rn(acc2));
                 } else {
+                    const int cp = lane_exact ? __float2int_rz(__fmul_rn(pp, 1.f / 16384.f)) + 1 : 2100;
+                    const int cm = lane_exact ? __float2int_rz(__fmul_rn(pm, 1.f / 16384.f)) + 1 : 2100;
+                    const unsigned cpk = (unsigned)cp | ((unsigned)cm << 16);
                     bool ok = true;
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) ok = ok && __reduce_add_sync(full, chain == c ? bi : 0) < (int)kExactBound;
+                    for (int c = 0; c < 5; ++c) {
+                        const unsigned r = __reduce_add_sync(full, chain == c ? cpk : 0u);
+                        ok = ok && (r & 0xffffu) <= 2047u && (r >> 16) <= 2047u;      // 2047 * 2^13 < 2^24
+                    }
                     float e1[5], e2[5];
                     if (ok) {
                         // tier 1: every chain is exact; OpenCV's four float additions on top
@@ -316,35 +352,45 @@ lk_chain_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict_
                         }
                     } else {
                         // tier 2: terms in chain order through shared memory (the integer pair sums of OpenCV's v_dotprod for the
-                        // SIMD chains), then lanes 0..9 replay the sequential float additions
+                        // SIMD chains), then lanes 0..9 replay the sequential float additions.  The taps are read again (L1).
+                        int rs, rc;
+                        replay_geo(lane, rs, rc);
+                        float* rdB = sm + (rs & 1) * kPlaneB + (rc < 4 ? 44 * rc : 176);
                         if (lane < 10) {
                             if (rc < 4) { rdB[42] = 0.f; rdB[43] = 0.f; }
                             else { rdB[105] = 0.f; rdB[106] = 0.f; rdB[107] = 0.f; }
                         }
+                        {
+                            const LaneGeo g = lane_geo(lane);
+                            float* w0 = sm + g.ta;
+                            float* w1 = sm + g.tb;
 #pragma unroll
-                        for (int t = 0; t < kStripLen; ++t) {
-                            const int d0 = __float2int_rn(fd[t]), d1 = __float2int_rn(fd[kStripLen + t]);
-                            const int u1 = d0 * __float2int_rn(Ix[t]), u2 = d0 * __float2int_rn(Iy[t]);
-                            const int g1 = d1 * __float2int_rn(Ix[kStripLen + t]), g2 = d1 * __float2int_rn(Iy[kStripLen + t]);
-                            sm[ta + t * sb] = (float)(isP ? u1 + g1 : u1);
-                            sm[kPlaneB + ta + t * sb] = (float)(isP ? u2 + g2 : u2);
-                            if (!isP && v1) {
-                                sm[tb + t * sb] = (float)g1;
-                                sm[kPlaneB + tb + t * sb] = (float)g2;
+                            for (int t = 0; t < kStripLen; ++t) {
+                                const unsigned qa = __ldg(Jp0 + t * P), qb = __ldg(Jp1 + t * P);
+                                const int d0 = (dp2a_lo_su(vt01, qa, dp2a_hi_su(vt23, qa, 1 << 8)) >> 9) - (__float_as_int(Iw[t]) - 0x4B000000);
+                                const int d1 = (dp2a_lo_su(vt01, qb, dp2a_hi_su(vt23, qb, 1 << 8)) >> 9) - (__float_as_int(Iw[kStripLen + t]) - 0x4B000000);
+                                const int u1 = d0 * __float2int_rn(Ix[t]), u2 = d0 * __float2int_rn(Iy[t]);
+                                const int g1 = d1 * __float2int_rn(Ix[kStripLen + t]), g2 = d1 * __float2int_rn(Iy[kStripLen + t]);
+                                w0[t * g.sb] = (float)(isP ? u1 + g1 : u1);
+                                w0[kPlaneB + t * g.sb] = (float)(isP ? u2 + g2 : u2);
+                                if (!isP && v1) {
+                                    w1[t * g.sb] = (float)g1;
+                                    w1[kPlaneB + t * g.sb] = (float)g2;
+                                }
                             }
                         }
                         __syncwarp();
                         float acc = 0.f;
                         if (lane < 10) {
                             const float4* p4 = reinterpret_cast<const float4*>(rdB);
-#pragma unroll 3
-                            for (int i = 0; i < nB4; ++i) {
-                                const float4 v = p4[i];
-                                acc = __fadd_rn(acc, v.x);
-                                acc = __fadd_rn(acc, v.y);
-                                acc = __fadd_rn(acc, v.z);
-                                acc = __fadd_rn(acc, v.w);
+#define VSTAB_LK_B_STEP(i) { const float4 v = p4[i]; acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w); }
+#pragma unroll 4
+                            for (int i = 0; i < 11; ++i) VSTAB_LK_B_STEP(i)          // 42 pair terms (+ 2 zero pads): all chains
+                            if (rc == 4) {
+#pragma unroll 4
+                                for (int i = 11; i < 27; ++i) VSTAB_LK_B_STEP(i)     // the scalar chain has 105 (+ 3 zero pads)
                             }
+#undef VSTAB_LK_B_STEP
                         }
                         __syncwarp();
 #pragma unroll
@@ -411,14 +457,14 @@ void launch_lk(const uint8_t* prev_pyr, const uint8_t* next_pyr, size_t prev_str
     count_launch(1);
     // One warp per CTA: a CTA's registers and shared memory are held until its slowest feature converges, so one-warp
     // CTAs refill soonest (round 1: 4 / 2 / 1 warps per CTA 1.73 / 1.71 / 1.66 ms per 256 frames).
-    // VSTAB_LK_REGS: 128 (16 CTAs per SM) or 96 (20 CTAs per SM) registers per thread.
+    // VSTAB_LK_REGS: 128 (16 CTAs per SM), 96 (20) or 80 (24) registers per thread.
     static const int regs = [] { const char* r = getenv("VSTAB_LK_REGS"); return r ? atoi(r) : 128; }();
     bool uniform = true;
     for (int l = 1; l < d.nlev; ++l) uniform = uniform && d.pitch[l] == d.pitch[0];
     const int P = uniform ? d.pitch[0] : 0;
 #define VSTAB_LK_ARGS P, nframes, st, prev_pyr, next_pyr, prev_stride, next_stride, d, pts, counts, out_pts, status
     // min blocks per SM = 65536 / (registers * threads per CTA)
-    if (regs == 96) launch_chain<1, 20>(VSTAB_LK_ARGS); else launch_chain<1, 16>(VSTAB_LK_ARGS);
+    if (regs == 80) launch_chain<1, 24>(VSTAB_LK_ARGS); else if (regs == 96) launch_chain<1, 20>(VSTAB_LK_ARGS); else launch_chain<1, 16>(VSTAB_LK_ARGS);
 #undef VSTAB_LK_ARGS
 }
 

@@ -692,12 +692,9 @@ static void launch_orb_body(OrbPlan* P, const uint8_t* gray, OrbKeypoint* kps, u
     // the kept keys reuse the (now free) unsorted candidate buffer
     orb_compact_kernel<<<1, 1024, 0, st>>>(P->cand_sorted, P->counters, P->cap, P->counters + 4, P->cand, count, P->max_kp);
     if (reference_order && L.nlevels_used > 0) {
-        static bool attr = false;
         const int words = 50 * 1024;
-        if (!attr) {
-            cudaFuncSetAttribute(orb_reference_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (words + 1) * 4);
-            attr = true;
-        }
+        static PerDeviceOnce once;
+        once.run([&] { cudaFuncSetAttribute(orb_reference_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (words + 1) * 4); });
         int one = 1;
         cudaMemcpyAsync(P->counters + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st);
         orb_reference_order_kernel<<<L.nlevels_used, 32, (words + 1) * 4, st>>>(P->cand_sorted, P->counters, P->cap, P->hist, L,

@@ -176,8 +176,8 @@ template <int R>
 static void launch_blur_t(const float* src, float* dst, int w, int h, int ki, cudaStream_t st) {
     constexpr int TW = TBX + 2 * R, TH = TBY + 2 * R, TWS = (TW + 3) & ~3;
     constexpr int smem = (int)(sizeof(float) * (TH * TWS + TH * TBX));
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sift_blur_t_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    static PerDeviceOnce once;
+    once.run([] { cudaFuncSetAttribute(sift_blur_t_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     sift_blur_t_kernel<R><<<dim3((w + TBX - 1) / TBX, (h + TBY - 1) / TBY), 256, smem, st>>>(src, dst, w, h, ki);
 }
 
@@ -793,9 +793,9 @@ void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t
 
 static void launch_sift_body(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t* desc, int* count, cudaStream_t st) {
     SiftOctaves& O = *(SiftOctaves*)P->octaves;
-    static bool attr = false;
     const int max_smem = (int)(sizeof(float) * ((GBY + 2 * kMaxRadius) * (GBX + 2 * kMaxRadius) + (GBY + 2 * kMaxRadius) * GBX));
-    if (!attr) { cudaFuncSetAttribute(sift_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); attr = true; }
+    static PerDeviceOnce once;
+    once.run([&] { cudaFuncSetAttribute(sift_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); });
     const int* hr = P->radii;
     auto blur = [&](const float* src, float* dst, int w, int h, int ki, cudaStream_t st) {
         const int R = hr[ki];

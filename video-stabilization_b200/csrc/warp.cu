@@ -180,15 +180,37 @@ VSTAB_D TileBox tile_box(const double* M, const uint8_t* src, size_t pitch, int 
     return bx;
 }
 
-VSTAB_D void store4(uint8_t* __restrict__ o, const unsigned* px, bool vec, int n) {
+// Per-frame output checksum (offline jobs whose output is never downloaded, e.g. BASELINE config 5): over the tight
+// rows of the frame, cut into 12-byte groups (4 pixels, the last group zero-padded) read as three little-endian words,
+//   checksum = sum_y sum_g (y + 1) (g + 1) (w0 + 3 w1 + 5 w2)   mod 2^64
+// (order-free, so every tiling and every shard split gives the same value; numpy twin: vstab_b200.frame_checksum).
+struct RowSums { unsigned long long a0 = 0, a1 = 0, a2 = 0; };
+
+template <bool kCheck>
+VSTAB_D void store4(uint8_t* __restrict__ o, const unsigned* px, bool vec, int n, int y, RowSums& cs) {
+    const unsigned w0 = __byte_perm(px[0], px[1], 0x4210), w1 = __byte_perm(px[1], px[2], 0x5421), w2 = __byte_perm(px[2], px[3], 0x6542);
     if (vec) {
         unsigned* o32 = reinterpret_cast<unsigned*>(o);
-        o32[0] = __byte_perm(px[0], px[1], 0x4210);
-        o32[1] = __byte_perm(px[1], px[2], 0x5421);
-        o32[2] = __byte_perm(px[2], px[3], 0x6542);
+        o32[0] = w0; o32[1] = w1; o32[2] = w2;
+        if (kCheck) {
+            cs.a0 += (unsigned long long)w0 * (unsigned)(y + 1);
+            cs.a1 += (unsigned long long)w1 * (unsigned)(y + 1);
+            cs.a2 += (unsigned long long)w2 * (unsigned)(y + 1);
+        }
     } else {
         for (int k = 0; k < n; ++k) {
             o[3 * k] = (uint8_t)(px[k] & 0xff); o[3 * k + 1] = (uint8_t)((px[k] >> 8) & 0xff); o[3 * k + 2] = (uint8_t)(px[k] >> 16);
+        }
+        if (kCheck) {
+            // bytes beyond pixel n - 1 count as zero
+            const unsigned long long lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+            const int nb = 3 * n;                                         // valid bytes of the 12
+            const unsigned long long mlo = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
+            const unsigned m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
+            const unsigned v0 = (unsigned)(lo & mlo), v1 = (unsigned)((lo & mlo) >> 32), v2 = w2 & m2;
+            cs.a0 += (unsigned long long)v0 * (unsigned)(y + 1);
+            cs.a1 += (unsigned long long)v1 * (unsigned)(y + 1);
+            cs.a2 += (unsigned long long)v2 * (unsigned)(y + 1);
         }
     }
 }
@@ -196,8 +218,9 @@ VSTAB_D void store4(uint8_t* __restrict__ o, const unsigned* px, bool vec, int n
 // The 128 x 32 destination tile at (tx0, ty0): thread (tx, ty) of the 32 x 8 thread tile produces
 // 4 consecutive pixels on each of the rows ty, ty+8, ty+16, ty+24.
 // Interior tile: every tap is in the staged box, M is affine.
+template <bool kCheck>
 VSTAB_D void compute_tile_inside(const uint8_t* __restrict__ sm, const TileBox box, const double* M, int w, int h,
-                                 uint8_t* __restrict__ dst, size_t out_pitch, int tx0, int ty0, int tx, int ty) {
+                                 uint8_t* __restrict__ dst, size_t out_pitch, int tx0, int ty0, int tx, int ty, RowSums& cs) {
     const int x0 = tx0 + tx * 4;
     if (x0 >= w) return;
     const double M0 = M[0], M1 = M[1], M2 = M[2], M3 = M[3], M4 = M[4], M5 = M[5];
@@ -230,15 +253,15 @@ VSTAB_D void compute_tile_inside(const uint8_t* __restrict__ sm, const TileBox b
             const int o = (iY >> 5) * kSP + 3 * (iX >> 5) + obase;
             px[i] = staged_pixel(sm, o, iX & 31, iY & 31);
         }
-        store4(orow, px, vec, min(4, w - x0));
+        store4<kCheck>(orow, px, vec, min(4, w - x0), y, cs);
     }
 }
 
 // Any tile: per-pixel test against the staged box (may be empty), generic_pixel otherwise.
-template <bool kAffine>
+template <bool kAffine, bool kCheck>
 VSTAB_D void compute_tile_border(const uint8_t* __restrict__ sm, const TileBox box, const double* M, const int* border,
                                  const uint8_t* __restrict__ src, size_t pitch, int w, int h,
-                                 uint8_t* __restrict__ dst, size_t out_pitch, int tx0, int ty0, int tx, int ty) {
+                                 uint8_t* __restrict__ dst, size_t out_pitch, int tx0, int ty0, int tx, int ty, RowSums& cs) {
     const int x0 = tx0 + tx * 4;
     if (x0 >= w) return;
     const double M0 = M[0], M1 = M[1], M2 = M[2], M3 = M[3], M4 = M[4], M5 = M[5], M6 = M[6], M7 = M[7], M8 = M[8];
@@ -276,20 +299,31 @@ VSTAB_D void compute_tile_border(const uint8_t* __restrict__ sm, const TileBox b
             else
                 px[i] = generic_pixel(src, pitch, w, h, al_ok, iX, iY, border);
         }
-        store4(dst + (size_t)y * out_pitch + (size_t)x0 * 3, px, vec, min(4, w - x0));
+        store4<kCheck>(dst + (size_t)y * out_pitch + (size_t)x0 * 3, px, vec, min(4, w - x0), y, cs);
     }
 }
 
-// One destination tile, whichever path it needs.
+// One destination tile, whichever path it needs.  kCheck: the thread's share of the frame checksum goes to *check
+// (one 64-bit atomic per warp).
+template <bool kCheck>
 VSTAB_D void compute_tile(const uint8_t* __restrict__ sm, const TileBox box, const double* M, const int* border,
                           const uint8_t* __restrict__ src, size_t pitch, int w, int h,
-                          uint8_t* __restrict__ dst, size_t out_pitch, int tx0, int ty0, int tx, int ty) {
+                          uint8_t* __restrict__ dst, size_t out_pitch, int tx0, int ty0, int tx, int ty,
+                          unsigned long long* check) {
+    RowSums cs;
     if (box.inside)
-        compute_tile_inside(sm, box, M, w, h, dst, out_pitch, tx0, ty0, tx, ty);
+        compute_tile_inside<kCheck>(sm, box, M, w, h, dst, out_pitch, tx0, ty0, tx, ty, cs);
     else if (M[6] == 0.0 && M[7] == 0.0 && M[8] != 0.0)
-        compute_tile_border<true>(sm, box, M, border, src, pitch, w, h, dst, out_pitch, tx0, ty0, tx, ty);
+        compute_tile_border<true, kCheck>(sm, box, M, border, src, pitch, w, h, dst, out_pitch, tx0, ty0, tx, ty, cs);
     else
-        compute_tile_border<false>(sm, box, M, border, src, pitch, w, h, dst, out_pitch, tx0, ty0, tx, ty);
+        compute_tile_border<false, kCheck>(sm, box, M, border, src, pitch, w, h, dst, out_pitch, tx0, ty0, tx, ty, cs);
+    if (kCheck) {
+        const unsigned long long g1 = (unsigned long long)((tx0 + tx * 4) >> 2) + 1ull;
+        unsigned long long c = (tx0 + tx * 4 < w) ? (cs.a0 + 3ull * cs.a1 + 5ull * cs.a2) * g1 : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (tx == 0) atomicAdd(check, c);
+    }
 }
 
 VSTAB_D void fill_tile_info(TileInfo& I, const WarpParams& P, const uint8_t* frames, size_t frame_stride, long slot_mod) {
@@ -301,10 +335,11 @@ VSTAB_D void fill_tile_info(TileInfo& I, const WarpParams& P, const uint8_t* fra
 }
 
 // ---- variant 0: one CTA per tile ----------------------------------------------------------------------------
+template <bool kCheck>
 __global__ void __launch_bounds__(NTX * NTY, 4)
 warp_tile_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t frame_stride, long slot_mod,
                  const WarpParams* __restrict__ wps, int w, int h,
-                 uint8_t* __restrict__ out, size_t out_pitch, size_t out_frame_stride) {
+                 uint8_t* __restrict__ out, size_t out_pitch, size_t out_frame_stride, unsigned long long* __restrict__ check) {
     __shared__ __align__(128) uint4 stage[kStageStride / 16];
     __shared__ TileInfo I;
     const int oi = blockIdx.z;
@@ -331,8 +366,8 @@ warp_tile_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t frame_
     }
     __syncthreads();
     uint8_t* dst = out + (size_t)oi * out_frame_stride;
-    compute_tile(reinterpret_cast<const uint8_t*>(stage), box, I.M, I.border, I.src, pitch, w, h, dst, out_pitch, tx0, ty0,
-                 threadIdx.x, threadIdx.y);
+    compute_tile<kCheck>(reinterpret_cast<const uint8_t*>(stage), box, I.M, I.border, I.src, pitch, w, h, dst, out_pitch, tx0, ty0,
+                         threadIdx.x, threadIdx.y, kCheck ? check + oi : nullptr);
 }
 
 // ---- variant 1: persistent, TMA-fed ------------------------------------------------------------------------
@@ -449,7 +484,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_wait(&S.full[s], (it / kStages) & 1);
         const TileInfo& I = S.info[s];
         uint8_t* dst = out + (size_t)I.oi * out_frame_stride;
-        compute_tile(S.stage[s], I.box, I.M, I.border, I.src, pitch, w, h, dst, out_pitch, I.tx0, I.ty0, tx, ty);
+        compute_tile<false>(S.stage[s], I.box, I.M, I.border, I.src, pitch, w, h, dst, out_pitch, I.tx0, I.ty0, tx, ty, nullptr);
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.empty[s]);            // this warp is done reading stage s
     }
@@ -498,30 +533,29 @@ bool make_maps(TmaMaps& m, const uint8_t* frames, size_t pitch, size_t frame_str
 
 void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long slot_mod,
                  const WarpParams* wp, int nout, int w, int h,
-                 uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st) {
+                 uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st, unsigned long long* check) {
     if (nout <= 0) return;
-    static int num_sms = 0, variant = 0, ctas_per_sm = 4;
+    static const int variant = getenv("VSTAB_WARP_VARIANT") ? atoi(getenv("VSTAB_WARP_VARIANT")) : 0;
+    static const int ctas_per_sm = getenv("VSTAB_WARP_CTAS") && atoi(getenv("VSTAB_WARP_CTAS")) > 0 ? atoi(getenv("VSTAB_WARP_CTAS")) : 4;
     static thread_local TmaMaps maps;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem));
-        if (num_sms <= 0) num_sms = 148;
-        if (const char* e = getenv("VSTAB_WARP_VARIANT")) variant = atoi(e);
-        if (const char* e = getenv("VSTAB_WARP_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 4;
-    }
+    static PerDeviceOnce once;
+    once.run([] { cudaFuncSetAttribute(warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)); });
+    const int num_sms = device_sm_count();
     count_launch(1);
     const long ntiles = (long)((w + TW - 1) / TW) * ((h + TH - 1) / TH) * nout;
-    if (variant == 1 && make_maps(maps, frames, pitch, frame_stride, h)) {
+    if (variant == 1 && !check && make_maps(maps, frames, pitch, frame_stride, h)) {
         const int grid = (int)(ntiles < (long)num_sms * ctas_per_sm ? ntiles : (long)num_sms * ctas_per_sm);
         warp_tma_kernel<<<grid, kThreads, sizeof(WarpSmem), st>>>(maps.a, maps.b, frames, pitch, frame_stride, slot_mod, wp, nout,
                                                                   w, h, out, out_pitch, out_frame_stride);
         return;
     }
     dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, nout);
-    warp_tile_kernel<<<grid, dim3(NTX, NTY), 0, st>>>(frames, pitch, frame_stride, slot_mod, wp, w, h, out, out_pitch,
-                                                      out_frame_stride);
+    if (check)
+        warp_tile_kernel<true><<<grid, dim3(NTX, NTY), 0, st>>>(frames, pitch, frame_stride, slot_mod, wp, w, h, out, out_pitch,
+                                                                out_frame_stride, check);
+    else
+        warp_tile_kernel<false><<<grid, dim3(NTX, NTY), 0, st>>>(frames, pitch, frame_stride, slot_mod, wp, w, h, out, out_pitch,
+                                                                 out_frame_stride, nullptr);
 }
 
 }  // namespace vstabk

@@ -17,7 +17,8 @@ import numpy as np
 
 ACCUMULATED_FULL_LOCK, ORB_FULL_LOCK, SIFT_FULL_LOCK, TRANSLATION_LOCK, ROTATION_LOCK, GLOBAL_SMOOTHING = range(6)
 
-OK, ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = range(6)
+OK, ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NCCL = range(7)
+SRC_HOST, SRC_SIMULATOR = 0, 1
 
 TAP_GRAY, TAP_PYR1, TAP_PYR2, TAP_PYR3, TAP_PREV_PTS, TAP_LK_PTS, TAP_LK_STATUS, TAP_NEW_PTS, TAP_T, TAP_M, \
     TAP_H_STABILIZE, TAP_H_SCALED, TAP_BORDER, TAP_EIG, TAP_INLIERS, TAP_CHANNEL_SUMS, TAP_LOCK_H, TAP_ORB_COUNTS, \
@@ -35,6 +36,28 @@ class HParams(C.Structure):
     """struct HomographyParameters, include/stabilizer.hpp:44-57"""
     _fields_ = [("s", C.c_double), ("theta", C.c_double), ("k", C.c_double), ("delta", C.c_double),
                 ("t", C.c_double * 2), ("v", C.c_double * 2)]
+
+
+class NcclId(C.Structure):
+    _fields_ = [("bytes", C.c_char * 128)]
+
+
+class ShardPlan(C.Structure):
+    _fields_ = [("first", C.c_long), ("last", C.c_long), ("call_first", C.c_long), ("call_last", C.c_long)]
+
+
+class OfflineCfg(C.Structure):          # vstab_offline_cfg
+    _fields_ = [("n_total", C.c_long), ("mode", C.c_int), ("lock_call", C.c_long), ("source", C.c_int),
+                ("host_frames", C.c_void_p), ("frame_stride", C.c_size_t), ("step", C.c_size_t), ("host_halo", C.c_void_p),
+                ("d_texture", C.c_void_p), ("tex_rows", C.c_int), ("tex_cols", C.c_int), ("poses", C.POINTER(C.c_double)),
+                ("focal", C.c_double),
+                ("host_out", C.c_void_p), ("out_frame_stride", C.c_size_t), ("out_step", C.c_size_t),
+                ("checksums", C.POINTER(C.c_uint64)), ("T_all", C.POINTER(C.c_double))]
+
+
+class OfflineReport(C.Structure):       # vstab_offline_report
+    _fields_ = [("source_ms", C.c_float), ("estimate_ms", C.c_float), ("exchange_ms", C.c_float), ("render_ms", C.c_float),
+                ("total_ms", C.c_float), ("frames", C.c_long), ("calls", C.c_long)]
 
 
 _u8p = C.POINTER(C.c_uint8)
@@ -77,6 +100,12 @@ SYMBOLS = {
     "vstab_offline_register": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
     "vstab_offline_set_registrations": (C.c_int, [_vp, _vp, C.c_long]),
     "vstab_offline_synchronize": (C.c_int, [_vp]),
+    "vstab_offline_last_error": (C.c_char_p, [_vp]),
+    "vstab_nccl_get_unique_id": (C.c_int, [C.POINTER(NcclId)]),
+    "vstab_offline_comm_init": (C.c_int, [_vp, C.POINTER(NcclId), C.c_int, C.c_int]),
+    "vstab_offline_plan": (C.c_int, [C.c_long, C.c_int, C.c_int, C.c_size_t, C.POINTER(ShardPlan)]),
+    "vstab_offline_run": (C.c_int, [_vp, C.POINTER(OfflineCfg), C.POINTER(OfflineReport)]),
+    "vstab_frame_checksum": (C.c_uint64, [_vp, C.c_int, C.c_int, C.c_size_t]),
     "vstab_offline_prepare": (C.c_int, [_vp, _vp, C.c_long, C.c_int, C.c_long]),
     "vstab_offline_set_timing": (None, [_vp, C.c_int]),
     "vstab_offline_stage_times": (C.c_int, [_vp, _f32p, C.POINTER(C.c_int)]),
@@ -126,11 +155,11 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(_vp)
 
 
-def _check(st: int, handle=None):
+def _check(st: int, handle=None, offline: bool = False):
     if st == OK:
         return
     lib = load_library()
-    msg = lib.vstab_last_error(handle)
+    msg = lib.vstab_offline_last_error(handle) if offline else lib.vstab_last_error(handle)
     msg = msg.decode() if msg else lib.vstab_status_string(st).decode()
     if st in (ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED):
         raise ValueError(msg)                # std::invalid_argument in the reference
@@ -139,6 +168,21 @@ def _check(st: int, handle=None):
     if st == ERR_STATE:
         raise AssertionError(msg)            # the reference asserts (stabilizer.cpp:329)
     raise VstabError(msg)
+
+
+def frame_checksum(img: np.ndarray) -> int:
+    """The per-frame output checksum the warp kernel accumulates (csrc/warp.cu, include/vstab.h vstab_frame_checksum):
+    rows cut into 12-byte groups (4 pixels, zero-padded) read as three little-endian words,
+    sum_y sum_g (y + 1)(g + 1)(w0 + 3 w1 + 5 w2) mod 2^64.  numpy twin of the C function."""
+    h, w, _ = img.shape
+    wp = (w + 3) // 4 * 4
+    row = np.zeros((h, wp * 3), np.uint8)
+    row[:, :w * 3] = img.reshape(h, -1)
+    wd = row.view("<u4").reshape(h, wp // 4, 3).astype(np.uint64)
+    t = wd[..., 0] + np.uint64(3) * wd[..., 1] + np.uint64(5) * wd[..., 2]
+    with np.errstate(over="ignore"):
+        t = t * (np.arange(h, dtype=np.uint64) + np.uint64(1))[:, None] * (np.arange(wp // 4, dtype=np.uint64) + np.uint64(1))[None, :]
+        return int(t.sum(dtype=np.uint64))
 
 
 @dataclass

@@ -18,7 +18,13 @@ from __future__ import annotations
 
 import ctypes as C
 
-from . import (ACCUMULATED_FULL_LOCK, GLOBAL_SMOOTHING, _check, _vp, load_library)  # noqa: F401
+from . import (ACCUMULATED_FULL_LOCK, GLOBAL_SMOOTHING, SRC_HOST, SRC_SIMULATOR, NcclId, OfflineCfg, OfflineReport,  # noqa: F401
+               ShardPlan, _vp, load_library)
+from . import _check as _check_any
+
+
+def _check(st, handle=None):
+    _check_any(st, handle, offline=True)        # messages of offline instances come from vstab_offline_last_error
 
 
 # ----------------------------------------------------------------------------------------------
@@ -124,6 +130,69 @@ class OfflineStabilizer:
         estimation, warps and downloads; returns when the output buffer is complete."""
         _check(self._lib.vstab_offline_run_host(self._h, _vp(frames_ptr), frame_stride, step, n_total, mode, lock_call,
                                                 _vp(out_ptr), out_frame_stride, out_step), self._h)
+
+    # ---- the whole sharded job in the library (vstab_offline_run: NCCL all-gather inside) ---------------------
+    def comm_init(self, rank: int, world: int, group=None):
+        """Join the library-side NCCL communicator of the job: rank 0 makes the id, torch.distributed (any backend)
+        only carries its 128 bytes to the other ranks."""
+        import torch.distributed as dist
+        nid = NcclId()
+        if world > 1:
+            if rank == 0:
+                _check(self._lib.vstab_nccl_get_unique_id(C.byref(nid)))
+            box = [bytes(nid.bytes) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            C.memmove(C.byref(nid), box[0], 128)
+            _check(self._lib.vstab_offline_comm_init(self._h, C.byref(nid), rank, world), self._h)
+        self.rank, self.world = rank, world
+
+    def plan(self, n_total: int):
+        pl = ShardPlan()
+        _check(self._lib.vstab_offline_plan(n_total, getattr(self, "world", 1), getattr(self, "rank", 0), self.F, C.byref(pl)))
+        return pl.first, pl.last, pl.call_first, pl.call_last
+
+    def run(self, n_total: int, mode: int, lock_call: int = 0, *, texture=None, poses=None, focal: float = 0.0,
+            host_frames=None, host_halo=None, host_out=None, want_checksums: bool = True, want_T: bool = False):
+        """vstab_offline_run: this rank's share of a clip of n_total frames.  Source: `texture` (uint8 CUDA tensor
+        [th, tw, 3]) + `poses` (float64 [n_total, 6]) for the device simulator, or `host_frames` (uint8 numpy / pinned
+        tensor [n_local, rows, cols, 3], + `host_halo` [rows, cols, 3] on ranks > 0).  Returns a dict with the report,
+        `checksums` (uint64 numpy, one per call of this rank) and optionally `T` [n_total, 3, 3]."""
+        import numpy as np
+        cfg = OfflineCfg()
+        cfg.n_total, cfg.mode, cfg.lock_call = n_total, mode, lock_call
+        keep = []
+        if texture is not None:
+            poses = np.ascontiguousarray(poses, np.float64)
+            assert poses.shape == (n_total, 6) and texture.is_cuda and texture.is_contiguous()
+            cfg.source = SRC_SIMULATOR
+            cfg.d_texture, cfg.tex_rows, cfg.tex_cols = texture.data_ptr(), texture.shape[0], texture.shape[1]
+            cfg.poses, cfg.focal = poses.ctypes.data_as(C.POINTER(C.c_double)), float(focal)
+            keep.append(poses)
+        else:
+            cfg.source = SRC_HOST
+            ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+            strides = lambda a: (a.stride(0), a.stride(1)) if hasattr(a, "data_ptr") else (a.strides[0], a.strides[1])
+            cfg.host_frames = ptr(host_frames)
+            cfg.frame_stride, cfg.step = strides(host_frames)
+            cfg.host_halo = ptr(host_halo) if host_halo is not None else None
+        first, last, c0, c1 = self.plan(n_total)
+        if host_out is not None:
+            assert host_out.shape[0] >= c1 - c0
+            cfg.host_out = host_out.data_ptr() if hasattr(host_out, "data_ptr") else host_out.ctypes.data
+            cfg.out_frame_stride, cfg.out_step = (host_out.stride(0), host_out.stride(1)) if hasattr(host_out, "data_ptr") \
+                else (host_out.strides[0], host_out.strides[1])
+        sums = np.zeros(max(c1 - c0, 1), np.uint64)
+        if want_checksums:
+            cfg.checksums = sums.ctypes.data_as(C.POINTER(C.c_uint64))
+        T = np.zeros((n_total, 9)) if want_T else None
+        if want_T:
+            cfg.T_all = T.ctypes.data_as(C.POINTER(C.c_double))
+        rep = OfflineReport()
+        _check(self._lib.vstab_offline_run(self._h, C.byref(cfg), C.byref(rep)), self._h)
+        out = {k: getattr(rep, k) for k, _ in OfflineReport._fields_}
+        out.update(first=first, last=last, call_first=c0, call_last=c1, checksums=sums[:c1 - c0] if want_checksums else None,
+                   T=T.reshape(-1, 3, 3) if want_T else None)
+        return out
 
     # ---- ORB / SIFT registration (frame-independent units + one broadcast + one all-gather) -----------
     def capture_reference(self, frame, mode: int):
