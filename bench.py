@@ -50,6 +50,48 @@ WORKLOAD = "c2_lk_full_lock_1080p_wh360_window60_45"
 PATH_DRIFT = 0.0
 
 
+def shared_config():
+    """The part of `config` both arms (ours / --impl reference) print identically."""
+    return {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST, "future": FUTURE,
+            "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL,
+            "camera_path": "survey 8d jitter+sinusoid+roll, drift 0",
+            "l2_policy": "inputs_exceed_l2 (every step reads its frames from memory: ours 512 x 6.2 MB of frames per GPU per "
+                         "step vs 126 MB of L2; reference arm 48 distinct 1080p frames = 299 MB vs the host's last-level cache)"}
+
+
+def pin_to_gpu_numa_node(torch, local):
+    """Bind this process (and therefore its pinned allocations, first touch) to the CPU cores / NUMA node the GPU hangs off
+    (/sys/bus/pci/devices/<bdf>/local_cpulist).  Returns a description for the JSON line."""
+    info = {"bound": False}
+    try:
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bdf is None:
+            import ctypes as CC
+            rt = CC.CDLL("libcudart.so.12")
+            buf = CC.create_string_buffer(32)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, local) == 0:
+                bdf = buf.value.decode()
+        if not bdf:
+            return info
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"bound": True, "pci": bdf, "numa_node": node, "cpus": cpulist, "n_cpus": len(allowed)}
+    except Exception as e:          # no sysfs / no permission: run unbound and say so
+        info["error"] = str(e)[:80]
+    return info
+
+
 def working_width():
     return int(W * (WH / H))
 
@@ -167,14 +209,14 @@ class CpuArm:
     """Streams the workload through oracle.StabilizerRef (the reference's per-frame loop over the
     same OpenCV kernels, all quirks kept incl. GFTT twice and the three full-frame clones)."""
 
-    def __init__(self, frames):
+    def __init__(self, frames, faithful_waste=True):
         import cv2
         from oracle import stabilizer_ref as sr
         cv2.setNumThreads(os.cpu_count() or 1)
         self.cores = int(cv2.getNumThreads())
         self.sr = sr
         self.frames = frames
-        self.ref = sr.StabilizerRef(PAST, FUTURE, WH, faithful_waste=True)
+        self.ref = sr.StabilizerRef(PAST, FUTURE, WH, faithful_waste=faithful_waste)
         self.ref.collect_taps = False
         self.i = 0
 
@@ -209,9 +251,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST, "future": FUTURE,
-                   "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL, "frames_per_step": per_step,
-                   "camera_path": "survey 8d jitter+sinusoid+roll, drift 0"},
+        "config": shared_config(),
+        "run": {"frames_per_step": per_step, "distinct_frames": n_distinct},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -242,8 +283,11 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    vs.load_library()
     lib = vs.load_library()
+    numa = pin_to_gpu_numa_node(torch, local)       # before any pinned allocation: first touch decides the NUMA node
+
+    if args.workload == "c5":
+        return run_c5_line(args, torch, dist, vs, rank, world, local, numa)
 
     n_local = args.frames_per_gpu
     n_total = n_local * world
@@ -265,22 +309,16 @@ def run_ours(args):
     frames = buf[1:] if has_halo else buf[:n_local]
     halo = buf[0] if has_halo else None
     out = torch.empty((max(ncalls, 1), H, W, 3), dtype=torch.uint8, device=dev)
-    T_local = torch.zeros((pad, 9), dtype=torch.float64, device=dev)
-    sums = torch.zeros((n_local, 3), dtype=torch.int64, device=dev)
 
     off = offline.OfflineStabilizer(PAST, FUTURE, WH, H, W, args.batch, device=local)
+    off.comm_init(rank, world)                      # library-side NCCL communicator (the id travels over torch.distributed)
     mode = vs.ACCUMULATED_FULL_LOCK
+    last_run = {}
 
     def step():
-        off.estimate(frames, first, halo, T_local, sums)
-        if world > 1:
-            with torch.cuda.stream(off.stream):
-                T_all = offline.gather_transforms(T_local, n_total, world)
-        else:
-            T_all = T_local[:n_total]
-        off.prepare(T_all, mode, LOCK_CALL)
-        if ncalls > 0:
-            off.render(frames, first, c0, ncalls, T_all, mode, LOCK_CALL, sums, out)
+        # the whole sharded job behind one C-ABI call: estimate -> ncclAllGather of 72 B/frame (inside the library) ->
+        # prefix scan -> smooth + warp; frames and outputs resident in HBM, per-call checksums fused into the warp
+        last_run.update(off.run(n_total, mode, LOCK_CALL, device_frames=frames, device_halo=halo, device_out=out))
 
     def barrier():
         if world > 1:
@@ -361,10 +399,30 @@ def run_ours(args):
         arm.run(50)
         ncpu = args.cpu_sample_frames
         t = arm.run(ncpu)
+        lean = CpuArm(host_frames, faithful_waste=False)
+        lean.run(50)
+        nlean = max(ncpu // 2, 50)
+        tl = lean.run(nlean)
         cpu = {"value": ncpu / t, "unit": UNIT, "cores": arm.cores, "kind": "port",
                "sample": f"{ncpu} stabilizeFrame calls after 50 warm-up calls over the first {nd} frames of the clip "
                          f"(ping-pong), oracle.StabilizerRef over cv2 with {arm.cores} threads; host has "
-                         f"{os.cpu_count()} logical cores"}
+                         f"{os.cpu_count()} logical cores",
+               # the reference minus its obvious waste, so the speed-up is not inflated by it
+               "without_reference_waste": {"value": nlean / tl, "unit": UNIT,
+                                           "what": "goodFeaturesToTrack once per frame instead of twice, no full-frame clones",
+                                           "sample": f"{nlean} calls after 50 warm-up calls, same frames"}}
+
+    # ---- BASELINE config 5 (4K, simulator source, sharded over the ranks): bounded probe at every N -------------
+    c5 = None
+    if not args.no_c5_probe:
+        halo = None
+        del buf, frames, out
+        torch.cuda.empty_cache()
+        c5 = run_c5(args, torch, dist, vs, rank, world, local, args.c5_probe_frames, args.c5_batch)
+
+    parity = None
+    if world == 1 and rank == 0 and not args.no_parity:
+        parity = run_parity(args, torch, local)
 
     modes, modes_offline = None, None
     if world == 1 and rank == 0 and not args.no_mode_probes:
@@ -377,20 +435,129 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "resolution": [W, H], "working_height": WH, "past": PAST,
-                       "future": FUTURE, "mode": "ACCUMULATED_FULL_LOCK", "lock_call": LOCK_CALL,
-                       "frames_per_gpu": n_local, "frames_total": n_total, "batch": args.batch,
-                       "camera_path": "survey 8d jitter+sinusoid+roll, drift 0",
-                       "l2_policy": f"inputs_exceed_l2 ({n_local * 3 * W * H / 1e6:.0f} MB of frames per GPU per step vs 126 MB L2)",
-                       "parallelism": f"frame-sharded x{world}, one all-gather of 72 B/frame" if world > 1 else "single GPU"},
-            "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "other_modes_streaming": modes, "other_modes_offline": modes_offline,
+            "config": shared_config(),
+            "run": {"frames_per_gpu": n_local, "frames_total": n_total, "batch": args.batch,
+                    "api": "vstab_offline_run (VSTAB_SRC_DEVICE: shard and outputs resident in HBM)",
+                    "parallelism": (f"frame-sharded x{world}, one ncclAllGather of 72 B/frame inside libvstab.so"
+                                    if world > 1 else "single GPU"),
+                    "numa": numa,
+                    "checksum_xor_of_calls_rank0": f"{int(np.bitwise_xor.reduce(last_run['checksums'])) if len(last_run.get('checksums', [])) else 0:016x}"},
+            "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
+            "gpu_launches": int(launches), "clocks": clocks, "c5_probe": c5,
+            "other_modes_streaming": modes, "other_modes_offline": modes_offline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+C5 = dict(W=3840, H=2160, WH=360, mode="GLOBAL_SMOOTHING")
+
+
+def run_c5(args, torch, dist, vs, rank, world, local, n_total, batch):
+    """BASELINE config 5: offline stabilization of a synthetic 4K clip of n_total frames, frame-sharded over the ranks.
+    Nothing of the clip is stored: every chunk is rendered on the device by the simulator kernel (K13), in both passes
+    of vstab_offline_run (estimate -> ncclAllGather of the 3x3 transforms -> window average -> warp); the output of every
+    call is reduced to a 64-bit checksum inside the warp kernel.  Strong scaling: the clip is fixed, ranks split it."""
+    from vstab_b200 import offline, synth
+    w, h, wh = C5["W"], C5["H"], C5["WH"]
+    dev = torch.device("cuda", local)
+    tex = torch.from_numpy(synth.make_texture(2048)).to(dev)
+    poses = synth.camera_path(n_total)                       # the survey's path incl. its drift (smoothing follows it)
+    off = offline.OfflineStabilizer(PAST, FUTURE, wh, h, w, batch, device=local)
+    off.comm_init(rank, world)
+    mode = getattr(vs, C5["mode"])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = off.run(n_total, mode, 0, texture=tex, poses=poses, focal=synth.focal_for_width(w))
+    wall = time.perf_counter() - t0
+    off.close()
+    cs = int(np.bitwise_xor.reduce(r["checksums"])) if len(r["checksums"]) else 0
+    sm = int(r["checksums"].sum(dtype=np.uint64)) if len(r["checksums"]) else 0
+    t = torch.tensor([r["total_ms"], r["source_ms"], r["estimate_ms"], r["exchange_ms"], r["render_ms"], wall * 1e3],
+                     dtype=torch.float64, device=dev)
+    acc = torch.tensor([cs - (1 << 64) if cs >= (1 << 63) else cs, sm - (1 << 64) if sm >= (1 << 63) else sm],
+                       dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parts = [torch.zeros_like(acc) for _ in range(world)]
+        dist.all_gather(parts, acc)
+    else:
+        parts = [acc]
+    x, sacc = 0, 0
+    for pt in parts:
+        a, b = int(pt[0].item()) & ((1 << 64) - 1), int(pt[1].item()) & ((1 << 64) - 1)
+        x ^= a
+        sacc = (sacc + b) & ((1 << 64) - 1)
+    ms = [float(v) for v in t.tolist()]
+    B = 3 * w * h
+    calls = n_total
+    return {"workload": f"c5_offline_4k_wh{wh}_{C5['mode'].lower()}_{n_total}_frames", "frames_total": n_total,
+            "resolution": [w, h], "working_height": wh, "window": [PAST, FUTURE], "batch": batch,
+            "value": n_total / (ms[0] * 1e-3), "unit": UNIT, "scaling": "strong", "n_gpus": world,
+            "ms_total_max_over_ranks": ms[0], "wall_ms_max_over_ranks": ms[5],
+            "phases_ms_max_over_ranks": {"simulator_render_both_passes": ms[1], "estimate": ms[2],
+                                         "exchange_allgather_plus_prefix": ms[3], "smooth_warp_checksum": ms[4]},
+            "value_without_frame_synthesis": n_total / (max(ms[0] - ms[1], 1e-6) * 1e-3),
+            "warp_hbm_gbs": 2 * B * (calls / world) / (ms[4] * 1e-3) / 1e9 if ms[4] > 0 else None,
+            "checksum_xor_of_calls": f"{x:016x}", "checksum_sum_of_calls": f"{sacc:016x}",
+            "resident_frames_max": batch + 1,
+            "api": "vstab_offline_run (VSTAB_SRC_SIMULATOR; library-side ncclAllGather; checksums fused into the warp)"}
+
+
+def run_c5_line(args, torch, dist, vs, rank, world, local, numa):
+    """`--workload c5`: BASELINE config 5 as the line's workload.  One step = the whole clip (default 100 000 4K frames)."""
+    for _ in range(args.warmup):
+        run_c5(args, torch, dist, vs, rank, world, local, min(1024, args.c5_frames), args.c5_batch)
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib = vs.load_library()
+    launches0 = lib.vstab_launch_count()
+    runs = [run_c5(args, torch, dist, vs, rank, world, local, args.c5_frames, args.c5_batch) for _ in range(args.steps)]
+    launches = lib.vstab_launch_count() - launches0
+    clocks = sampler.stop()
+    ms = sum(r["ms_total_max_over_ranks"] for r in runs)
+    r = runs[-1]
+    peak, peak_src = measured_peak()
+    if rank == 0:
+        line = {"metric": "stabilized_frames_per_sec_4k_offline_sharded", "value": args.c5_frames * args.steps / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+                "config": {"workload": r["workload"], "resolution": r["resolution"], "working_height": r["working_height"],
+                           "past": PAST, "future": FUTURE, "mode": C5["mode"], "frames_total": args.c5_frames,
+                           "camera_path": "survey 8d (with drift)", "batch": args.c5_batch,
+                           "l2_policy": "inputs_exceed_l2 (every chunk of 32 4K frames = 796 MB is rendered, read and dropped)"},
+                "roofline": {"bound": "hbm", "kernel": "warp", "achieved": r["warp_hbm_gbs"], "peak": peak, "unit": "GB/s",
+                             "frac": (r["warp_hbm_gbs"] or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "smooth + warp + checksum phase of the job, algorithmic 2 x 3WH bytes per frame"},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "c5": r, "run": {"numa": numa},
+                "note": "e2e: none -- the clip (2.5 TB) exists only on the device, chunk by chunk; the output is checksummed"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_parity(args, torch, local):
+    """A bounded parity run of the headline configuration against the oracle, so that the line carries what the
+    north-star tolerances look like on this very build (full-length runs: tools/parity_report.py, profiles/)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_report
+    try:
+        r = parity_report.run("c2", args.parity_frames, check_render=0)
+    except Exception as e:      # the line must still be printed
+        return {"error": str(e)[:200]}
+    keep = ("config", "frames", "h_px", "t_px", "t_bit_equal", "lk_bit_equal", "calls", "max_lsb", "px_gt1", "frames_gt1",
+            "frac_gt1", "px_differ", "px_total")
+    out = {k: r[k] for k in keep}
+    out["tolerances"] = {"lk_px": 0.05, "h_px": 0.1, "pixels_lsb": 1}
+    out["oracle"] = "oracle.StabilizerRef (cv2 restatement of the reference), same frames"
+    return out
 
 
 def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
@@ -456,8 +623,13 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
     st.close()
     lib.vstab_host_free(C.c_void_p(hin))
     lib.vstab_host_free(C.c_void_p(hout))
+    per_gpu_gbs = n_clip * nbytes * args.steps / dt_clip / 1e9
     return {"value": world * n_clip * args.steps / dt_clip, "unit": UNIT,
             "h2d_bytes_per_step": n_clip * nbytes, "d2h_bytes_per_step": n_clip * nbytes,
+            # every frame crosses PCIe once per direction, both directions at the same time: the leg is bound by the link
+            "pcie": {"gbs_per_direction_per_gpu": per_gpu_gbs, "frac_of_gen5_x16": per_gpu_gbs / 63.0,
+                     "peak": "63.0 GB/s per direction nominal (PCIe Gen5 x16); ~55 GB/s is what pinned cudaMemcpy reaches"},
+            "replicas": world,
             "api": "vstab_offline_run_host (whole clip of pinned host frames in/out, pipelined H2D / compute / D2H)",
             "frames_per_step": n_clip, "timer": "host wall clock around the synchronous call, max over ranks",
             "streaming": {"value": world * per_step * args.steps / dt_stream, "unit": UNIT,
@@ -626,6 +798,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--no-mode-probes", action="store_true", help="skip the ORB / SIFT streaming figures")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE config 5 as the line's workload")
+    ap.add_argument("--c5-frames", type=int, default=100000, help="--workload c5: frames of the 4K clip (whole job)")
+    ap.add_argument("--c5-probe-frames", type=int, default=2048, help="frames of the bounded config-5 probe in the default run")
+    ap.add_argument("--c5-batch", type=int, default=32, help="frames per chunk of the config-5 job")
+    ap.add_argument("--no-c5-probe", action="store_true")
+    ap.add_argument("--parity-frames", type=int, default=160, help="frames of the bounded parity run against the oracle")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

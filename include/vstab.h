@@ -233,19 +233,21 @@ vstab_status vstab_offline_comm_init(vstab_offline_t* o, const vstab_nccl_id* id
 typedef struct vstab_shard_plan { long first, last, call_first, call_last; } vstab_shard_plan;
 vstab_status vstab_offline_plan(long n_total, int world, int rank, size_t future_frames, vstab_shard_plan* out);
 
-typedef enum vstab_frame_source { VSTAB_SRC_HOST = 0, VSTAB_SRC_SIMULATOR = 1 } vstab_frame_source;
+typedef enum vstab_frame_source { VSTAB_SRC_HOST = 0, VSTAB_SRC_SIMULATOR = 1, VSTAB_SRC_DEVICE = 2 } vstab_frame_source;
 typedef struct vstab_offline_cfg {
     long n_total;                   /* frames of the whole clip                                                  */
     int mode;                       /* vstab_mode; lock modes: lock_call = call index of setStabilizationMode      */
     long lock_call;
     int source;                     /* vstab_frame_source                                                          */
-    /* VSTAB_SRC_HOST: this rank's frames [first, last) (pinned memory recommended) and frame first-1 (NULL on rank 0) */
+    /* VSTAB_SRC_HOST: this rank's frames [first, last) (pinned memory recommended) and frame first-1 (NULL on rank 0).
+     * VSTAB_SRC_DEVICE: the same two pointers are DEVICE pointers (the shard is resident in HBM: no staging copies) */
     const uint8_t* host_frames; size_t frame_stride, step;
     const uint8_t* host_halo;
     /* VSTAB_SRC_SIMULATOR: device-resident BGR texture and the host array poses[n_total][6] = x y z pan tilt roll   */
     const uint8_t* d_texture; int tex_rows, tex_cols; const double* poses; double focal;
     /* sinks (each may be NULL): outputs of this rank's calls in call order, their checksums, all transforms         */
     uint8_t* host_out; size_t out_frame_stride, out_step;
+    uint8_t* d_out;                 /* device sink with the same strides (instead of host_out)                     */
     uint64_t* checksums;            /* [call_last - call_first]                                                    */
     double* T_all;                  /* [n_total][9] host copy of the gathered transforms                           */
 } vstab_offline_cfg;

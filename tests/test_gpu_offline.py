@@ -241,3 +241,20 @@ def test_frame_checksum_odd_width_and_c_twin(texture_small):
         assert int(r["checksums"][c]) == vs.frame_checksum(out[c])
         assert vs.frame_checksum(out[c]) == lib.vstab_frame_checksum(out[c].ctypes.data_as(C.c_void_p), H, W, W * 3)
     off.close()
+
+
+def test_offline_run_resident_source_equals_simulator_source(texture_small):
+    """VSTAB_SRC_DEVICE (shard resident in HBM, device sink) == VSTAB_SRC_SIMULATOR for the same clip."""
+    W, H, n = 640, 360, 19
+    frames, path = _dev_clip(texture_small, W, H, n)
+    tex = torch.from_numpy(texture_small).cuda()
+    off = offline.OfflineStabilizer(5, 3, 180, H, W, 4)
+    off.comm_init(0, 1)
+    a = off.run(n, vs.ACCUMULATED_FULL_LOCK, 7, texture=tex, poses=path, focal=synth.focal_for_width(W))
+    out = torch.zeros((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    b = off.run(n, vs.ACCUMULATED_FULL_LOCK, 7, device_frames=frames, device_out=out)
+    assert np.array_equal(a["checksums"], b["checksums"])
+    got = out.cpu().numpy()
+    for c in range(n):
+        assert int(b["checksums"][c]) == vs.frame_checksum(got[c])
+    off.close()

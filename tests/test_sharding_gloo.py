@@ -37,6 +37,39 @@ def test_shard_plan_covers_every_call():
         assert calls == list(range(n_total))
 
 
+def test_c_abi_shard_plan_equals_python_plan():
+    """vstab_offline_plan (what vstab_offline_run shards by, include/vstab.h) == the Python index algebra above."""
+    import ctypes as C
+    import vstab_b200 as vs
+    lib = vs.load_library()
+    for n_total, world, fut in [(100, 8, 45), (1000, 8, 45), (37, 4, 5), (16, 2, 0), (9, 8, 3), (100000, 8, 45), (5, 8, 2)]:
+        shards = offline.plan_shards(n_total, world)
+        for r, (a, b) in enumerate(shards):
+            pl = vs.ShardPlan()
+            assert lib.vstab_offline_plan(n_total, world, r, fut, C.byref(pl)) == 0
+            assert (pl.first, pl.last) == (a, b)
+            assert (pl.call_first, pl.call_last) == offline.calls_of_shard(a, b, n_total, fut)
+    pl = vs.ShardPlan()
+    assert lib.vstab_offline_plan(10, 2, 2, 3, C.byref(pl)) != 0 and lib.vstab_offline_plan(0, 1, 0, 3, C.byref(pl)) != 0
+
+
+def test_frame_checksum_c_equals_numpy_and_is_position_sensitive():
+    import ctypes as C
+    import vstab_b200 as vs
+    lib = vs.load_library()
+    rng = np.random.default_rng(3)
+    for (h, w) in [(37, 53), (16, 64), (9, 5), (1, 1)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        a = vs.frame_checksum(img)
+        assert a == lib.vstab_frame_checksum(img.ctypes.data_as(C.c_void_p), h, w, w * 3)
+        if h > 1:
+            sw = img.copy(); sw[[0, 1]] = sw[[1, 0]]
+            assert np.array_equal(sw, img) or vs.frame_checksum(sw) != a      # swapping two rows changes it
+        if w > 4:
+            sw = img.copy(); sw[:, [0, 4]] = sw[:, [4, 0]]
+            assert np.array_equal(sw, img) or vs.frame_checksum(sw) != a      # and two columns of different groups
+
+
 # ---- oracle-backed estimate / render callbacks ---------------------------------------------------
 def _estimate(frames_local, first, halo):
     """T[first+i] from the pair (frame first+i-1, frame first+i): stabilizer.cpp:1169-1209."""

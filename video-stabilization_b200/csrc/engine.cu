@@ -1471,12 +1471,14 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     const long N = cfg->n_total;
     const int mode = cfg->mode;
     const bool sim = cfg->source == VSTAB_SRC_SIMULATOR;
+    const bool resident = cfg->source == VSTAB_SRC_DEVICE;
     const bool feature_lock = mode == VSTAB_ORB_FULL_LOCK || mode == VSTAB_SIFT_FULL_LOCK;
     if (mode < 0 || mode > 5) { o->err = "Stabilizer: Invalid stabilization mode"; return VSTAB_ERR_INVALID_ARGUMENT; }
     if (sim && (!cfg->d_texture || !cfg->poses || cfg->tex_rows < 1 || cfg->tex_cols < 1)) { o->err = "simulator source needs d_texture and poses"; return VSTAB_ERR_INVALID_ARGUMENT; }
     const size_t row_bytes = (size_t)g.cols * 3;
-    if (!sim && (!cfg->host_frames || cfg->step < row_bytes)) { o->err = "host source needs host_frames with step >= 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
-    if (cfg->host_out && cfg->out_step < row_bytes) { o->err = "out_step smaller than 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (!sim && (!cfg->host_frames || cfg->step < row_bytes)) { o->err = "host / device source needs frames with step >= 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if ((cfg->host_out || cfg->d_out) && cfg->out_step < row_bytes) { o->err = "out_step smaller than 3*cols"; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (cfg->host_out && cfg->d_out) { o->err = "give host_out or d_out, not both"; return VSTAB_ERR_INVALID_ARGUMENT; }
     if ((mode == VSTAB_ACCUMULATED_FULL_LOCK || feature_lock) && cfg->lock_call < (long)o->F) {
         o->err = "lock modes must be set at a call index >= future (SURVEY B.6)"; return VSTAB_ERR_STATE;
     }
@@ -1495,7 +1497,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
 
     // ---- buffers: one chunk of frames (+ halo), one chunk of outputs, transforms, sums, checksums -----------------
     DevBuf& chunk = o->job_chunk; DevBuf& outc = o->job_out;
-    if (o->job_chunk_frames < (size_t)B + 1) {
+    if (!(resident && cfg->d_out) && o->job_chunk_frames < (size_t)B + 1) {
         CK(chunk.alloc(g.frame_bytes * ((size_t)B + 1) + 64));
         CK(outc.alloc(g.frame_bytes * (size_t)B + 64));
         o->job_chunk_frames = (size_t)B + 1;
@@ -1510,6 +1512,9 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     CK(cudaMemsetAsync(checks.p, 0, sizeof(unsigned long long) * (size_t)(n_calls > 0 ? n_calls : 1), q));
     uint8_t* cb = chunk.as<uint8_t>();
     const size_t fb = g.frame_bytes;
+    // resident shard: frame f of the clip lives at dframe(f); no staging
+    auto dframe = [&](long f) -> const uint8_t* { return f == pl.first - 1 ? cfg->host_halo : cfg->host_frames + (size_t)(f - pl.first) * cfg->frame_stride; };
+    const size_t src_fs = resident ? cfg->frame_stride : fb, src_step = resident ? cfg->step : g.pitch;
     // simulator: poses of the frames this rank may touch (first-1 .. last-1, the anchor frame), as renderer poses
     if (sim) {
         std::vector<RenderPose> hp((size_t)N);
@@ -1520,7 +1525,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     }
     // frames [f0, f0 + n) of the clip -> chunk slots [slot, slot + n)
     auto fetch = [&](long f0, long n, int slot) -> vstab_status {
-        if (n <= 0) return VSTAB_OK;
+        if (n <= 0 || resident) return VSTAB_OK;
         clock.begin(PH_SOURCE, q);
         if (sim) {
             launch_render(cfg->d_texture, cfg->tex_rows, cfg->tex_cols, poses_d.as<RenderPose>() + f0, (int)n, g.cols, g.rows, cfg->focal,
@@ -1552,7 +1557,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         CK(pack.alloc(vstab_offline_reference_bytes()));
         if (rank == owner) {
             if ((st = fetch(anchor, 1, 0)) != VSTAB_OK) return st;
-            if ((st = vstab_offline_reference_capture(o, cb, g.pitch, mode)) != VSTAB_OK) return st;
+            if ((st = vstab_offline_reference_capture(o, resident ? dframe(anchor) : cb, src_step, mode)) != VSTAB_OK) return st;
             if ((st = vstab_offline_reference_export(o, pack.p)) != VSTAB_OK) return st;
         }
         if (world > 1) {
@@ -1572,19 +1577,23 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     // ---- pass 1: estimate T[f] for f in [first, last), chunk by chunk ----------------------------------------------
     for (long f0 = pl.first; f0 < pl.last; f0 += B) {
         const long n = pl.last - f0 < B ? pl.last - f0 : B;
-        if (f0 == pl.first) {
-            if (f0 > 0 && (st = fetch(f0 - 1, 1, 0)) != VSTAB_OK) return st;        // halo frame
-        } else {
-            // the last frame of the previous chunk is this chunk's halo
-            CK(cudaMemcpyAsync(cb, cb + (size_t)B * fb, fb, cudaMemcpyDeviceToDevice, q));
+        if (!resident) {
+            if (f0 == pl.first) {
+                if (f0 > 0 && (st = fetch(f0 - 1, 1, 0)) != VSTAB_OK) return st;        // halo frame
+            } else {
+                // the last frame of the previous chunk is this chunk's halo
+                CK(cudaMemcpyAsync(cb, cb + (size_t)B * fb, fb, cudaMemcpyDeviceToDevice, q));
+            }
+            if ((st = fetch(f0, n, 1)) != VSTAB_OK) return st;
         }
-        if ((st = fetch(f0, n, 1)) != VSTAB_OK) return st;
+        const uint8_t* fr = resident ? dframe(f0) : cb + fb;
+        const uint8_t* hl = f0 > 0 ? (resident ? dframe(f0 - 1) : cb) : nullptr;
         clock.begin(PH_ESTIMATE, q);
-        st = vstab_offline_estimate(o, cb + fb, fb, g.pitch, (int)n, f0, f0 > 0 ? cb : nullptr,
+        st = vstab_offline_estimate(o, fr, src_fs, src_step, (int)n, f0, hl,
                                     T_local.as<double>() + (size_t)(f0 - pl.first) * 9,
                                     sums.as<unsigned long long>() + (size_t)(f0 - pl.first) * 3);
         if (st == VSTAB_OK && feature_lock)
-            st = vstab_offline_register(o, cb + fb, fb, g.pitch, (int)n, reg_local.as<double>() + (size_t)(f0 - pl.first) * 10);
+            st = vstab_offline_register(o, fr, src_fs, src_step, (int)n, reg_local.as<double>() + (size_t)(f0 - pl.first) * 10);
         clock.end(q);
         if (st != VSTAB_OK) return st;
     }
@@ -1620,8 +1629,10 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         const long p_lo = c0 - F > 0 ? c0 - F : 0, p_hi = c0 + n - 1 - F > 0 ? c0 + n - 1 - F : 0;
         if ((st = fetch(p_lo, p_hi - p_lo + 1, 0)) != VSTAB_OK) return st;
         clock.begin(PH_RENDER, q);
-        st = offline_render_impl(o, cb, fb, g.pitch, p_lo, (int)n, c0, T_all.as<double>(), N, mode, cfg->lock_call,
-                                 sums.as<unsigned long long>() + (size_t)(p_lo - pl.first) * 3, outc.as<uint8_t>(), fb, g.pitch,
+        uint8_t* dst = cfg->d_out ? cfg->d_out + (size_t)(c0 - pl.call_first) * cfg->out_frame_stride : outc.as<uint8_t>();
+        st = offline_render_impl(o, resident ? dframe(p_lo) : cb, src_fs, src_step, p_lo, (int)n, c0, T_all.as<double>(), N, mode,
+                                 cfg->lock_call, sums.as<unsigned long long>() + (size_t)(p_lo - pl.first) * 3, dst,
+                                 cfg->d_out ? cfg->out_frame_stride : fb, cfg->d_out ? cfg->out_step : g.pitch,
                                  cfg->checksums ? checks.as<unsigned long long>() + (c0 - pl.call_first) : nullptr);
         clock.end(q);
         if (st != VSTAB_OK) return st;

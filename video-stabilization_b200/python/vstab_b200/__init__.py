@@ -18,7 +18,7 @@ import numpy as np
 ACCUMULATED_FULL_LOCK, ORB_FULL_LOCK, SIFT_FULL_LOCK, TRANSLATION_LOCK, ROTATION_LOCK, GLOBAL_SMOOTHING = range(6)
 
 OK, ERR_INVALID_ARGUMENT, ERR_SIZE_CHANGED, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NCCL = range(7)
-SRC_HOST, SRC_SIMULATOR = 0, 1
+SRC_HOST, SRC_SIMULATOR, SRC_DEVICE = 0, 1, 2
 
 TAP_GRAY, TAP_PYR1, TAP_PYR2, TAP_PYR3, TAP_PREV_PTS, TAP_LK_PTS, TAP_LK_STATUS, TAP_NEW_PTS, TAP_T, TAP_M, \
     TAP_H_STABILIZE, TAP_H_SCALED, TAP_BORDER, TAP_EIG, TAP_INLIERS, TAP_CHANNEL_SUMS, TAP_LOCK_H, TAP_ORB_COUNTS, \
@@ -51,7 +51,7 @@ class OfflineCfg(C.Structure):          # vstab_offline_cfg
                 ("host_frames", C.c_void_p), ("frame_stride", C.c_size_t), ("step", C.c_size_t), ("host_halo", C.c_void_p),
                 ("d_texture", C.c_void_p), ("tex_rows", C.c_int), ("tex_cols", C.c_int), ("poses", C.POINTER(C.c_double)),
                 ("focal", C.c_double),
-                ("host_out", C.c_void_p), ("out_frame_stride", C.c_size_t), ("out_step", C.c_size_t),
+                ("host_out", C.c_void_p), ("out_frame_stride", C.c_size_t), ("out_step", C.c_size_t), ("d_out", C.c_void_p),
                 ("checksums", C.POINTER(C.c_uint64)), ("T_all", C.POINTER(C.c_double))]
 
 

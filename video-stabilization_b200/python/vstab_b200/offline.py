@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-from . import (ACCUMULATED_FULL_LOCK, GLOBAL_SMOOTHING, SRC_HOST, SRC_SIMULATOR, NcclId, OfflineCfg, OfflineReport,  # noqa: F401
+from . import (ACCUMULATED_FULL_LOCK, GLOBAL_SMOOTHING, SRC_DEVICE, SRC_HOST, SRC_SIMULATOR, NcclId, OfflineCfg, OfflineReport,  # noqa: F401
                ShardPlan, _vp, load_library)
 from . import _check as _check_any
 
@@ -152,11 +152,14 @@ class OfflineStabilizer:
         return pl.first, pl.last, pl.call_first, pl.call_last
 
     def run(self, n_total: int, mode: int, lock_call: int = 0, *, texture=None, poses=None, focal: float = 0.0,
-            host_frames=None, host_halo=None, host_out=None, want_checksums: bool = True, want_T: bool = False):
+            host_frames=None, host_halo=None, host_out=None, device_frames=None, device_halo=None, device_out=None,
+            want_checksums: bool = True, want_T: bool = False):
         """vstab_offline_run: this rank's share of a clip of n_total frames.  Source: `texture` (uint8 CUDA tensor
         [th, tw, 3]) + `poses` (float64 [n_total, 6]) for the device simulator, or `host_frames` (uint8 numpy / pinned
         tensor [n_local, rows, cols, 3], + `host_halo` [rows, cols, 3] on ranks > 0).  Returns a dict with the report,
-        `checksums` (uint64 numpy, one per call of this rank) and optionally `T` [n_total, 3, 3]."""
+        `checksums` (uint64 numpy, one per call of this rank) and optionally `T` [n_total, 3, 3].
+        `device_frames` / `device_halo` / `device_out`: the shard, its halo frame and the outputs as CUDA tensors
+        (resident in HBM, no staging copies)."""
         import numpy as np
         cfg = OfflineCfg()
         cfg.n_total, cfg.mode, cfg.lock_call = n_total, mode, lock_call
@@ -168,6 +171,11 @@ class OfflineStabilizer:
             cfg.d_texture, cfg.tex_rows, cfg.tex_cols = texture.data_ptr(), texture.shape[0], texture.shape[1]
             cfg.poses, cfg.focal = poses.ctypes.data_as(C.POINTER(C.c_double)), float(focal)
             keep.append(poses)
+        elif device_frames is not None:
+            self._frames_ok(device_frames)
+            cfg.source = SRC_DEVICE
+            cfg.host_frames, cfg.frame_stride, cfg.step = device_frames.data_ptr(), device_frames.stride(0), device_frames.stride(1)
+            cfg.host_halo = device_halo.data_ptr() if device_halo is not None else None
         else:
             cfg.source = SRC_HOST
             ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
@@ -181,6 +189,10 @@ class OfflineStabilizer:
             cfg.host_out = host_out.data_ptr() if hasattr(host_out, "data_ptr") else host_out.ctypes.data
             cfg.out_frame_stride, cfg.out_step = (host_out.stride(0), host_out.stride(1)) if hasattr(host_out, "data_ptr") \
                 else (host_out.strides[0], host_out.strides[1])
+        if device_out is not None:
+            self._frames_ok(device_out)
+            assert device_out.shape[0] >= c1 - c0
+            cfg.d_out, cfg.out_frame_stride, cfg.out_step = device_out.data_ptr(), device_out.stride(0), device_out.stride(1)
         sums = np.zeros(max(c1 - c0, 1), np.uint64)
         if want_checksums:
             cfg.checksums = sums.ctypes.data_as(C.POINTER(C.c_uint64))
