@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 
 H_TOL_PX = 0.1     # north star: homography corner reprojection
 PIX_TOL = 1        # north star: warped pixels <= 1 LSB
-# The warp kernel itself is bit-exact for a given H (tests/test_gpu_kernels.py::test_warp_bit_exact).
-# End to end, H differs from the oracle's by ~1e-6..1e-4 px (LK float summation order), which moves
-# a few Q5 source coordinates across a rounding boundary (1/32 px): those pixels change by up to
-# 255/32 ~ 8 LSB on hard edges.  The pipeline bar is therefore: at most FRAC_GT1 of the pixels of
-# any frame may differ by more than 1 LSB, and never by more than one Q5 step on full contrast.
-FRAC_GT1 = 2e-3
-MAX_Q5_STEP = 9
+# The tracker replays OpenCV's float accumulation order (csrc/lk.cu), so the tracked points -- and with them the RANSAC
+# consensus set -- carry the oracle's bits; the transforms differ only where the oracle's Levenberg-Marquardt refinement
+# and the closed-form least squares differ (~1e-12 px), and the warp is bit-exact for equal H.  The pipeline bar is therefore
+# the north star's, with nothing added: no pixel off by more than 1 LSB.  (Round 1 needed 0.2 % of the pixels and 9 LSB here.)
+FRAC_GT1 = 0.0
+MAX_Q5_STEP = 1
+H_ACHIEVED_PX = 1e-9   # what the pipeline achieves on the transforms (tolerance: H_TOL_PX)
 
 
 def _corner_diff(Ha, Hb, W, H):
@@ -71,7 +71,7 @@ def test_config1_global_smoothing_720p(texture):
     assert s["lk"] <= 0.05
     assert s["t"] <= H_TOL_PX and s["h"] <= H_TOL_PX
     assert s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
-    assert s["h"] <= 1e-3            # what the pipeline actually achieves with the exact RANSAC restatement
+    assert s["h"] <= H_ACHIEVED_PX and s["lk"] == 0.0        # what the pipeline achieves: identical tracked points
 
 
 def test_config2_accumulated_lock_1080p(texture):
@@ -92,7 +92,7 @@ def test_golden_clip(golden):
                 st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
             out = st.stabilize_frame(fr)
             d = np.abs(out.astype(int) - golden[f"clip_{name}_out"][i])
-            assert (d > PIX_TOL).mean() <= 5 * FRAC_GT1 and d.max() <= MAX_Q5_STEP     # tiny 256x192 frames
+            assert (d > PIX_TOL).mean() <= FRAC_GT1 and d.max() <= MAX_Q5_STEP
             if i:
                 assert _corner_diff(st.tap(vs.TAP_H_SCALED), golden[f"clip_{name}_H"][i], 256, 192) <= H_TOL_PX
         st.close()
@@ -103,7 +103,7 @@ def test_general_resize_and_odd_sizes(texture_small):
     frames = render_clip(texture_small, 333, 250, 14)
     for P, F in ((5, 0), (0, 6), (3, 3)):
         s = _run_both(frames, P, F, 100)
-        assert s["h"] <= H_TOL_PX and s["frac_gt1"] <= 5 * FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
+        assert s["h"] <= H_TOL_PX and s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
 
 
 def test_translation_rotation_lock_identity(golden):
@@ -165,14 +165,15 @@ def test_two_instances_are_independent(golden):
         s.close()
 
 
-@pytest.mark.parametrize("W,H,wh,n", [(1280, 720, 360, 22), (1920, 1080, 1080, 14)])
-def test_orb_full_lock_matches_oracle(texture, W, H, wh, n):
+@pytest.mark.parametrize("W,H,wh,n,P,F", [(1280, 720, 360, 22, 6, 4), (1920, 1080, 1080, 14, 6, 4), (1280, 720, 360, 16, 5, 1),
+                                          (1280, 720, 360, 16, 5, 2), (1280, 720, 360, 14, 0, 3)])
+def test_orb_full_lock_matches_oracle(texture, W, H, wh, n, P, F):
     """BASELINE config 3 (shortened): ORB registration to the reference frame.  Integer stages are
     bit-exact (conditioned image, keypoint counts, match counts) and the reference keypoints are kept in
     cv::ORB's own order, so the similarity fit sees the same match list as OpenCV's RANSAC:
     homography <= 0.1 px at the frame corners (north-star tolerance; observed ~1e-9)."""
     frames = render_clip(texture, W, H, n)
-    P, F, switch = 6, 4, 8
+    switch = 8                  # future = 1: the registration of a presentation frame may not run ahead of its upload
     ref = sr.StabilizerRef(P, F, wh)
     st = vs.Stabilizer(P, F, wh)
     worst_h, worst_frac = 0.0, 0.0
@@ -225,13 +226,13 @@ def test_orb_lock_keeps_previous_h_on_failure(texture):
     st.close()
 
 
-@pytest.mark.parametrize("W,H,wh,n", [(1280, 720, 360, 18), (1920, 1080, 1080, 13)])
-def test_sift_full_lock_matches_oracle(texture, W, H, wh, n):
+@pytest.mark.parametrize("W,H,wh,n,P,F", [(1280, 720, 360, 18, 6, 4), (1920, 1080, 1080, 13, 6, 4), (1280, 720, 360, 13, 5, 1)])
+def test_sift_full_lock_matches_oracle(texture, W, H, wh, n, P, F):
     """BASELINE config 4 (shortened, 1080p): SIFT registration to the reference frame.  The oracle runs the
     reference's control flow with the exact L2 matcher (FLANN is approximate and not reproducible call to
     call); parity is at the homography level: <= 0.1 px at the frame corners."""
     frames = render_clip(texture, W, H, n)
-    P, F, switch = 6, 4, 8
+    switch = 8
     ref = sr.StabilizerRef(P, F, wh, exact_sift_matcher=True)
     st = vs.Stabilizer(P, F, wh)
     worst_h = 0.0
@@ -310,5 +311,42 @@ def test_integer_shift_is_undone_by_full_lock(texture, W, H, wh, k):
         want[1, 2] = (shifts[j][1] - shifts[a][1]) * k
         assert _corner_diff(st.tap(vs.TAP_H_SCALED), want, W, H) <= H_TOL_PX, i
         d = np.abs(got[m:H - m, m:W - m].astype(int) - frames[a][m:H - m, m:W - m])
-        assert d.mean() < 0.5 and d.max() <= 4 * MAX_Q5_STEP, (i, float(d.mean()), int(d.max()))
+        assert d.mean() < 0.5 and d.max() <= 36, (i, float(d.mean()), int(d.max()))      # vs the anchor FRAME, not the oracle
     st.close()
+
+
+# ---------------------------------------------------------------- BASELINE configurations at full length
+def _full_length(name, frames):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import parity_report
+    return parity_report.run(name, frames)
+
+
+def test_config1_full_length_300_frames_window_60_45():
+    """BASELINE config 1 as stated: --simulator 1280x720, working height 360, GLOBAL_SMOOTHING, window 60/45, 300 frames."""
+    s = _full_length("c1", 300)
+    assert s["lk_bit_equal"] == s["calls"]                       # every call: the oracle's tracked points, bit for bit
+    assert s["h_px"] <= H_ACHIEVED_PX and s["t_px"] <= H_ACHIEVED_PX
+    assert s["max_lsb"] <= PIX_TOL and s["px_gt1"] == 0
+    assert s["px_differ"] <= 1e-8 * s["px_total"]                # observed: 0 of 8.3e8
+
+
+def test_config2_full_length_2000_frames_lock_at_46():
+    """BASELINE config 2 as stated: 1920x1080, working height 360, window 60/45, ACCUMULATED_FULL_LOCK set at call 46 and
+    held for 2000 frames: the accumulated product multiplies every transform since the anchor, so the bar is on the LAST frame."""
+    s = _full_length("c2", 2000)
+    assert s["lk_bit_equal"] == s["calls"]
+    assert s["h_px"] <= H_ACHIEVED_PX and s["h_px_last"] <= H_ACHIEVED_PX      # no drift: 0.1 px is the tolerance
+    assert s["max_lsb"] <= PIX_TOL and s["px_gt1"] == 0
+    assert s["px_differ"] <= 1e-8 * s["px_total"]
+
+
+def test_config4_sift_pipeline_at_4k_working_height_2160():
+    """BASELINE config 4 as stated: SIFT registration at 3840x2160, working height 2160 (the streaming pipeline, not only
+    the kernel): homography within the north-star 0.1 px of the oracle's (exact L2 matcher on both sides)."""
+    s = _full_length("c4", 24)
+    assert s["h_px"] <= H_TOL_PX
+    print(f"SIFT lock 4K / 2160: worst corner difference {s['h_px']:.4f} px, max pixel difference {s['max_lsb']} LSB, "
+          f"{s['px_gt1']} of {s['px_total']} px off by more than 1 LSB")

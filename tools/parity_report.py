@@ -52,7 +52,8 @@ def run(name, n_frames=None, check_render=97, chunk=64, verbose=False):
     focal = synth.focal_for_width(W)
     tex_d = torch.from_numpy(tex).cuda()
     buf = torch.empty((chunk, H, W, 3), dtype=torch.uint8, device="cuda")
-    ref = sr.StabilizerRef(cfg["P"], cfg["F"], wh)
+    # SIFT: the oracle matches exactly (the reference's FLANN KD-trees are approximate and not reproducible)
+    ref = sr.StabilizerRef(cfg["P"], cfg["F"], wh, exact_sift_matcher=cfg["mode"] == "SIFT_FULL_LOCK")
     st = vs.Stabilizer(cfg["P"], cfg["F"], wh)
     mode = getattr(sr, cfg["mode"])
     s = dict(config=name, frames=n, h_px=0.0, h_px_last=0.0, t_px=0.0, t_bit_equal=0, lk_bit_equal=0, calls=0, max_lsb=0,

@@ -339,7 +339,7 @@ static vstab_status stream_feature_lock(vstab* s, long p, cudaStream_t q, int sl
         CK(s->ref_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(s->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp));
         CK(s->ref_desc.alloc(128 * kOrbMaxKp)); CK(s->cur_desc.alloc(128 * kOrbMaxKp));   // 32 B (ORB) or 128 B (SIFT) per row
         CK(s->orb_counts.alloc(sizeof(int) * 4));                            // {nref, ncur, nmatch}
-        CK(s->m_idx.alloc(4 * kOrbMaxKp)); CK(s->m_d0.alloc(4 * kOrbMaxKp)); CK(s->m_d1.alloc(4 * kOrbMaxKp));
+        CK(s->m_idx.alloc(4 * kOrbMaxKp)); CK(s->m_d0.alloc(4 * kOrbMaxKp)); CK(s->m_d1.alloc(l2_match_scratch_bytes(kOrbMaxKp, 1)));   // m_d1: second distances (Hamming) / matcher scratch (L2)
         CK(s->m_good.alloc(kOrbMaxKp)); CK(s->m_status.alloc(kOrbMaxKp));
         CK(s->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(s->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
         CK(s->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));        // T[9], M[6], counts[2]
@@ -382,7 +382,7 @@ static vstab_status stream_feature_lock(vstab* s, long p, cudaStream_t q, int sl
                                  s->m_status.as<uint8_t>(), counts + 2, q);                        // :647-673, :711-716
         else
             launch_l2_match(s->ref_desc.as<uint8_t>(), counts + 0, s->ref_kps.as<OrbKeypoint>(), s->cur_desc.as<uint8_t>(),
-                            counts + 1, s->cur_kps.as<OrbKeypoint>(), kOrbMaxKp, s->m_idx.as<int>(), s->m_d0.as<int>(),
+                            counts + 1, s->cur_kps.as<OrbKeypoint>(), kOrbMaxKp, s->m_d1.p, s->m_idx.as<int>(), s->m_d0.as<int>(),
                             s->m_good.as<uint8_t>(), s->m_ref.as<float2>(), s->m_cur.as<float2>(), s->m_status.as<uint8_t>(),
                             counts + 2, q);                                                        // :675-708, :711-716
         launch_fit_large(s->m_ref.as<float2>(), s->m_cur.as<float2>(), s->m_status.as<uint8_t>(), counts + 2, 5.0,
@@ -839,7 +839,7 @@ static vstab_status offline_feature_setup(vstab_offline* o, int mode) {
         CK(o->ref_pack.alloc(kRefPackBytes));
         CK(o->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(o->cur_desc.alloc(128 * kOrbMaxKp));
         CK(o->f_counts.alloc(sizeof(int) * 4));
-        CK(o->m_idx.alloc(4 * kOrbMaxKp)); CK(o->m_d0.alloc(4 * kOrbMaxKp)); CK(o->m_d1.alloc(4 * kOrbMaxKp));
+        CK(o->m_idx.alloc(4 * kOrbMaxKp)); CK(o->m_d0.alloc(4 * kOrbMaxKp)); CK(o->m_d1.alloc(l2_match_scratch_bytes(kOrbMaxKp, 1)));
         CK(o->m_good.alloc(kOrbMaxKp)); CK(o->m_status.alloc(kOrbMaxKp));
         CK(o->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(o->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
         CK(o->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));
@@ -928,7 +928,7 @@ vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames,
         CK(L->feat_gray.alloc((size_t)g.ww * g.wh));
         CK(L->cur_kps.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(L->cur_desc.alloc(128 * kOrbMaxKp));
         CK(L->f_counts.alloc(sizeof(int) * 4));
-        CK(L->m_idx.alloc(4 * kOrbMaxKp)); CK(L->m_d0.alloc(4 * kOrbMaxKp)); CK(L->m_d1.alloc(4 * kOrbMaxKp));
+        CK(L->m_idx.alloc(4 * kOrbMaxKp)); CK(L->m_d0.alloc(4 * kOrbMaxKp)); CK(L->m_d1.alloc(l2_match_scratch_bytes(kOrbMaxKp, 1)));
         CK(L->m_good.alloc(kOrbMaxKp)); CK(L->m_status.alloc(kOrbMaxKp));
         CK(L->m_ref.alloc(sizeof(float2) * kOrbMaxKp)); CK(L->m_cur.alloc(sizeof(float2) * kOrbMaxKp));
         CK(L->lock_fit.alloc(sizeof(double) * 16 + sizeof(int) * 4));
@@ -969,7 +969,7 @@ vstab_status vstab_offline_register(vstab_offline_t* o, const uint8_t* d_frames,
                                  m_ref, m_cur, m_status, counts + 2, ql);
         } else {
             launch_sift(L ? L->sift : o->sift, feat_gray, cur_kps, cur_desc, counts + 1, ql);
-            launch_l2_match(ref_desc, nref, ref_kps, cur_desc, counts + 1, cur_kps, kOrbMaxKp, m_idx, m_d0, m_good, m_ref, m_cur,
+            launch_l2_match(ref_desc, nref, ref_kps, cur_desc, counts + 1, cur_kps, kOrbMaxKp, m_d1, m_idx, m_d0, m_good, m_ref, m_cur,
                             m_status, counts + 2, ql);
         }
         launch_fit_large(m_ref, m_cur, m_status, counts + 2, 5.0, g.ww / 2.0, g.wh / 2.0, Tfit, Tfit + 9, fitc, ql);
@@ -1927,7 +1927,8 @@ extern "C" vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref
     if (!ref || !cur || !best_idx || !best_d2 || !good || nref < 0 || ncur < 0 || nref > kOrbMaxKp || ncur > kOrbMaxKp)
         return VSTAB_ERR_INVALID_ARGUMENT;
     if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
-    DevBuf a, b, na, nb, bi, bd, gd, ka, kb, rp, cp, stt, nm;
+    DevBuf a, b, na, nb, bi, bd, gd, ka, kb, rp, cp, stt, nm, scr;
+    CK(scr.alloc(l2_match_scratch_bytes(kOrbMaxKp, 1)));
     CK(a.alloc(128 * kOrbMaxKp)); CK(b.alloc(128 * kOrbMaxKp)); CK(na.alloc(4)); CK(nb.alloc(4));
     CK(bi.alloc(4 * kOrbMaxKp)); CK(bd.alloc(4 * kOrbMaxKp)); CK(gd.alloc(kOrbMaxKp));
     CK(ka.alloc(sizeof(OrbKeypoint) * kOrbMaxKp)); CK(kb.alloc(sizeof(OrbKeypoint) * kOrbMaxKp));
@@ -1937,7 +1938,7 @@ extern "C" vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref
     CK(cudaMemcpy(b.p, cur, (size_t)128 * ncur, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(na.p, &nref, 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(nb.p, &ncur, 4, cudaMemcpyHostToDevice));
     launch_l2_match(a.as<uint8_t>(), na.as<int>(), ka.as<OrbKeypoint>(), b.as<uint8_t>(), nb.as<int>(), kb.as<OrbKeypoint>(),
-                    kOrbMaxKp, bi.as<int>(), bd.as<int>(), gd.as<uint8_t>(), rp.as<float2>(), cp.as<float2>(),
+                    kOrbMaxKp, scr.p, bi.as<int>(), bd.as<int>(), gd.as<uint8_t>(), rp.as<float2>(), cp.as<float2>(),
                     stt.as<uint8_t>(), nm.as<int>(), 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

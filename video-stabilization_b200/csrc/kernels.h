@@ -244,9 +244,14 @@ void launch_sift(SiftPlan* P, const uint8_t* gray, OrbKeypoint* kps_out, uint8_t
 
 // ---------------------------------------------------------------- K12 exact L2 matcher (tcgen05)
 // descriptors: u8 [n][128] (SIFT descriptors are integers 0..255).  best_d2 = exact squared distances.
-void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, const uint8_t* cur_desc,
-                     const int* ncur, const OrbKeypoint* cur_kps, int max_kp, int* best_idx, int* best_d2, uint8_t* good,
+// scratch: l2_match_scratch_bytes(max_kp, 1) device bytes.  The current rows beyond *ncur up to the next multiple of 128 are zeroed.
+size_t l2_match_scratch_bytes(int max_kp, int nframes);
+void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, uint8_t* cur_desc,
+                     const int* ncur, const OrbKeypoint* cur_kps, int max_kp, void* scratch, int* best_idx, int* best_d2, uint8_t* good,
                      float2* ref_pts, float2* cur_pts, uint8_t* status, int* nmatch, cudaStream_t st);
+// the nearest-neighbour search alone, `nframes` current sets (cur_desc + f * max_kp * 128, ncur[f]) against one reference set
+void launch_l2_nn_batch(const uint8_t* ref_desc, const int* nref, uint8_t* cur_desc, const int* ncur, int max_kp, int nframes,
+                        void* scratch, int* best_idx, int* best_d2, cudaStream_t st);
 
 // ---------------------------------------------------------------- K13 simulator render
 struct RenderPose { double R[9]; double cam[3]; };
