@@ -124,6 +124,10 @@ def test_api_errors(golden):
     st.stabilize_frame(clip[0])
     with pytest.raises(ValueError, match="size has changed"):
         st.stabilize_frame(np.ascontiguousarray(clip[1][:100]))
+    # a caller-supplied output buffer must have the frame's shape and packed pixels (the native call writes rows*cols*3 bytes)
+    for bad in (np.zeros((10, 10, 3), np.uint8), np.zeros(clip[0].shape, np.float32), np.zeros(clip[0].shape[:2] + (4,), np.uint8)[:, :, :3]):
+        with pytest.raises(ValueError, match="out must be"):
+            st.stabilize_frame(clip[1], out=bad)
     with pytest.raises(ValueError, match="invalid size"):
         vs.Stabilizer(4, 3, 96).stabilize_frame(np.zeros((10, 200, 3), np.uint8))
     # ACCUMULATED_FULL_LOCK before the window can advance: the reference asserts

@@ -814,6 +814,7 @@ struct vstab_offline {
     int rank = 0, world = 1;
     DevBuf job_chunk, job_out;
     size_t job_chunk_frames = 0;
+    std::vector<cudaEvent_t> host_events;         // vstab_offline_run_host: upload / render / download marks per chunk
     std::string err;
     void set_err(const std::string& e) { err = e; }
 };
@@ -1045,6 +1046,7 @@ void vstab_offline_destroy(vstab_offline_t* o) {
     }
     if (o->ev_reg_fork) cudaEventDestroy(o->ev_reg_fork);
     if (o->comm) nccl_comm_destroy(o->comm);
+    for (auto e : o->host_events) if (e) cudaEventDestroy(e);
     delete o;
 }
 
@@ -1261,9 +1263,14 @@ extern "C" vstab_status vstab_offline_run_host(vstab_offline_t* o, const uint8_t
     double* T = o->clipT.as<double>();
     unsigned long long* sums = o->clipSums.as<unsigned long long>();
     const long nchunks = (n_total + B - 1) / B;
-    std::vector<cudaEvent_t> ev((size_t)nchunks * 3, nullptr);
-    auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); };
-    for (auto& e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cleanup(); o->err = "cudaEventCreate failed"; return VSTAB_ERR_CUDA; }
+    // per-chunk events live in the instance (created once, reused by every call, destroyed with it)
+    std::vector<cudaEvent_t>& ev = o->host_events;
+    while (ev.size() < (size_t)nchunks * 3) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { o->err = "cudaEventCreate failed"; return VSTAB_ERR_CUDA; }
+        ev.push_back(e);
+    }
+    auto cleanup = [] {};
     cudaEvent_t* ev_up = ev.data();                 // chunk k uploaded
     cudaEvent_t* ev_rd = ev.data() + nchunks;       // chunk k rendered
     cudaEvent_t* ev_dn = ev.data() + 2 * nchunks;   // chunk k downloaded

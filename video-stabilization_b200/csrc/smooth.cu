@@ -187,69 +187,8 @@ __global__ void acc_update_kernel(const double* T, long t_mod, long p, int reset
     for (int i = 0; i < 9; ++i) acc[i] = tmp[i];
 }
 
-// ---- offline prefix product: acc[k] = T[k] * acc[k-1], acc[anchor] = I -----------------------
-// Segmented scan over 3x3 transforms: each block reduces a contiguous chunk (phase 1), a
-// single warp scans the chunk totals (phase 2), each block re-walks its chunk with the
-// incoming prefix (phase 3).  Products are left-multiplications in frame order.
+// ---- offline prefix product: acc[k] = T[k] * acc[k-1], acc[anchor] = I (acc_seq_kernel below) ----------
 constexpr int kScanChunk = 256;
-
-// One CTA per chunk: the chunk's transforms are staged in shared memory by all threads (the serial chain would
-// otherwise pay a global-memory round trip per product), then thread 0 walks the chain.
-__global__ void __launch_bounds__(128)
-acc_chunk_reduce_kernel(const double* __restrict__ T, long n_total, long anchor, double* __restrict__ chunk_tot) {
-    __shared__ double sT[kScanChunk * 9];
-    const long chunk = blockIdx.x;
-    const long k0 = anchor + 1 + chunk * kScanChunk;
-    if (k0 >= n_total) return;
-    const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
-    for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) sT[i] = T[(size_t)k0 * 9 + i];
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    double acc[9], tmp[9];
-    eye3(acc);
-    for (long k = k0; k < k1; ++k) {
-        matmul3(sT + (size_t)(k - k0) * 9, acc, tmp);
-        for (int i = 0; i < 9; ++i) acc[i] = tmp[i];
-    }
-    for (int i = 0; i < 9; ++i) chunk_tot[(size_t)chunk * 9 + i] = acc[i];
-}
-
-__global__ void acc_chunk_scan_kernel(double* chunk_tot, long nchunks) {
-    // exclusive scan (sequential over chunk totals: nchunks = n/256 is small), in place
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double run[9], tmp[9], cur[9];
-    eye3(run);
-    for (long c = 0; c < nchunks; ++c) {
-        for (int i = 0; i < 9; ++i) cur[i] = chunk_tot[(size_t)c * 9 + i];
-        for (int i = 0; i < 9; ++i) chunk_tot[(size_t)c * 9 + i] = run[i];
-        matmul3(cur, run, tmp);
-        for (int i = 0; i < 9; ++i) run[i] = tmp[i];
-    }
-}
-
-__global__ void __launch_bounds__(128)
-acc_chunk_apply_kernel(const double* __restrict__ T, long n_total, long anchor,
-                       const double* __restrict__ chunk_pre, double* __restrict__ acc_out) {
-    __shared__ double sT[kScanChunk * 9];
-    const long chunk = blockIdx.x;
-    const long k0 = anchor + 1 + chunk * kScanChunk;
-    if (chunk == 0 && threadIdx.x == 0 && anchor < n_total) eye3(acc_out + (size_t)anchor * 9);
-    if (k0 >= n_total) return;
-    const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
-    for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) sT[i] = T[(size_t)k0 * 9 + i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double acc[9], tmp[9];
-        for (int i = 0; i < 9; ++i) acc[i] = chunk_pre[(size_t)chunk * 9 + i];
-        for (long k = k0; k < k1; ++k) {
-            matmul3(sT + (size_t)(k - k0) * 9, acc, tmp);
-            // the running product replaces the transform in shared memory; all threads write the chunk out below
-            for (int i = 0; i < 9; ++i) { acc[i] = tmp[i]; sT[(size_t)(k - k0) * 9 + i] = tmp[i]; }
-        }
-    }
-    __syncthreads();
-    for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) acc_out[(size_t)k0 * 9 + i] = sT[i];
-}
 
 }  // namespace
 
@@ -276,20 +215,43 @@ void launch_acc_update(const double* T, long t_mod, long p, int reset, double* a
     acc_update_kernel<<<1, 32, 0, st>>>(T, t_mod, p, reset, acc_state);
 }
 
-// chunk scratch lives at the tail of `acc` (caller allocates n_total + 2*ceil(n_total/256)+2 matrices)
+namespace {
+// The accumulated-lock prefix acc[k] = T[k] * acc[k-1] (acc[anchor] = I) as ONE strictly sequential chain in the reference's
+// own order (src/stabilizer.cpp:334: `acc <- T[p-1] * acc` once per call): products of 3x3 doubles do not associate bit for
+// bit, and a chunked scan (reduce / scan / apply, round 1) re-associates them across chunk boundaries, so a 2000-frame offline
+// clip and the streaming calls would differ in the last bits.  One thread walks the chain; the CTA stages 256 transforms at
+// a time through shared memory and writes the running products back coalesced.  ~50 ns per frame: 0.03 ms for the bench's 512
+// frames (the three-kernel scan took 0.06 ms), 5 ms for 100 000.
+__global__ void __launch_bounds__(128)
+acc_seq_kernel(const double* __restrict__ T, long n_total, long anchor, double* __restrict__ acc_out) {
+    __shared__ double sT[kScanChunk * 9];
+    __shared__ double run[9];
+    if (threadIdx.x == 0) { eye3(run); if (anchor < n_total) eye3(acc_out + (size_t)anchor * 9); }
+    for (long k0 = anchor + 1; k0 < n_total; k0 += kScanChunk) {
+        const long k1 = k0 + kScanChunk < n_total ? k0 + kScanChunk : n_total;
+        __syncthreads();
+        for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) sT[i] = T[(size_t)k0 * 9 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a[9], tmp[9];
+            for (int i = 0; i < 9; ++i) a[i] = run[i];
+            for (long k = k0; k < k1; ++k) {
+                matmul3(sT + (size_t)(k - k0) * 9, a, tmp);
+                for (int i = 0; i < 9; ++i) { a[i] = tmp[i]; sT[(size_t)(k - k0) * 9 + i] = tmp[i]; }
+            }
+            for (int i = 0; i < 9; ++i) run[i] = a[i];
+        }
+        __syncthreads();
+        for (long i = threadIdx.x; i < (k1 - k0) * 9; i += blockDim.x) acc_out[(size_t)k0 * 9 + i] = sT[i];
+    }
+}
+
+}  // namespace
+
 void launch_acc_scan(const double* T, long n_total, long anchor, double* acc, cudaStream_t st) {
     if (anchor >= n_total) return;
-    const long n = n_total - anchor - 1;
-    const long nchunks = n > 0 ? (n + kScanChunk - 1) / kScanChunk : 0;
-    double* chunk = acc + (size_t)n_total * 9;
-    const int threads = 128;
-    const int blocks = (int)(nchunks > 0 ? nchunks : 1);
-    count_launch(nchunks > 0 ? 3 : 1);
-    if (nchunks > 0) {
-        acc_chunk_reduce_kernel<<<blocks, threads, 0, st>>>(T, n_total, anchor, chunk);
-        acc_chunk_scan_kernel<<<1, 32, 0, st>>>(chunk, nchunks);
-    }
-    acc_chunk_apply_kernel<<<blocks, threads, 0, st>>>(T, n_total, anchor, chunk, acc);
+    count_launch(1);
+    acc_seq_kernel<<<1, 128, 0, st>>>(T, n_total, anchor, acc);
 }
 
 }  // namespace vstabk

@@ -228,6 +228,10 @@ class Stabilizer:
             frame = np.ascontiguousarray(frame)
         if out is None:
             out = np.empty((frame.shape[0], frame.shape[1], 3), np.uint8)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != frame.shape or out.strides[2] != 1
+              or out.strides[1] != 3 or out.strides[0] < 3 * frame.shape[1] or not out.flags.writeable):
+            # the native call writes rows * cols * 3 bytes at out.strides[0]: anything else would be out of bounds
+            raise ValueError("out must be a writeable uint8 array of the frame's shape with packed BGR pixels")
         _check(self._lib.vstab_stabilize_frame(self._h, _ptr(frame), frame.shape[0], frame.shape[1],
                                                frame.strides[0], _ptr(out), out.strides[0]), self._h)
         return out
