@@ -64,18 +64,9 @@ def pin_to_gpu_numa_node(torch, local):
     (/sys/bus/pci/devices/<bdf>/local_cpulist).  Returns a description for the JSON line."""
     info = {"bound": False}
     try:
-        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bdf is None:
-            import ctypes as CC
-            rt = CC.CDLL("libcudart.so.12")
-            buf = CC.create_string_buffer(32)
-            if rt.cudaDeviceGetPCIBusId(buf, 32, local) == 0:
-                bdf = buf.value.decode()
-        if not bdf:
-            return info
-        bdf = bdf.lower()
-        if len(bdf.split(":")[0]) == 8:
-            bdf = bdf[4:]
+        pr = torch.cuda.get_device_properties(local)
+        # torch exposes the PCI address as three integers
+        bdf = f"{int(getattr(pr, 'pci_domain_id', 0)):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
         base = f"/sys/bus/pci/devices/{bdf}"
         node = int(open(base + "/numa_node").read().strip())
         cpulist = open(base + "/local_cpulist").read().strip()
@@ -83,10 +74,12 @@ def pin_to_gpu_numa_node(torch, local):
         for part in cpulist.split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        allowed = cpus & set(os.sched_getaffinity(0))
+        before = set(os.sched_getaffinity(0))
+        allowed = cpus & before
         if allowed:
             os.sched_setaffinity(0, allowed)
-            info = {"bound": True, "pci": bdf, "numa_node": node, "cpus": cpulist, "n_cpus": len(allowed)}
+            info = {"bound": True, "pci": bdf, "numa_node": node, "cpus": cpulist, "n_cpus": len(allowed),
+                    "restore": sorted(before)}
     except Exception as e:          # no sysfs / no permission: run unbound and say so
         info["error"] = str(e)[:80]
     return info
@@ -392,6 +385,8 @@ def run_ours(args):
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
+    if numa.get("restore"):
+        os.sched_setaffinity(0, set(numa.pop("restore")))      # the CPU legs below get every host core again
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         nd = args.cpu_distinct_frames
         host_frames = [frames[i].cpu().numpy() for i in range(nd)]     # same bytes as the numpy renderer (tests)
@@ -534,7 +529,8 @@ def run_c5_line(args, torch, dist, vs, rank, world, local, numa):
                 "roofline": {"bound": "hbm", "kernel": "warp", "achieved": r["warp_hbm_gbs"], "peak": peak, "unit": "GB/s",
                              "frac": (r["warp_hbm_gbs"] or 0.0) / peak, "traffic": None, "peak_source": peak_src,
                              "note": "smooth + warp + checksum phase of the job, algorithmic 2 x 3WH bytes per frame"},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "c5": r, "run": {"numa": numa},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "c5": r,
+                "run": {"numa": {k: v for k, v in numa.items() if k != "restore"}},
                 "note": "e2e: none -- the clip (2.5 TB) exists only on the device, chunk by chunk; the output is checksummed"}
         print(json.dumps(line), flush=True)
     if world > 1:
