@@ -184,7 +184,7 @@ VSTAB_D TileBox tile_box(const double* M, const uint8_t* src, size_t pitch, int 
 // rows of the frame, cut into 12-byte groups (4 pixels, the last group zero-padded) read as three little-endian words,
 //   checksum = sum_y sum_g (y + 1) (g + 1) (w0 + 3 w1 + 5 w2)   mod 2^64
 // (order-free, so every tiling and every shard split gives the same value; numpy twin: vstab_b200.frame_checksum).
-struct RowSums { unsigned long long a0 = 0, a1 = 0, a2 = 0; };
+struct RowSums { unsigned long long a = 0; };   // sum over the thread's rows of (y + 1) (w0 + 3 w1 + 5 w2)
 
 template <bool kCheck>
 VSTAB_D void store4(uint8_t* __restrict__ o, const unsigned* px, bool vec, int n, int y, RowSums& cs) {
@@ -192,11 +192,7 @@ VSTAB_D void store4(uint8_t* __restrict__ o, const unsigned* px, bool vec, int n
     if (vec) {
         unsigned* o32 = reinterpret_cast<unsigned*>(o);
         o32[0] = w0; o32[1] = w1; o32[2] = w2;
-        if (kCheck) {
-            cs.a0 += (unsigned long long)w0 * (unsigned)(y + 1);
-            cs.a1 += (unsigned long long)w1 * (unsigned)(y + 1);
-            cs.a2 += (unsigned long long)w2 * (unsigned)(y + 1);
-        }
+        if (kCheck) cs.a += ((unsigned long long)w0 + 3ull * w1 + 5ull * w2) * (unsigned)(y + 1);
     } else {
         for (int k = 0; k < n; ++k) {
             o[3 * k] = (uint8_t)(px[k] & 0xff); o[3 * k + 1] = (uint8_t)((px[k] >> 8) & 0xff); o[3 * k + 2] = (uint8_t)(px[k] >> 16);
@@ -208,9 +204,7 @@ VSTAB_D void store4(uint8_t* __restrict__ o, const unsigned* px, bool vec, int n
             const unsigned long long mlo = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
             const unsigned m2 = nb >= 12 ? ~0u : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
             const unsigned v0 = (unsigned)(lo & mlo), v1 = (unsigned)((lo & mlo) >> 32), v2 = w2 & m2;
-            cs.a0 += (unsigned long long)v0 * (unsigned)(y + 1);
-            cs.a1 += (unsigned long long)v1 * (unsigned)(y + 1);
-            cs.a2 += (unsigned long long)v2 * (unsigned)(y + 1);
+            cs.a += ((unsigned long long)v0 + 3ull * v1 + 5ull * v2) * (unsigned)(y + 1);
         }
     }
 }
@@ -319,7 +313,7 @@ VSTAB_D void compute_tile(const uint8_t* __restrict__ sm, const TileBox box, con
         compute_tile_border<false, kCheck>(sm, box, M, border, src, pitch, w, h, dst, out_pitch, tx0, ty0, tx, ty, cs);
     if (kCheck) {
         const unsigned long long g1 = (unsigned long long)((tx0 + tx * 4) >> 2) + 1ull;
-        unsigned long long c = (tx0 + tx * 4 < w) ? (cs.a0 + 3ull * cs.a1 + 5ull * cs.a2) * g1 : 0ull;
+        unsigned long long c = (tx0 + tx * 4 < w) ? cs.a * g1 : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (tx == 0) atomicAdd(check, c);
