@@ -98,6 +98,10 @@ int vstab_decompose_homography(const double H[9], double cx, double cy, vstab_hp
  * include/stabilizer.hpp:242, src/stabilizer.cpp:1535-1566 */
 void vstab_compose_homography(const vstab_hparams* p, double cx, double cy, double H[9]);
 
+/* The trail compositing branch of stabilizeFrame (src/stabilizer.cpp:1303-1307; `#if 0` in the reference, kept there for "GPU-
+ * accelerated implementations", include/stabilizer.hpp:255-259): every output is copyFeathered(presentation frame,
+ * trail background, H) and becomes the next trail background (zeros at the start, :128-130).  Off by default. */
+vstab_status vstab_set_trail(vstab_t* s, int enable);
 const char* vstab_last_error(const vstab_t* s);      /* message of the last non-OK status */
 const char* vstab_status_string(vstab_status st);
 int vstab_abi_version(void);
@@ -282,6 +286,10 @@ vstab_status vstab_k_fit(int device, const float* prev_pts, const float* next_pt
                          double M_out[6], double T_out[9], int counts_out[2]);
 vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, int cols, size_t step,
                           const double H[9], const uint8_t border[3], uint8_t* out, size_t out_step);
+/* Stabilizer::copyFeathered(foreground, background, H) (src/stabilizer.cpp:1051-1155): warp + feathered alpha blend over a
+ * darkened, blurred gray background; both images rows x cols BGR with the same step. */
+vstab_status vstab_k_copy_feathered(int device, const uint8_t* fg, const uint8_t* bg, int rows, int cols, size_t step,
+                                    const double H[9], uint8_t* out, size_t out_step);
 
 /* ORB / SIFT registration path (src/stabilizer.cpp:448-477 preprocessing, :483-491 + :605-606 ORB
  * detectAndCompute, :647-673 Hamming 2-NN + ratio test).  kps_out: 6 floats per keypoint
@@ -303,6 +311,10 @@ vstab_status vstab_k_sift(int device, const uint8_t* gray, int rows, int cols, d
  * d <= max(0.5 * mean(d), 0.02) (src/stabilizer.cpp:675-697).  best_d2: exact squared distances. */
 vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref, const uint8_t* cur, int ncur,
                              int* best_idx, int* best_d2, uint8_t* good);
+/* The same nearest-neighbour search for `nframes` current sets (concatenated rows, ncur[f] rows each) against one reference
+ * set in ONE launch; results [nframes][nref]; *ms_out (may be NULL) = device time of one launch averaged over `reps`. */
+vstab_status vstab_k_l2match_batch(int device, const uint8_t* ref, int nref, const uint8_t* cur, const int* ncur, int nframes,
+                                   int* best_idx, int* best_d2, int reps, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -520,6 +520,193 @@ def warp_perspective_bgr(src: np.ndarray, H: np.ndarray, border) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------
+# Feathered trail compositing: Stabilizer::copyFeathered   stabilizer.cpp:1051-1155
+# (behind `#if 0` at :1304 in the reference).  Integer restatements of the
+# OpenCV pieces it calls, each pinned against cv2 in tests/test_oracle_restate.py.
+# ----------------------------------------------------------------------------
+# cv::GaussianBlur on CV_8U runs in 8.8 fixed point; these are the kernels OpenCV derives for
+# ksize 7 / sigma 0 (the exact small-kernel table) and for ksize 101 / sigma 0 (sigma 15.5,
+# quantised with error diffusion so that the taps sum to 256), read off cv2's impulse response.
+GAUSS7_Q8 = np.array([8, 28, 56, 72, 56, 28, 8], np.int64)
+GAUSS101_Q8 = np.array([0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 1, 1, 2, 1, 2, 1, 2, 3, 2, 3, 3, 3, 3, 4,
+                        4, 4, 4, 5, 5, 5, 5, 6, 5, 6, 6, 7, 6, 7, 6, 7, 6, 7, 6, 7, 6, 7, 6, 6, 5, 6, 5, 5, 5, 5, 4, 4, 4, 4,
+                        3, 3, 3, 3, 2, 3, 2, 1, 2, 1, 2, 1, 1, 1, 1, 0, 1, 0, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0],
+                       np.int64)
+
+
+def _reflect101_any(i: np.ndarray, n: int) -> np.ndarray:
+    i = np.asarray(i).copy()
+    while ((i < 0) | (i >= n)).any():
+        i = np.abs(i)
+        i = np.where(i >= n, 2 * n - 2 - i, i)
+    return i
+
+
+def gaussian_blur_u8(img: np.ndarray, kq8: np.ndarray) -> np.ndarray:
+    """cv::GaussianBlur(u8, Size(k, k), 0) with BORDER_REFLECT_101: rows in 8.8 fixed point, columns in
+    16.16, rounded once: (sum + 2^15) >> 16."""
+    h, w = img.shape
+    r = len(kq8) // 2
+    xi = _reflect101_any(np.arange(-r, w + r), w)
+    yi = _reflect101_any(np.arange(-r, h + r), h)
+    a = img.astype(np.int64)[:, xi]
+    hs = sum(int(kq8[j]) * a[:, j:j + w] for j in range(len(kq8)))
+    b = hs[yi]
+    vs = sum(int(kq8[j]) * b[j:j + h] for j in range(len(kq8)))
+    return ((vs + 32768) >> 16).astype(np.uint8)
+
+
+def _cdiv(a: int, b: int) -> int:
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+def _clip_line(w, h, x1, y1, x2, y2):
+    """cv::clipLine (Cohen-Sutherland with truncating double arithmetic)."""
+    right, bottom = w - 1, h - 1
+    c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8
+    c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8
+    if (c1 & c2) == 0 and (c1 | c2) != 0:
+        if c1 & 12:
+            a = 0 if c1 < 8 else bottom
+            x1 += int(float(a - y1) * (x2 - x1) / (y2 - y1)); y1 = a
+            c1 = (x1 < 0) + (x1 > right) * 2
+        if c2 & 12:
+            a = 0 if c2 < 8 else bottom
+            x2 += int(float(a - y2) * (x2 - x1) / (y2 - y1)); y2 = a
+            c2 = (x2 < 0) + (x2 > right) * 2
+        if (c1 & c2) == 0 and (c1 | c2) != 0:
+            if c1:
+                a = 0 if c1 == 1 else right
+                y1 += int(float(a - x1) * (y2 - y1) / (x2 - x1)); x1 = a; c1 = 0
+            if c2:
+                a = 0 if c2 == 1 else right
+                y2 += int(float(a - x2) * (y2 - y1) / (x2 - x1)); x2 = a; c2 = 0
+    return (c1 | c2) == 0, x1, y1, x2, y2
+
+
+def fill_convex_poly_rows(w: int, h: int, pts) -> np.ndarray:
+    """cv::fillConvexPoly(mask, pts, 255) (8-connected, shift 0) as row spans: int32 [h, n + 1, 2] = per row the
+    {first, last} filled column of the interior scan line (span 0) and of the run each of the n outline segments
+    leaves on that row (first > last: empty).  The outline is drawn first with cv::line (clipLine, then Bresenham
+    from the LEFT end point -- a clipped segment is displaced from the true edge by up to a pixel, so it cannot be
+    merged into the interior span), then the interior scan lines with 16.16 fixed-point edges."""
+    v = [(int(x), int(y)) for x, y in pts]
+    n = len(v)
+    sp = np.empty((h, n + 1, 2), np.int64)
+    sp[:, :, 0] = w
+    sp[:, :, 1] = -1
+
+    def put(k, y, xa, xb):
+        if 0 <= y < h and xb >= 0 and xa < w:
+            sp[y, k, 0] = min(sp[y, k, 0], max(xa, 0)); sp[y, k, 1] = max(sp[y, k, 1], min(xb, w - 1))
+
+    p0 = v[-1]
+    for k, p in enumerate(v):
+        ok, x0, y0, x1, y1 = _clip_line(w, h, p0[0], p0[1], p[0], p[1])
+        if ok:
+            dx, dy = x1 - x0, y1 - y0
+            if dx < 0:
+                x0, y0, dx, dy = x1, y1, -dx, -dy
+            sy = 1 if dy >= 0 else -1
+            dy = abs(dy)
+            steep = dy > dx
+            if steep:
+                dx, dy = dy, dx
+            err, plus, minus = dx - 2 * dy, 2 * dx, -2 * dy
+            x, y = x0, y0
+            for _ in range(dx + 1):
+                put(k + 1, y, x, x)
+                m = err < 0
+                err += minus + (plus if m else 0)
+                if steep:
+                    y += sy; x += 1 if m else 0
+                else:
+                    x += 1; y += sy if m else 0
+        p0 = p
+    ys = [q[1] for q in v]
+    xs = [q[0] for q in v]
+    ymin, ymax = min(ys), max(ys)
+    if n < 3 or max(xs) < 0 or ymax < 0 or min(xs) >= w or ymin >= h:
+        return sp.astype(np.int32)
+    ymax = min(ymax, h - 1)
+    imin = ys.index(ymin)
+    one = 1 << 16
+    edge = [dict(idx=imin, di=1, x=-one, dx=0, ye=ymin), dict(idx=imin, di=n - 1, x=-one, dx=0, ye=ymin)]
+    y, edges = ymin, n
+    while True:
+        for e in edge:
+            if y >= e["ye"]:
+                idx0, di = e["idx"], e["di"]
+                idx = (idx0 + di) % n
+                while True:
+                    edges -= 1
+                    if edges < 0:
+                        break
+                    ty = v[idx][1]
+                    if ty > y:
+                        xs_, xe_ = v[idx0][0] << 16, v[idx][0] << 16
+                        e.update(ye=ty, dx=_cdiv((xe_ - xs_) * 2 + (ty - y), 2 * (ty - y)), x=xs_, idx=idx)
+                        break
+                    idx0, idx = idx, (idx + di) % n
+        if edges < 0:
+            break
+        if y >= 0:
+            l, r = (0, 1) if edge[0]["x"] <= edge[1]["x"] else (1, 0)
+            put(0, y, (edge[l]["x"] + (one >> 1)) >> 16, (edge[r]["x"] + (one >> 1)) >> 16)
+        edge[0]["x"] += edge[0]["dx"]; edge[1]["x"] += edge[1]["dx"]
+        y += 1
+        if y > ymax:
+            break
+    return sp.astype(np.int32)
+
+
+def mask_from_row_spans(sp: np.ndarray, w: int) -> np.ndarray:
+    xs = np.arange(w)[None, None, :]
+    return np.where(((xs >= sp[:, :, 0:1]) & (xs <= sp[:, :, 1:2])).any(axis=1), 255, 0).astype(np.uint8)
+
+
+def perspective_points(pts: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """cv::perspectiveTransform on CV_32FC2 (double accumulators, result cast to float) followed by the
+    Point2f -> Point conversion of stabilizer.cpp:1107-1110 (cvRound: half to even)."""
+    out = []
+    for x, y in np.asarray(pts, np.float32):
+        x, y = float(x), float(y)
+        w = x * H[2, 0] + y * H[2, 1] + H[2, 2]
+        if abs(w) > np.finfo(np.float32).eps:
+            w = 1.0 / w
+            fx, fy = F32((x * H[0, 0] + y * H[0, 1] + H[0, 2]) * w), F32((x * H[1, 0] + y * H[1, 1] + H[1, 2]) * w)
+        else:
+            fx = fy = F32(0)
+        out.append((int(np.rint(fx)), int(np.rint(fy))))
+    return np.array(out, np.int64)
+
+
+def warp_perspective_gray(src: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """warpPerspective of a 1-channel u8 image, INTER_LINEAR, constant border 0 (same Q5 / Q15 path)."""
+    return warp_perspective_bgr(np.repeat(src[:, :, None], 3, axis=2), H, (0.0, 0.0, 0.0))[:, :, 0]
+
+
+def copy_feathered(fg: np.ndarray, bg: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """Stabilizer::copyFeathered (stabilizer.cpp:1051-1155) without OpenCV."""
+    h, w = fg.shape[:2]
+    warped = warp_perspective_bgr(fg, H, (0.0, 0.0, 0.0)).astype(np.float32)                 # :1069-1073
+    g = bgr2gray(bg)                                                                         # :1078-1079
+    g = gaussian_blur_u8(g, GAUSS7_Q8)                                                       # :1081-1082
+    g = np.rint(g.astype(np.float32) * F32(0.99)).astype(np.uint8)                           # :1085
+    bgf = g.astype(np.float32)[:, :, None]                                                   # :1087-1090 (3 equal channels)
+    B = 10                                                                                   # :1096
+    corners = np.float32([[B, B], [w - B, B], [w - B, h - B], [B, h - B]])
+    poly = perspective_points(corners, H)                                                    # :1104-1110
+    mask = mask_from_row_spans(fill_convex_poly_rows(w, h, poly), w)                         # :1113
+    mask = warp_perspective_gray(mask, H)                                                    # :1116-1118 (warped AGAIN by H)
+    alpha = gaussian_blur_u8(mask, GAUSS101_Q8).astype(np.float32) * F32(1.0 / 255.0)        # :1121-1129
+    alpha = alpha[:, :, None]
+    out = alpha * warped + (F32(1.0) - alpha) * bgf                                          # :1137-1147
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)                                    # :1151
+
+
+# ----------------------------------------------------------------------------
 # A.10 estimateAffinePartial2D -> closed-form LS similarity on an inlier set
 # ----------------------------------------------------------------------------
 def ls_similarity(src: np.ndarray, dst: np.ndarray) -> np.ndarray:

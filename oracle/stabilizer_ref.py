@@ -149,6 +149,34 @@ def compose_homography(p: HomographyParameters, center=(0.0, 0.0)) -> np.ndarray
     return H
 
 
+def copy_feathered(foreground: np.ndarray, background_image: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """Stabilizer::copyFeathered, stabilizer.cpp:1051-1155, call for call over cv2 (the reference keeps it behind
+    `#if 0` at :1304; `StabilizerRef(trail=True)` takes that branch)."""
+    if foreground.shape != background_image.shape:
+        raise ValueError("Stabilizer: copyFeathered: foreground and background_image must have the same size")
+    H = np.asarray(H)
+    if H.shape != (3, 3) or H.dtype != np.float64 or not np.all(np.isfinite(H)):
+        raise ValueError("Stabilizer: copyFeathered: Bad homography matrix H.")
+    h, w = foreground.shape[:2]
+    warped = cv2.warpPerspective(foreground, H, (w, h)).astype(np.float32)
+    bg = cv2.cvtColor(background_image, cv2.COLOR_BGR2GRAY)
+    bg = cv2.GaussianBlur(bg, (7, 7), 0)
+    bg = cv2.multiply(bg, 0.99)                                   # background_image_changed *= 0.99
+    bgf = cv2.cvtColor(bg, cv2.COLOR_GRAY2BGR).astype(np.float32)
+    B = 10
+    corners = np.float32([[B, B], [w - B, B], [w - B, h - B], [B, h - B]]).reshape(-1, 1, 2)
+    tc = cv2.perspectiveTransform(corners, H).reshape(-1, 2)
+    poly = np.array([[int(np.rint(x)), int(np.rint(y))] for x, y in tc], np.int32)     # cv::Point(Point2f): cvRound
+    mask = np.zeros((h, w), np.uint8)
+    cv2.fillConvexPoly(mask, poly, 255)
+    mask = cv2.warpPerspective(mask, H, (w, h))
+    alpha = cv2.GaussianBlur(mask, (101, 101), 0, 0).astype(np.float32) * np.float32(1.0 / 255.0)
+    alpha3 = cv2.cvtColor(alpha, cv2.COLOR_GRAY2BGR)
+    fgc = cv2.multiply(alpha3, warped)
+    bgc = cv2.multiply(1.0 - alpha3, bgf)
+    return np.clip(np.rint(cv2.add(fgc, bgc)), 0, 255).astype(np.uint8)
+
+
 def filter_keypoints_by_relative_size(image_height, kps, desc, max_rel=0.05):
     """stabilizer.cpp:290-309 (float compare: size < float(image_height*ratio))."""
     max_allowed = np.float32(np.float32(image_height) * np.float32(max_rel))
@@ -184,7 +212,7 @@ class StabilizerRef:
 
     def __init__(self, past_frames: int = 15, future_frames: int = 15,
                  working_height: int = 360, faithful_waste: bool = True,
-                 exact_sift_matcher: bool = False):
+                 exact_sift_matcher: bool = False, trail: bool = False):
         # stabilizer.cpp:36-53
         if past_frames == 0 and future_frames == 0:
             raise ValueError("Stabilizer: pastFrames and futureFrames cannot both be 0")
@@ -195,6 +223,7 @@ class StabilizerRef:
         self.P, self.F, self.wh = past_frames, future_frames, working_height
         self.faithful_waste = faithful_waste
         self.exact_sift_matcher = exact_sift_matcher
+        self.trail = trail                      # take the `#if 0` copyFeathered branch of stabilizeFrame (:1303-1307)
         self.scale = 1.0
         self.orig_size = (0, 0)      # (w, h)
         self.work_size = (0, 0)
@@ -243,8 +272,8 @@ class StabilizerRef:
             self.orig_size = (cols, rows)
             self.scale = float(self.wh) / rows
             self.work_size = (int(cols * self.scale), self.wh)
-        if self.faithful_waste and (self.trail_background is None):
-            self.trail_background = np.zeros_like(frame)
+        if (self.faithful_waste or self.trail) and (self.trail_background is None):
+            self.trail_background = np.zeros_like(frame)             # :128-130
 
     def _detect_new_features(self, gray):        # stabilizer.cpp:931-980
         ratio = float(gray.shape[0]) / 720.0
@@ -410,7 +439,7 @@ class StabilizerRef:
     def stabilize_frame(self, frame: np.ndarray) -> np.ndarray:   # stabilizer.cpp:1158-1325
         self._initialize_frame(frame)
         t0 = time.perf_counter()
-        if self.faithful_waste:
+        if self.faithful_waste and self.trail_background is not None:
             _ = self.trail_background.copy()                     # :1163 -> :129
         idx = self.frames[-1][1] + 1 if self.frames else 0       # :152-168
         self.frames.append((frame.copy(), idx))
@@ -489,9 +518,13 @@ class StabilizerRef:
         avg = tuple(0.5 * v for v in m)
         self.timers["mean"] += time.perf_counter() - t0
         t0 = time.perf_counter()
-        out = cv2.warpPerspective(pres, H_scaled, (frame.shape[1], frame.shape[0]),
-                                  flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
-                                  borderValue=avg)
+        if self.trail:                                           # the `#if 0` branch, :1303-1307
+            out = copy_feathered(pres, self.trail_background, H_scaled)
+            self.trail_background = out.copy()
+        else:
+            out = cv2.warpPerspective(pres, H_scaled, (frame.shape[1], frame.shape[0]),
+                                      flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                                      borderValue=avg)
         self.timers["warp"] += time.perf_counter() - t0
 
         self.prev_pts = self._detect_new_features(gray)          # :1318-1319

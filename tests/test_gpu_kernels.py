@@ -236,3 +236,22 @@ def test_warp_golden(golden):
     bv = [int(np.clip(np.rint(b), 0, 255)) for b in golden["warp_border"]]
     for i in range(2):
         assert np.array_equal(vs.k_warp(f0, golden[f"warp_H{i}"], bv), golden[f"warp_out{i}"])
+
+
+# ------------------------------------------------------------------ K14 feathered trail (copyFeathered)
+@pytest.mark.parametrize("shape", [(360, 640), (250, 333), (720, 1280)])
+def test_copy_feathered_bit_exact(texture, shape):
+    """K14 == Stabilizer::copyFeathered over cv2 (src/stabilizer.cpp:1051-1155): warp + 7x7 / 101x101 fixed-point Gaussians
+    + fillConvexPoly mask + float blend, byte for byte -- also when the warped polygon leaves the image."""
+    h, w = shape
+    fs = render_clip(texture, w, h, 2, start=11)
+    fg, bg = fs[0], fs[1]
+    for th, tx, ty in ((0.0, 0.0, 0.0), (0.02, 7.3, -4.1), (-0.05, -30.5, 12.25), (0.11, 60.0, 45.0)):
+        Hm = _rigid(th, tx, ty)
+        ref = sr.copy_feathered(fg, bg, Hm)
+        assert np.array_equal(vs.k_copy_feathered(fg, bg, Hm), ref)
+    # a black trail background (the first call) and a projective H
+    Hm = _rigid(0.01, 3.0, 2.0)
+    Hm[2, 0] = 1e-5
+    z = np.zeros_like(fg)
+    assert np.array_equal(vs.k_copy_feathered(fg, z, Hm), sr.copy_feathered(fg, z, Hm))

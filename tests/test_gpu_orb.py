@@ -130,6 +130,12 @@ def test_l2_match_tcgen05_equals_bfmatcher(texture):
     assert np.array_equal(np.sqrt(bd2.astype(np.float32)), want_d)
     avg = float(np.sum(want_d.astype(np.float64))) / len(d0)
     assert np.array_equal(good.astype(bool), want_d.astype(np.float64) <= max(avg * 0.5, 0.02))
+    # a batch of current sets against the one reference set in ONE launch (frames along the grid's z axis)
+    sets = [d1, d1[:1000], d0[::-1].copy(), d1[300:301]]
+    bis, bds, _ = vs.k_l2match_batch(d0, sets)
+    for k, c in enumerate(sets):
+        dd = ((d0.astype(np.int64)[:, None, :] - c.astype(np.int64)[None, :, :]) ** 2).sum(-1)
+        assert np.array_equal(bds[k], dd.min(1)) and np.array_equal(bis[k], dd.argmin(1))
     # ragged sizes: a non-multiple of the 128-row tiles on both sides, and a single train row
     for nr, nc in ((300, 77), (129, 1), (5, 2500)):
         bi, bd2, _ = vs.k_l2match(d0[:nr], d1[:nc])

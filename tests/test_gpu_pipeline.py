@@ -354,3 +354,20 @@ def test_config4_sift_pipeline_at_4k_working_height_2160():
     assert s["h_px"] <= H_TOL_PX
     print(f"SIFT lock 4K / 2160: worst corner difference {s['h_px']:.4f} px, max pixel difference {s['max_lsb']} LSB, "
           f"{s['px_gt1']} of {s['px_total']} px off by more than 1 LSB")
+
+
+def test_trail_branch_matches_oracle(texture_small):
+    """The copyFeathered branch of stabilizeFrame (`#if 0` at src/stabilizer.cpp:1304 in the reference, kept for GPU
+    implementations): every output is the feathered blend over the running trail background -- the error of one frame would
+    feed every later one, so the whole sequence must carry the oracle's bytes."""
+    frames = render_clip(texture_small, 480, 270, 14)
+    ref = sr.StabilizerRef(4, 3, 135, trail=True)
+    st = vs.Stabilizer(4, 3, 135)
+    st.set_trail(True)
+    for i, f in enumerate(frames):
+        if i == 8:
+            ref.set_stabilization_mode(sr.ACCUMULATED_FULL_LOCK)
+            st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
+        want, got = ref.stabilize_frame(f), st.stabilize_frame(f)
+        assert np.array_equal(got, want), f"call {i}: {int(np.abs(got.astype(int) - want).max())} LSB"
+    st.close()

@@ -161,3 +161,51 @@ def test_ransac_random_vs_cv2():
         M, mask = R.estimate_affine_partial_2d(p, q, 3.0)
         assert np.array_equal(mask, inl.reshape(-1))
         assert np.abs(M - Mr).max() < 1e-8
+
+
+# ---------------------------------------------------------------- copyFeathered (stabilizer.cpp:1051-1155)
+def test_gaussian_blur_u8_fixed_point_tables():
+    """cv::GaussianBlur on u8 is 8.8 / 16.16 fixed point with these tap tables (7x7 and 101x101, sigma 0)."""
+    import cv2
+    rng = np.random.default_rng(0)
+    for shape in ((90, 120), (270, 480), (37, 53)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(R.gaussian_blur_u8(img, R.GAUSS7_Q8), cv2.GaussianBlur(img, (7, 7), 0))
+        if min(shape) > 50:
+            assert np.array_equal(R.gaussian_blur_u8(img, R.GAUSS101_Q8), cv2.GaussianBlur(img, (101, 101), 0, 0))
+    assert R.GAUSS7_Q8.sum() == 256 and R.GAUSS101_Q8.sum() == 256
+
+
+def test_fill_convex_poly_rows_equal_opencv():
+    """clipLine + left-to-right Bresenham outline + 16.16 scan-line edges == cv2.fillConvexPoly on warped inset rectangles,
+    including vertices outside the image."""
+    import cv2
+    rng = np.random.default_rng(1)
+    for _ in range(120):
+        w, h = int(rng.integers(60, 400)), int(rng.integers(40, 300))
+        ang, s = rng.uniform(-0.25, 0.25), rng.uniform(0.85, 1.15)
+        Hm = np.array([[s * np.cos(ang), -s * np.sin(ang), rng.uniform(-40, 40)], [s * np.sin(ang), s * np.cos(ang), rng.uniform(-40, 40)],
+                       [0, 0, 1.0]])
+        c = np.float32([[10, 10], [w - 10, 10], [w - 10, h - 10], [10, h - 10]])
+        poly = R.perspective_points(c, Hm)
+        t = cv2.perspectiveTransform(c.reshape(-1, 1, 2), Hm).reshape(-1, 2)
+        assert np.array_equal(poly, np.array([[int(np.rint(x)), int(np.rint(y))] for x, y in t]))
+        ref = np.zeros((h, w), np.uint8)
+        cv2.fillConvexPoly(ref, poly.astype(np.int32), 255)
+        assert np.array_equal(R.mask_from_row_spans(R.fill_convex_poly_rows(w, h, poly), w), ref)
+
+
+def test_copy_feathered_restatement_equals_opencv():
+    """The integer restatement of Stabilizer::copyFeathered == the reference's cv2 call sequence, byte for byte."""
+    import cv2
+    from oracle import stabilizer_ref as sr
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        w, h = int(rng.integers(120, 360)), int(rng.integers(110, 260))
+        fg = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 1.2)
+        bg = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 2.0)
+        ang = rng.uniform(-0.08, 0.08)
+        Hm = np.array([[np.cos(ang), -np.sin(ang), rng.uniform(-25, 25)], [np.sin(ang), np.cos(ang), rng.uniform(-25, 25)], [0, 0, 1.0]])
+        assert np.array_equal(R.copy_feathered(fg, bg, Hm), sr.copy_feathered(fg, bg, Hm))
+    with pytest.raises(ValueError):
+        sr.copy_feathered(fg, bg[:-1], Hm)

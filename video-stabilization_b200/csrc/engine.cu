@@ -216,6 +216,8 @@ struct vstab {
     OrbPlan* orb = nullptr;
     SiftPlan* sift = nullptr;
     bool has_reference = false;
+    bool trail = false;                     // copyFeathered branch of stabilizeFrame (:1303-1307)
+    DevBuf trail_bg, trail_ws;              // trail_background_ (:129) and K14 scratch
     DevBuf feat_ws, feat_gray, nn_x, nn_y, ref_kps, ref_desc, cur_kps, cur_desc, orb_counts, m_idx, m_d0, m_d1, m_good,
         m_ref, m_cur, m_status, lock_fit, lock_h, lock_tap;
     std::string err;
@@ -444,8 +446,20 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
         s->feat_p = pn;
         s->feat_pending = true;
     }
-    launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
-                d_out, out_pitch, 0, q);                                                               // :1309-1313
+    if (s->trail) {
+        // presentation_output = copyFeathered(presentation_image, trail_background_, H); trail_background_ = its clone (:1303-1307)
+        if (!s->trail_bg.p) {
+            CK(s->trail_bg.alloc(g.frame_bytes + 64));
+            CK(s->trail_ws.alloc(trail_workspace_bytes(g.cols, g.rows, g.frame_bytes)));
+            CK(cudaMemsetAsync(s->trail_bg.p, 0, g.frame_bytes, q));                                   // Mat::zeros, :128-130
+        }
+        launch_trail(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), -1, s->trail_bg.as<uint8_t>(),
+                     g.cols, g.rows, s->trail_ws.p, d_out, out_pitch, q);
+        CK(cudaMemcpy2DAsync(s->trail_bg.p, g.pitch, d_out, out_pitch, (size_t)g.cols * 3, g.rows, cudaMemcpyDeviceToDevice, q));
+    } else {
+        launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
+                    d_out, out_pitch, 0, q);                                                           // :1309-1313
+    }
     s->mark(9, q);
     CK(cudaGetLastError());
     s->last_presented = p;
@@ -1841,6 +1855,35 @@ extern "C" vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, i
     return VSTAB_OK;
 }
 
+extern "C" vstab_status vstab_set_trail(vstab_t* s, int enable) {
+    if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
+    s->trail = enable != 0;
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_k_copy_feathered(int device, const uint8_t* fg, const uint8_t* bg, int rows, int cols, size_t step,
+                                               const double H[9], uint8_t* out, size_t out_step) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!fg || !bg || !H || !out || rows < 1 || cols < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!finite9(H)) { g_err = "Stabilizer: copyFeathered: Bad homography matrix H."; return VSTAB_ERR_INVALID_ARGUMENT; }
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    const size_t pitch = align_up((size_t)cols * 3, 16);
+    const size_t fb = align_up(pitch * (size_t)rows, 256);
+    DevBuf dfg, dbg, dout, wp, ws;
+    CK(dfg.alloc(fb + 64)); CK(dbg.alloc(fb + 64)); CK(dout.alloc(fb + 64)); CK(wp.alloc(sizeof(WarpParams)));
+    CK(ws.alloc(trail_workspace_bytes(cols, rows, fb)));
+    CK(cudaMemcpy2D(dfg.p, pitch, fg, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(dbg.p, pitch, bg, step, (size_t)cols * 3, rows, cudaMemcpyHostToDevice));
+    WarpParams h{};
+    for (int i = 0; i < 9; ++i) { h.Hs[i] = H[i]; h.Hw[i] = H[i]; }
+    invert3(H, h.Minv);
+    CK(cudaMemcpy(wp.p, &h, sizeof(h), cudaMemcpyHostToDevice));
+    launch_trail(dfg.as<uint8_t>(), pitch, 0, 0, wp.as<WarpParams>(), 0, dbg.as<uint8_t>(), cols, rows, ws.p, dout.as<uint8_t>(), pitch, 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2D(out, out_step, dout.p, pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
 // ---- ORB / SIFT registration path: single-kernel entry points (host buffers) ------------------
 extern "C" vstab_status vstab_k_featprep(int device, const uint8_t* bgr, int rows, int cols, size_t step,
                                          int working_height, uint8_t* gray_out) {
@@ -1952,6 +1995,48 @@ extern "C" vstab_status vstab_k_l2match(int device, const uint8_t* ref, int nref
     CK(cudaMemcpy(best_idx, bi.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(best_d2, bd.p, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(good, gd.p, (size_t)nref, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+// The nearest-neighbour search of K12 for a batch of current sets against one reference set in ONE launch (frames stacked
+// along the grid's z axis): cur is [nframes][max_rows][128], ncur[nframes]; results [nframes][nref].  `reps` > 1 repeats the
+// launch and returns the average device time in *ms_out (CUDA events) for the tensor-pipe measurement.
+extern "C" vstab_status vstab_k_l2match_batch(int device, const uint8_t* ref, int nref, const uint8_t* cur, const int* ncur,
+                                              int nframes, int* best_idx, int* best_d2, int reps, float* ms_out) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!ref || !cur || !ncur || !best_idx || !best_d2 || nref < 0 || nref > kOrbMaxKp || nframes < 1 || nframes > 256) return VSTAB_ERR_INVALID_ARGUMENT;
+    for (int f = 0; f < nframes; ++f) if (ncur[f] < 0 || ncur[f] > kOrbMaxKp) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    DevBuf a, b, na, nb, bi, bd, scr;
+    CK(a.alloc((size_t)128 * kOrbMaxKp)); CK(b.alloc((size_t)128 * kOrbMaxKp * nframes)); CK(na.alloc(4)); CK(nb.alloc(4 * (size_t)nframes));
+    CK(bi.alloc(4 * (size_t)kOrbMaxKp * nframes)); CK(bd.alloc(4 * (size_t)kOrbMaxKp * nframes));
+    CK(scr.alloc(l2_match_scratch_bytes(kOrbMaxKp, nframes)));
+    CK(cudaMemset(a.p, 0, (size_t)128 * kOrbMaxKp)); CK(cudaMemset(b.p, 0, (size_t)128 * kOrbMaxKp * nframes));
+    CK(cudaMemcpy(a.p, ref, (size_t)128 * nref, cudaMemcpyHostToDevice));
+    size_t off = 0;
+    for (int f = 0; f < nframes; ++f) {
+        CK(cudaMemcpy(b.as<uint8_t>() + (size_t)f * kOrbMaxKp * 128, cur + off, (size_t)128 * ncur[f], cudaMemcpyHostToDevice));
+        off += (size_t)128 * ncur[f];
+    }
+    CK(cudaMemcpy(na.p, &nref, 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(nb.p, ncur, 4 * (size_t)nframes, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int R = reps > 0 ? reps : 1;
+    launch_l2_nn_batch(a.as<uint8_t>(), na.as<int>(), b.as<uint8_t>(), nb.as<int>(), kOrbMaxKp, nframes, scr.p, bi.as<int>(), bd.as<int>(), 0);   // warm-up
+    CK(cudaEventRecord(e0, 0));
+    for (int r = 0; r < R; ++r)
+        launch_l2_nn_batch(a.as<uint8_t>(), na.as<int>(), b.as<uint8_t>(), nb.as<int>(), kOrbMaxKp, nframes, scr.p, bi.as<int>(), bd.as<int>(), 0);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms / (float)R;
+    for (int f = 0; f < nframes; ++f) {
+        CK(cudaMemcpy(best_idx + (size_t)f * nref, bi.as<int>() + (size_t)f * kOrbMaxKp, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(best_d2 + (size_t)f * nref, bd.as<int>() + (size_t)f * kOrbMaxKp, 4 * (size_t)nref, cudaMemcpyDeviceToHost));
+    }
     return VSTAB_OK;
 }
 

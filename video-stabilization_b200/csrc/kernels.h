@@ -132,6 +132,12 @@ void launch_warp(const uint8_t* frames, size_t pitch, size_t frame_stride, long 
                  uint8_t* out, size_t out_pitch, size_t out_frame_stride, cudaStream_t st,
                  unsigned long long* check = nullptr /* [nout], pre-zeroed: per-frame output checksum (warp.cu) */);
 
+// ---------------------------------------------------------------- K14 feathered trail compositing (copyFeathered)
+size_t trail_workspace_bytes(int w, int h, size_t frame_bytes);
+// out = copyFeathered(frames[slot], bg, wp->Hs) (src/stabilizer.cpp:1051-1155); src_slot < 0: the slot named by *wp
+void launch_trail(const uint8_t* frames, size_t pitch, size_t frame_stride, long slot_mod, const WarpParams* wp, int src_slot,
+                  const uint8_t* bg, int w, int h, void* workspace, uint8_t* out, size_t out_pitch, cudaStream_t st);
+
 // ---------------------------------------------------------------- K8 feature-path preprocessing
 void build_nn_table(int src, int dst, int* host_tab);                       // cv::resize INTER_NEAREST offsets
 size_t featprep_workspace_bytes(int w, int h);

@@ -80,6 +80,8 @@ SYMBOLS = {
     "vstab_decompose_homography": (C.c_int, [_f64p, C.c_double, C.c_double, C.POINTER(HParams)]),
     "vstab_compose_homography": (None, [C.POINTER(HParams), C.c_double, C.c_double, _f64p]),
     "vstab_last_error": (C.c_char_p, [_vp]),
+    "vstab_set_trail": (C.c_int, [_vp, C.c_int]),
+    "vstab_k_copy_feathered": (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _f64p, _vp, C.c_size_t]),
     "vstab_host_alloc": (_vp, [C.c_size_t]),
     "vstab_host_free": (None, [_vp]),
     "vstab_read_tap": (C.c_long, [_vp, C.c_int, _vp, C.c_size_t]),
@@ -125,6 +127,7 @@ SYMBOLS = {
     "vstab_k_orb": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
     "vstab_k_hamming": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_float, _vp, _vp, _vp, _vp]),
     "vstab_k_l2match": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "vstab_k_l2match_batch": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.POINTER(C.c_int), C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
     "vstab_k_sift": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_double, _vp, _vp, C.POINTER(C.c_int), C.c_int]),
 }
 
@@ -217,6 +220,10 @@ class Stabilizer:
 
     def total_frame_window_size(self) -> int:
         return int(self._lib.vstab_total_frame_window_size(self._h))
+
+    def set_trail(self, enable: bool) -> None:
+        """The copyFeathered branch of stabilizeFrame (src/stabilizer.cpp:1303-1307), off by default as in the reference."""
+        _check(self._lib.vstab_set_trail(self._h, 1 if enable else 0), self._h)
 
     def set_stabilization_mode(self, mode: int) -> None:
         _check(self._lib.vstab_set_mode(self._h, int(mode)), self._h)
@@ -377,6 +384,20 @@ def k_warp(bgr: np.ndarray, H: np.ndarray, border, device: int = 0):
     return out
 
 
+def k_copy_feathered(fg: np.ndarray, bg: np.ndarray, H: np.ndarray, device: int = 0) -> np.ndarray:
+    """Stabilizer::copyFeathered (src/stabilizer.cpp:1051-1155) on the GPU."""
+    lib = load_library()
+    fg = np.ascontiguousarray(fg)
+    bg = np.ascontiguousarray(bg)
+    if fg.shape != bg.shape:
+        raise ValueError("Stabilizer: copyFeathered: foreground and background_image must have the same size")
+    H = np.ascontiguousarray(H, np.float64)
+    out = np.empty_like(fg)
+    _check(lib.vstab_k_copy_feathered(device, _ptr(fg), _ptr(bg), fg.shape[0], fg.shape[1], fg.strides[0],
+                                      H.ctypes.data_as(_f64p), _ptr(out), out.strides[0]))
+    return out
+
+
 def k_featprep(bgr: np.ndarray, working_height: int, device: int = 0) -> np.ndarray:
     """ORB/SIFT preprocessing chain of the reference (src/stabilizer.cpp:448-477) on the GPU."""
     lib = load_library()
@@ -423,6 +444,19 @@ def k_l2match(ref: np.ndarray, cur: np.ndarray, device: int = 0):
     bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); good = np.zeros(n, np.uint8)
     _check(lib.vstab_k_l2match(device, _ptr(ref8), n, _ptr(cur8), len(cur8), _ptr(bi), _ptr(bd), _ptr(good)))
     return bi, bd, good
+
+
+def k_l2match_batch(ref: np.ndarray, curs, reps: int = 1, device: int = 0):
+    """Nearest neighbours of every row of `ref` in each of the descriptor sets `curs` (one launch for the whole batch)
+    -> (best_idx [n, nref], best_d2 [n, nref], ms per launch)."""
+    lib = load_library()
+    ref8 = np.ascontiguousarray(ref, np.uint8)
+    cat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.uint8) for c in curs], 0))
+    ncur = (C.c_int * len(curs))(*[len(c) for c in curs])
+    bi = np.zeros((len(curs), len(ref8)), np.int32); bd = np.zeros((len(curs), len(ref8)), np.int32)
+    ms = C.c_float(0)
+    _check(lib.vstab_k_l2match_batch(device, _ptr(ref8), len(ref8), _ptr(cat), ncur, len(curs), _ptr(bi), _ptr(bd), reps, C.byref(ms)))
+    return bi, bd, float(ms.value)
 
 
 def k_sift(gray: np.ndarray, size_ratio: float = 0.0, device: int = 0):
