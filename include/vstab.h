@@ -210,6 +210,10 @@ void vstab_offline_set_timing(vstab_offline_t* o, int enable);
 vstab_status vstab_offline_stage_times(vstab_offline_t* o, float* ms, int* counts);
 /* number of this library's kernels launched by the process so far */
 long long vstab_launch_count(void);
+/* VSTAB_GUARD=1 in the environment puts every device buffer of the library between two 4 KB guard bands; when a buffer is
+ * released the bands are read back.  Bytes found overwritten so far (out-of-bounds writes) / buffers allocated with bands. */
+long long vstab_debug_guard_violations(void);
+long long vstab_debug_guard_buffers(void);
 /* device-side H_stabilize_scaled of the last render (9 doubles per call) for parity tests */
 long vstab_offline_read_h(vstab_offline_t* o, double* dst, size_t n_calls);
 /* cudaStream_t of the instance, as an integer handle, so callers can order NCCL work after it */

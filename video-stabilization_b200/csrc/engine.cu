@@ -101,12 +101,58 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 thread_local std::string g_err;   // for entry points without an instance
 void nccl_comm_destroy(void* comm);
 
+// VSTAB_GUARD=1 (tests): every device buffer of the library is allocated between two 4 KB guard bands filled with a pattern;
+// when the buffer is released the bands are read back and every byte that changed counts as an out-of-bounds WRITE
+// (vstab_debug_guard_violations).  compute-sanitizer is closed on the GPU pool this was developed on; this is the bounds
+// check "of your own" that runs in its place over the whole GPU test suite (tests/conftest.py).
+constexpr size_t kGuardBytes = 4096;
+std::atomic<long long> g_guard_violations{0};
+std::atomic<long long> g_guard_buffers{0};
+inline bool guard_enabled() {
+    static const bool on = getenv("VSTAB_GUARD") && atoi(getenv("VSTAB_GUARD")) != 0;
+    return on;
+}
+
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    size_t guarded_bytes = 0;               // > 0: p sits kGuardBytes into an allocation of guarded_bytes + 2 * kGuardBytes
+    ~DevBuf() { release(); }
+    void release() {
+        if (!p) return;
+        if (guarded_bytes) {
+            unsigned char* base = (unsigned char*)p - kGuardBytes;
+            std::vector<unsigned char> g(2 * kGuardBytes);
+            if (cudaMemcpy(g.data(), base, kGuardBytes, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                cudaMemcpy(g.data() + kGuardBytes, (unsigned char*)p + guarded_bytes, kGuardBytes, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                long long bad = 0;
+                for (unsigned char c : g) bad += c != 0xA5;
+                if (bad) {
+                    g_guard_violations.fetch_add(bad);
+                    fprintf(stderr, "[vstab guard] %lld byte(s) written outside a %zu-byte device buffer\n", bad, guarded_bytes);
+                }
+            } else {
+                cudaGetLastError();
+            }
+            cudaFree(base);
+        } else {
+            cudaFree(p);
+        }
+        p = nullptr; guarded_bytes = 0;
+    }
     cudaError_t alloc(size_t bytes) {
-        if (p) { cudaFree(p); p = nullptr; }
-        return cudaMalloc(&p, bytes ? bytes : 1);
+        release();
+        if (!bytes) bytes = 1;
+        if (!guard_enabled()) return cudaMalloc(&p, bytes);
+        const size_t padded = (bytes + 255) & ~(size_t)255;        // keep the tail band's start aligned; slack bytes are guard too
+        void* base = nullptr;
+        cudaError_t e = cudaMalloc(&base, padded + 2 * kGuardBytes);
+        if (e != cudaSuccess) return e;
+        cudaMemset(base, 0xA5, kGuardBytes);
+        cudaMemset((unsigned char*)base + kGuardBytes + bytes, 0xA5, padded - bytes + kGuardBytes);
+        p = (unsigned char*)base + kGuardBytes;
+        guarded_bytes = bytes;
+        g_guard_buffers.fetch_add(1);
+        return cudaSuccess;
     }
     template <typename T> T* as() const { return (T*)p; }
 };
@@ -1362,6 +1408,9 @@ extern "C" vstab_status vstab_offline_stage_times(vstab_offline_t* o, float* ms,
 }
 
 extern "C" long long vstab_launch_count(void) { return vstabk::launch_count(); }
+// VSTAB_GUARD=1: bytes found overwritten in the guard bands of released device buffers so far, and buffers checked
+extern "C" long long vstab_debug_guard_violations(void) { return g_guard_violations.load(); }
+extern "C" long long vstab_debug_guard_buffers(void) { return g_guard_buffers.load(); }
 
 extern "C" long vstab_offline_read_h(vstab_offline_t* o, double* dst, size_t n_calls) {
     if (!o || !dst) return -1;

@@ -344,32 +344,47 @@ l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned taddr = tmem + (unsigned)(a * TN) + ((unsigned)(q * 32) << 16);
             int best = 0x7fffffff;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TN; c0 += 32) {
-                unsigned r[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr + (unsigned)c0)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int4* kc4 = reinterpret_cast<const int4*>(&S.kc[a][c0]);
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const int4 k4 = kc4[c >> 2];
-                    best = min(best, (int)r[c] * -2 * TN + k4.x);
-                    best = min(best, (int)r[c + 1] * -2 * TN + k4.y);
-                    best = min(best, (int)r[c + 2] * -2 * TN + k4.z);
-                    best = min(best, (int)r[c + 3] * -2 * TN + k4.w);
-                }
+            // two register buffers of 32 columns: the TMEM load of the next chunk is in flight while this one is folded
+            unsigned r0[32], r1[32];
+#define VSTAB_TMEM_LD32(r, col)                                                                                                   \
+            asm volatile(                                                                                                         \
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "  \
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                         \
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),     \
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),          \
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),         \
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                       \
+                : "r"(taddr + (unsigned)(col))                                                                                    \
+                : "memory")
+#define VSTAB_FOLD32(r, col)                                                                                                      \
+            {                                                                                                                     \
+                const int4* kc4 = reinterpret_cast<const int4*>(&S.kc[a][col]);                                                   \
+                _Pragma("unroll") for (int c = 0; c < 32; c += 4) {                                                               \
+                    const int4 k4 = kc4[c >> 2];                                                                                  \
+                    best = min(best, (int)r[c] * -2 * TN + k4.x);                                                                 \
+                    best = min(best, (int)r[c + 1] * -2 * TN + k4.y);                                                             \
+                    best = min(best, (int)r[c + 2] * -2 * TN + k4.z);                                                             \
+                    best = min(best, (int)r[c + 3] * -2 * TN + k4.w);                                                             \
+                }                                                                                                                 \
             }
+            VSTAB_TMEM_LD32(r0, 0);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            VSTAB_TMEM_LD32(r1, 32);
+            VSTAB_FOLD32(r0, 0)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            VSTAB_TMEM_LD32(r0, 64);
+            VSTAB_FOLD32(r1, 32)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            VSTAB_TMEM_LD32(r1, 96);
+            VSTAB_FOLD32(r0, 64)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // the accumulator is in registers: hand it back to the MMA warp before the last fold
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.acc_empty[a]);
+            VSTAB_FOLD32(r1, 96)
+#undef VSTAB_TMEM_LD32
+#undef VSTAB_FOLD32
             // key = (|b|^2 - 2 a.b) * 128 + column: arithmetic shift recovers the signed value
             const int d2 = na + (best >> 7), j = j0 + (best & (TN - 1));
             if (best != 0x7fffffff && d2 < bd) { bd = d2; bi = j; }
@@ -387,9 +402,10 @@ __global__ void l2_unpack_kernel(const unsigned long long* __restrict__ packed, 
                                  int* __restrict__ best_idx, int* __restrict__ best_d2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(nref_p[0], max_kp)) return;
-    const unsigned long long p = packed[i];
-    best_idx[i] = p == ~0ull ? -1 : (int)(unsigned)(p & 0xffffffffull);
-    best_d2[i] = p == ~0ull ? 0x7fffffff : (int)(unsigned)(p >> 32);
+    const size_t k = (size_t)blockIdx.y * max_kp + i;                  // blockIdx.y = frame
+    const unsigned long long p = packed[k];
+    best_idx[k] = p == ~0ull ? -1 : (int)(unsigned)(p & 0xffffffffull);
+    best_d2[k] = p == ~0ull ? 0x7fffffff : (int)(unsigned)(p >> 32);
 }
 
 // distance filter of the reference (:680-697): d = sqrt(d2) as float (BFMatcher NORM_L2), mean over the
@@ -501,12 +517,10 @@ void launch_l2_nn_batch(const uint8_t* ref_desc, const int* nref, uint8_t* cur_d
     const int mt = (max_kp + TM - 1) / TM;
     int splits = (2 * device_sm_count() + mt * nframes - 1) / (mt * nframes);
     splits = splits < 1 ? 1 : (splits > 8 ? 8 : splits);
-    count_launch(2 + nframes);
+    count_launch(3);
     l2_prep_kernel<<<dim3((max_kp + 7) / 8, nframes), 256, 0, st>>>(ref_desc, nref, cur_desc, ncur, max_kp, (size_t)max_kp * TK, na, nb, packed);
     l2_nn_i8_kernel<<<dim3(mt, splits, nframes), 192, smem, st>>>(mapA, mapB, nref, ncur, max_kp, na, nb, packed);
-    for (int f = 0; f < nframes; ++f)
-        l2_unpack_kernel<<<(max_kp + 255) / 256, 256, 0, st>>>(packed + (size_t)f * max_kp, nref, max_kp, best_idx + (size_t)f * max_kp,
-                                                              best_d2 + (size_t)f * max_kp);
+    l2_unpack_kernel<<<dim3((max_kp + 255) / 256, nframes), 256, 0, st>>>(packed, nref, max_kp, best_idx, best_d2);
 }
 
 void launch_l2_match(const uint8_t* ref_desc, const int* nref, const OrbKeypoint* ref_kps, uint8_t* cur_desc,

@@ -112,6 +112,8 @@ SYMBOLS = {
     "vstab_offline_set_timing": (None, [_vp, C.c_int]),
     "vstab_offline_stage_times": (C.c_int, [_vp, _f32p, C.POINTER(C.c_int)]),
     "vstab_launch_count": (C.c_longlong, []),
+    "vstab_debug_guard_violations": (C.c_longlong, []),
+    "vstab_debug_guard_buffers": (C.c_longlong, []),
     "vstab_offline_read_h": (C.c_long, [_vp, _f64p, C.c_size_t]),
     "vstab_offline_stream": (C.c_size_t, [_vp]),
     "vstab_render_frames": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int, C.c_double,
