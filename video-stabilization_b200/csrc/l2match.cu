@@ -177,11 +177,11 @@ l2_nn_kernel(const uint8_t* __restrict__ ref, const int* __restrict__ nref_p, in
 // ---------------------------------------------------------------------------------------------------------------------
 // Pipelined version (default): kind::i8 on the raw descriptor bytes (u8 x u8 -> s32, exact; no conversion pass), operand
 // tiles brought in by the TMA engine (cp.async.bulk.tensor.2d, SWIZZLE_128B: a descriptor row IS the 128-byte swizzle
-// row), a 4-stage ring of B tiles, two 128-column TMEM accumulators, warp-specialised CTAs of 10 warps:
+// row), a 4-stage ring of B tiles, two 128-column TMEM accumulators, warp-specialised CTAs of 6 warps:
 //   warp 0 (one lane)  TMA producer: A tile once, then B tiles into the ring (full / empty mbarriers)
 //   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma M128 N128 K32 per tile, tcgen05.commit frees the stage and
 //                      publishes the accumulator
-//   warps 2..9         epilogue: tcgen05.ld of their TMEM lane quarter and column half, min over it of the packed key
+//   warps 2..5         epilogue: tcgen05.ld of their TMEM lane quarter, min over the tile of the packed key
 //                      (|b|^2 - 2 a.b) * 128 + column -- ONE integer multiply-add and one min per element -- then the
 //                      tile's winner against the running best (strict <, ascending tiles: lowest index wins ties)
 // The grid is (128-row reference tiles) x (splits of the current rows) x (frames), so one frame already fills the
@@ -256,7 +256,7 @@ l2_prep_kernel(const uint8_t* __restrict__ ref, const int* __restrict__ nref_p, 
     }
 }
 
-__global__ void __launch_bounds__(320, 2)
+__global__ void __launch_bounds__(192, 2)
 l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const int* __restrict__ nref_p, const int* __restrict__ ncur_p, int max_kp,
                 const int* __restrict__ na_g, const int* __restrict__ nb_g, unsigned long long* __restrict__ packed) {
@@ -274,7 +274,7 @@ l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
         for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
 #pragma unroll
-        for (int a = 0; a < kAccs; ++a) { mbar_init(&S.acc_full[a], 1); mbar_init(&S.acc_empty[a], 8); }
+        for (int a = 0; a < kAccs; ++a) { mbar_init(&S.acc_full[a], 1); mbar_init(&S.acc_empty[a], 4); }
         mbar_init(&S.a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -327,12 +327,9 @@ l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
-        // ================================ epilogue (warps 2..9) =======================
-        // warp w reads TMEM lane quarter w & 3 (the hardware's rule) and the column half (w - 2) / 4 of every tile: eight
-        // warps keep twice as many TMEM loads in flight as four (the loads, not the arithmetic, bound the epilogue)
-        const int te = threadIdx.x - 64;                           // 0..255; the first 128 prepare one column constant each
+        // ================================ epilogue (warps 2..5) =======================
+        const int te = threadIdx.x - 64;                           // 0..127: column this thread prepares
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                          // columns [64 half, 64 half + 64)
         const int row = row0 + q * 32 + lane;                      // reference row = TMEM lane
         const int na = row < nref ? na_g[row] : 0;
         const int* nbp = nb_g + (size_t)frame * max_kp;
@@ -341,13 +338,13 @@ l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int a = it % kAccs;
             const int j0 = ((int)blockIdx.y + it * (int)gridDim.y) * TN;
             // per-column constant of the packed key: |b_j|^2 * 128 + column (rows beyond the count: zero rows, largest key)
-            if (te < TN) S.kc[a][te] = j0 + te < ncur ? nbp[j0 + te] * TN + te : 0x7fffffff;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            S.kc[a][te] = j0 + te < ncur ? nbp[j0 + te] * TN + te : 0x7fffffff;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&S.acc_full[a], (it / kAccs) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned taddr = tmem + (unsigned)(a * TN + half * 64) + ((unsigned)(q * 32) << 16);
-            int best = 0x7fffffff;
-            // two register buffers of 32 columns: the TMEM load of the second chunk is in flight while the first is folded
+            const unsigned taddr = tmem + (unsigned)(a * TN) + ((unsigned)(q * 32) << 16);
+            int bq0 = 0x7fffffff, bq1 = 0x7fffffff, bq2 = 0x7fffffff, bq3 = 0x7fffffff;
+            // two register buffers of 32 columns: the TMEM load of the next chunk is in flight while this one is folded
             unsigned r0[32], r1[32];
 #define VSTAB_TMEM_LD32(r, col)                                                                                                   \
             asm volatile(                                                                                                         \
@@ -361,26 +358,34 @@ l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 : "memory")
 #define VSTAB_FOLD32(r, col)                                                                                                      \
             {                                                                                                                     \
-                const int4* kc4 = reinterpret_cast<const int4*>(&S.kc[a][half * 64 + (col)]);                                     \
+                const int4* kc4 = reinterpret_cast<const int4*>(&S.kc[a][col]);                                                   \
                 _Pragma("unroll") for (int c = 0; c < 32; c += 4) {                                                               \
                     const int4 k4 = kc4[c >> 2];                                                                                  \
-                    best = min(best, (int)r[c] * -2 * TN + k4.x);                                                                 \
-                    best = min(best, (int)r[c + 1] * -2 * TN + k4.y);                                                             \
-                    best = min(best, (int)r[c + 2] * -2 * TN + k4.z);                                                             \
-                    best = min(best, (int)r[c + 3] * -2 * TN + k4.w);                                                             \
+                    bq0 = min(bq0, (int)r[c] * -2 * TN + k4.x);          /* four independent min chains: on a single  */          \
+                    bq1 = min(bq1, (int)r[c + 1] * -2 * TN + k4.y);      /* one the fold is bound by its latency      */          \
+                    bq2 = min(bq2, (int)r[c + 2] * -2 * TN + k4.z);                                                               \
+                    bq3 = min(bq3, (int)r[c + 3] * -2 * TN + k4.w);                                                               \
                 }                                                                                                                 \
             }
             VSTAB_TMEM_LD32(r0, 0);
-            VSTAB_TMEM_LD32(r1, 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // the accumulator half is in registers: hand it back to the MMA warp before folding
+            VSTAB_TMEM_LD32(r1, 32);
+            VSTAB_FOLD32(r0, 0)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            VSTAB_TMEM_LD32(r0, 64);
+            VSTAB_FOLD32(r1, 32)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            VSTAB_TMEM_LD32(r1, 96);
+            VSTAB_FOLD32(r0, 64)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // the accumulator is in registers: hand it back to the MMA warp before the last fold
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.acc_empty[a]);
-            VSTAB_FOLD32(r0, 0)
-            VSTAB_FOLD32(r1, 32)
+            VSTAB_FOLD32(r1, 96)
 #undef VSTAB_TMEM_LD32
 #undef VSTAB_FOLD32
+            const int best = min(min(bq0, bq1), min(bq2, bq3));
             // key = (|b|^2 - 2 a.b) * 128 + column: arithmetic shift recovers the signed value
             const int d2 = na + (best >> 7), j = j0 + (best & (TN - 1));
             if (best != 0x7fffffff && d2 < bd) { bd = d2; bi = j; }
@@ -515,7 +520,7 @@ void launch_l2_nn_batch(const uint8_t* ref_desc, const int* nref, uint8_t* cur_d
     splits = splits < 1 ? 1 : (splits > 8 ? 8 : splits);
     count_launch(3);
     l2_prep_kernel<<<dim3((max_kp + 7) / 8, nframes), 256, 0, st>>>(ref_desc, nref, cur_desc, ncur, max_kp, (size_t)max_kp * TK, na, nb, packed);
-    l2_nn_i8_kernel<<<dim3(mt, splits, nframes), 320, smem, st>>>(mapA, mapB, nref, ncur, max_kp, na, nb, packed);
+    l2_nn_i8_kernel<<<dim3(mt, splits, nframes), 192, smem, st>>>(mapA, mapB, nref, ncur, max_kp, na, nb, packed);
     l2_unpack_kernel<<<dim3((max_kp + 255) / 256, nframes), 256, 0, st>>>(packed, nref, max_kp, best_idx, best_d2);
 }
 
