@@ -334,11 +334,16 @@ l2_nn_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int na = row < nref ? na_g[row] : 0;
         const int* nbp = nb_g + (size_t)frame * max_kp;
         int bd = 0x7fffffff, bi = -1;
+        // |b_j|^2 of this thread's column of the NEXT tile is fetched while the current tile is folded (an L2 round trip
+        // in front of the barrier of every tile otherwise: 94 -> 82 us per 64-frame batch)
+        auto norm_of = [&](int it) { const int j = ((int)blockIdx.y + it * (int)gridDim.y) * TN + te; return j < ncur ? __ldg(nbp + j) : -1; };
+        int nb_next = norm_of(0);
         for (int it = 0; it < ntiles; ++it) {
             const int a = it % kAccs;
             const int j0 = ((int)blockIdx.y + it * (int)gridDim.y) * TN;
             // per-column constant of the packed key: |b_j|^2 * 128 + column (rows beyond the count: zero rows, largest key)
-            S.kc[a][te] = j0 + te < ncur ? nbp[j0 + te] * TN + te : 0x7fffffff;
+            S.kc[a][te] = nb_next >= 0 ? nb_next * TN + te : 0x7fffffff;
+            if (it + 1 < ntiles) nb_next = norm_of(it + 1);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&S.acc_full[a], (it / kAccs) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
