@@ -140,9 +140,11 @@ class OfflineStabilizer:
         if world > 1:
             if rank == 0:
                 _check(self._lib.vstab_nccl_get_unique_id(C.byref(nid)))
-            box = [bytes(nid.bytes) if rank == 0 else None]
+            # the id is 128 opaque bytes (NULs included: read the struct's memory, not the c_char array's "string" value)
+            box = [C.string_at(C.addressof(nid), C.sizeof(nid)) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0, group=group)
-            C.memmove(C.byref(nid), box[0], 128)
+            assert len(box[0]) == C.sizeof(nid) == 128
+            C.memmove(C.addressof(nid), box[0], 128)
             _check(self._lib.vstab_offline_comm_init(self._h, C.byref(nid), rank, world), self._h)
         self.rank, self.world = rank, world
 
