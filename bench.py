@@ -588,6 +588,17 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
             return float(t.item())
         return dt
 
+    # ---- what the host memory system gives these ranks at the same time: a plain copy of the same pinned buffers ----
+    # (names the limiter of the e2e leg at N > 1: every e2e frame is read once and written once in host DRAM by the DMA engines)
+    hout_np = np.ctypeslib.as_array((C.c_uint8 * (n_clip * nbytes)).from_address(hout)).reshape(n_clip, H, W, 3)
+    np.copyto(hout_np, hin_np)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        np.copyto(hout_np, hin_np)
+    dt_copy = max_over_ranks(time.perf_counter() - t0)
+    host_copy_gbs_total = world * 2 * (2 * n_clip * nbytes) / dt_copy / 1e9      # bytes read + bytes written, all ranks
+
     # ---- whole clip, pipelined (each rank stabilizes its own clip: replicas, no collective) --------
     off = offline.OfflineStabilizer(PAST, FUTURE, WH, H, W, args.e2e_batch, device=local)
     for _ in range(2):
@@ -629,6 +640,10 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
             "pcie": {"gbs_per_direction_per_gpu": per_gpu_gbs, "frac_of_gen5_x16": per_gpu_gbs / 63.0,
                      "peak": "63.0 GB/s per direction nominal (PCIe Gen5 x16); ~55 GB/s is what pinned cudaMemcpy reaches"},
             "replicas": world,
+            "host_dram": {"numpy_copy_gbs_all_ranks": host_copy_gbs_total,
+                          "e2e_dma_gbs_all_ranks": 2 * world * n_clip * nbytes * args.steps / dt_clip / 1e9,
+                          "note": "one single-threaded numpy copy of the same pinned buffers per rank, all ranks at once (read + "
+                                  "written bytes) beside the bytes the e2e leg moves through host DRAM per second"},
             "api": "vstab_offline_run_host (whole clip of pinned host frames in/out, pipelined H2D / compute / D2H)",
             "frames_per_step": n_clip, "timer": "host wall clock around the synchronous call, max over ranks",
             "streaming": {"value": world * per_step * args.steps / dt_stream, "unit": UNIT,

@@ -1580,7 +1580,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         CK(outc.alloc(g.frame_bytes * (size_t)B + 64));
         o->job_chunk_frames = (size_t)B + 1;
     }
-    DevBuf T_local, T_gather, T_all, sums, checks, poses_d, reg_local, reg_gather, reg_all;
+    DevBuf T_local, T_gather, T_all, sums, checks, poses_d, rays_d, reg_local, reg_gather, reg_all;
     CK(T_local.alloc(sizeof(double) * 9 * (size_t)L));
     CK(T_all.alloc(sizeof(double) * 9 * (size_t)N));
     if (world > 1) CK(T_gather.alloc(sizeof(double) * 9 * (size_t)L * world));
@@ -1599,6 +1599,9 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         poses_to_render(cfg->poses, N, hp.data());                  // all N (72 + 24 bytes each): the anchor frame may be anyone's
         CK(poses_d.alloc(sizeof(RenderPose) * (size_t)N));
         CK(cudaMemcpyAsync(poses_d.p, hp.data(), sizeof(RenderPose) * (size_t)N, cudaMemcpyHostToDevice, q));
+        // the camera rays do not depend on the pose: once per job (24 bytes per pixel), not once per pixel and frame
+        CK(rays_d.alloc(sizeof(double) * 3 * (size_t)g.cols * g.rows));
+        launch_render_rays(g.cols, g.rows, cfg->focal, rays_d.as<double>(), q);
         CK(cudaStreamSynchronize(q));                               // hp goes out of scope
     }
     // frames [f0, f0 + n) of the clip -> chunk slots [slot, slot + n)
@@ -1607,7 +1610,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         clock.begin(PH_SOURCE, q);
         if (sim) {
             launch_render(cfg->d_texture, cfg->tex_rows, cfg->tex_cols, poses_d.as<RenderPose>() + f0, (int)n, g.cols, g.rows, cfg->focal,
-                          cb + (size_t)slot * fb, g.pitch, fb, q);
+                          cb + (size_t)slot * fb, g.pitch, fb, q, rays_d.as<double>());
         } else {
             for (long i = 0; i < n; ++i) {
                 const long f = f0 + i;
