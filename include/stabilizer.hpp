@@ -97,6 +97,10 @@ public:
 
     void setStabilizationMode(StabilizationMode mode) { check(vstab_set_mode(h_, static_cast<int>(mode))); }
 
+    // The reference selects its feathered-trail output (copyFeathered, src/stabilizer.cpp:1303-1307) at compile time with
+    // `#if 0`; here it is a run-time switch, off by default.
+    void setTrailCompositing(bool enable) { check(vstab_set_trail(h_, enable ? 1 : 0)); }
+
     inline size_t totalFrameWindowSize() const { return totalPastFrames_ + 1 + totalFutureFrames_; }
 
     // static bool decomposeHomography(const cv::Mat& H, HomographyParameters&, cv::Point2d rot_center = {0,0})
