@@ -228,7 +228,7 @@ struct vstab {
     cudaStream_t stream = nullptr;       // estimation stream: ingest -> pyramid -> LK -> fit -> corner detection
     cudaStream_t out_stream = nullptr;   // output stream: smoothing / lock -> warp -> device-to-host copy
     cudaEvent_t ev_in = nullptr;         // input frame is in the ring (caller may reuse its buffer)
-    cudaEvent_t ev_fit = nullptr;        // T[n] and the channel sums of frame n are final
+    cudaEvent_t ev_fit[4] = {};          // [n & 3]: T[n] and the channel sums of frame n are final
     cudaEvent_t ev_out = nullptr;        // output chain of the previous call has finished reading the ring
     cudaStream_t gftt_stream = nullptr;  // corner detection of frame n runs beside LK / fit of frame n
     cudaStream_t copy_stream = nullptr;  // host-to-device upload of frame n runs beside the estimation of frame n-1
@@ -241,6 +241,19 @@ struct vstab {
     long feat_p = -1;                    // presentation frame the pending look-ahead result belongs to
     bool feat_pending = false;           // something was enqueued on feat_stream since the last wait
     int lock_slot = 0;                   // lock_h / lock_tap half of the current call
+    // Output prepared one call ahead (host-buffer calls, LK-path modes, future >= 1): everything the output of call n+1
+    // reads is already on the device when call n has enqueued its estimation, so its smoothing / lock + warp run on
+    // pre_stream beside the download of call n and call n+1 only has to copy out.  wp / dout are double-buffered;
+    // setStabilizationMode / setTrail bump `epoch` and the prepared frame is dropped (the output is then built inside
+    // the call as before).
+    cudaStream_t pre_stream = nullptr;
+    cudaEvent_t ev_pre = nullptr;        // prepared output (and its ACCUMULATED product update) is complete
+    cudaEvent_t ev_chain = nullptr;      // in-call output chain has left the lock / smoothing state behind
+    bool pre_valid = false;
+    long pre_call = -1;
+    unsigned long pre_epoch = 0, epoch = 0;
+    long pre_acc_to = -1;                // accumulatedTransform_.to_frame_idx once the prepared output is presented
+    int out_slot = 0;                    // half of wp / dout that holds the latest presented output
     cudaEvent_t ev_pyr = nullptr;        // gray pyramid of frame n is complete
     cudaEvent_t ev_gftt = nullptr;       // corners of frame n are complete (needed by LK of frame n+1)
     size_t P = 15, F = 15;
@@ -249,12 +262,15 @@ struct vstab {
     long lock_call = 0;          // call index at which the current mode was set
     bool acc_valid = false;      // accumulatedTransform_.H non-empty
     long acc_to = -1;            // accumulatedTransform_.to_frame_idx
+    long acc_call = -1;          // call whose update of the accumulated product has been enqueued
     long n = 0;                  // number of frames pushed so far == index of the next call
     long last_presented = 0;
     bool inited = false;
     Geometry g;
     long W = 0;                  // window size in frames
-    DevBuf ring, sums, pyr0, pyr1, corners0, corners1, ccount, lkpts, lkstat, T, Mtap, fitc, acc, wp, gmem, dout;
+    DevBuf ring, sums, pyr0, pyr1, corners0, corners1, ccount, lkpts, lkstat, T, Mtap, fitc, acc, wp, gmem, dout, dout1;
+    WarpParams* wp_at(int slot) { return wp.as<WarpParams>() + (slot & 1); }
+    uint8_t* dout_at(int slot) { return (slot & 1) ? dout1.as<uint8_t>() : dout.as<uint8_t>(); }
     long t_mod = 0;
     GfttWorkspace gws{};
     // ORB registration state (reference: referenceGray_/Keypoints_/Descriptors_, hpp:447-456, and the
@@ -306,8 +322,9 @@ static vstab_status stream_init(vstab* s, int rows, int cols) {
     CK(s->Mtap.alloc(sizeof(double) * 6));
     CK(s->fitc.alloc(sizeof(int) * 2));
     CK(s->acc.alloc(sizeof(double) * 9));
-    CK(s->wp.alloc(sizeof(WarpParams)));
+    CK(s->wp.alloc(sizeof(WarpParams) * 2));
     CK(s->dout.alloc(g.frame_bytes + 64));
+    CK(s->dout1.alloc(g.frame_bytes + 64));
     size_t gbytes = gftt_workspace_bytes(g.ww, g.wh, g.min_distance, 1, &s->gws);
     CK(s->gmem.alloc(gbytes));
     gftt_bind_workspace(s->gmem.p, &s->gws);
@@ -354,7 +371,7 @@ static vstab_status stream_estimate(vstab* s) {
                    g.ww / 2.0, g.wh / 2.0, s->T.as<double>() + (size_t)(n % s->t_mod) * 9, s->Mtap.as<double>(),
                    s->fitc.as<int>(), nullptr, n, q);
     }
-    CK(cudaEventRecord(s->ev_fit, q));
+    CK(cudaEventRecord(s->ev_fit[n & 3], q));
     s->mark(4, q);
     // corner detection of this frame (:1318 / :1179) only feeds the next call's tracker: own stream
     CK(cudaStreamWaitEvent(s->gftt_stream, s->ev_pyr, 0));
@@ -443,17 +460,24 @@ static vstab_status stream_feature_lock(vstab* s, long p, cudaStream_t q, int sl
 
 // Output chain of call s->n (n >= 1) on s->out_stream; `d_out`/`out_pitch`: where the warped
 // presentation frame goes.  The caller has already made out_stream wait for the transforms it needs.
-static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
+// Output chain of call n on stream q: lock / window average -> warp of the presentation frame into d_out, its warp
+// parameters into *wp.  `ahead`: enqueued during call n-1 (no trace marks, `last_presented` moves when it is consumed).
+static vstab_status stream_output(vstab* s, long n, uint8_t* d_out, size_t out_pitch, WarpParams* wp, cudaStream_t q,
+                                  bool prepared_ahead) {
     auto set_err = [&](const std::string& e) { s->err = e; };
     Geometry& g = s->g;
-    cudaStream_t q = s->out_stream;
-    const long n = s->n;
     const long p = n - (long)s->F > 0 ? n - (long)s->F : 0;                                            // :1226-1229
-    s->mark(7, q);
+    if (!prepared_ahead) s->mark(7, q);
     if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) {                                                      // :317-338
-        launch_acc_update(s->T.as<double>(), s->t_mod, p, s->acc_valid ? 0 : 1, s->acc.as<double>(), q);
-        s->acc_valid = true;
-        s->acc_to = p;
+        // (acc_call == n: a prepared-ahead chain that was dropped afterwards has already made this call's update)
+        if (s->acc_call != n) launch_acc_update(s->T.as<double>(), s->t_mod, p, s->acc_valid ? 0 : 1, s->acc.as<double>(), q);
+        s->acc_call = n;
+        if (prepared_ahead) {
+            s->pre_acc_to = p;                 // host-side view moves when the prepared output is consumed
+        } else {
+            s->acc_valid = true;
+            s->acc_to = p;
+        }
     }
     const bool feature_lock = s->mode == VSTAB_ORB_FULL_LOCK || s->mode == VSTAB_SIFT_FULL_LOCK;
     if (feature_lock) {
@@ -476,8 +500,8 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
     a.scale = g.scale;
     a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
     a.npix = (double)g.rows * (double)g.cols;
-    launch_smooth(a, n, 1, s->wp.as<WarpParams>(), q);                                                 // :1234-1296
-    s->mark(8, q);
+    launch_smooth(a, n, 1, wp, q);                                                                     // :1234-1296
+    if (!prepared_ahead) s->mark(8, q);
     static const bool lookahead = !(getenv("VSTAB_LOOKAHEAD") && atoi(getenv("VSTAB_LOOKAHEAD")) == 0);
     if (feature_lock && lookahead && s->F >= 2 && s->has_reference) {
         // registration of the next call's presentation frame, beside this call's warp and download.  Only with
@@ -499,16 +523,16 @@ static vstab_status stream_output(vstab* s, uint8_t* d_out, size_t out_pitch) {
             CK(s->trail_ws.alloc(trail_workspace_bytes(g.cols, g.rows, g.frame_bytes)));
             CK(cudaMemsetAsync(s->trail_bg.p, 0, g.frame_bytes, q));                                   // Mat::zeros, :128-130
         }
-        launch_trail(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), -1, s->trail_bg.as<uint8_t>(),
+        launch_trail(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, wp, -1, s->trail_bg.as<uint8_t>(),
                      g.cols, g.rows, s->trail_ws.p, d_out, out_pitch, q);
         CK(cudaMemcpy2DAsync(s->trail_bg.p, g.pitch, d_out, out_pitch, (size_t)g.cols * 3, g.rows, cudaMemcpyDeviceToDevice, q));
     } else {
-        launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, s->wp.as<WarpParams>(), 1, g.cols, g.rows,
+        launch_warp(s->ring.as<uint8_t>(), g.pitch, g.frame_bytes, s->W, wp, 1, g.cols, g.rows,
                     d_out, out_pitch, 0, q);                                                           // :1309-1313
     }
-    s->mark(9, q);
+    if (!prepared_ahead) s->mark(9, q);
     CK(cudaGetLastError());
-    s->last_presented = p;
+    if (!prepared_ahead) s->last_presented = p;
     return VSTAB_OK;
 }
 
@@ -520,23 +544,53 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
     uint8_t* slot = s->ring.as<uint8_t>() + (size_t)(s->n % s->W) * g.frame_bytes;
     const size_t row_bytes = (size_t)cols * 3;
     const bool device_out = out_kind == cudaMemcpyDeviceToDevice;
-    uint8_t* warp_dst = device_out ? out : s->dout.as<uint8_t>();
-    const size_t warp_pitch = device_out ? out_step : g.pitch;
     const bool out_first = s->n > 0 && s->F >= 1;      // output chain does not need this call's transform
     static const bool trace = getenv("VSTAB_TRACE") != nullptr;
+    static const bool prepare_ok = !(getenv("VSTAB_PREPARE") && atoi(getenv("VSTAB_PREPARE")) == 0);
     auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = trace ? now_us() : 0.0;
     double tr1 = 0.0;
     if (trace && !s->tev[0][0])
         for (auto& set : s->tev) for (auto& e : set) cudaEventCreate(&e);
-
-    if (out_first) {
-        CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));          // T[n-1], sums of frames <= n-1
-        vstab_status st = stream_output(s, warp_dst, warp_pitch);
-        if (st != VSTAB_OK) return st;
+    // which fit the output chain of call c has to wait for.  The window average reads T up to c-1
+    // (stabilizer.cpp:825-826); every other mode reads nothing newer than the presentation frame p = c - F (its T for
+    // the ACCUMULATED product, its channel sums, its pixels), so with future >= 2 the chain does not wait for the
+    // estimation of frame c-1, which is what call c-1 left running
+    auto fit_event = [&](long c) {
+        const bool newest = s->mode == VSTAB_GLOBAL_SMOOTHING || s->F < 2 || c < 2;
+        return s->ev_fit[(c - (newest ? 1 : 2)) & 3];
+    };
+    auto output_into = [&](long c, int slot, cudaStream_t q, bool ahead) -> vstab_status {
+        uint8_t* dst = device_out ? out : s->dout_at(slot);
+        return stream_output(s, c, dst, device_out ? out_step : g.pitch, s->wp_at(slot), q, ahead);
+    };
+    auto copy_out = [&](int slot) -> vstab_status {
         if (!device_out)
-            CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
+            CK(cudaMemcpy2DAsync(out, out_step, s->dout_at(slot), g.pitch, row_bytes, rows, out_kind, s->out_stream));
+        return VSTAB_OK;
+    };
+
+    if (s->pre_valid) CK(cudaStreamWaitEvent(s->out_stream, s->ev_pre, 0));   // used or not, its state updates come first
+    bool in_call_chain = false;                                               // ev_chain: that chain's lock state is final
+    if (out_first) {
+        const long p = s->n - (long)s->F > 0 ? s->n - (long)s->F : 0;
+        if (s->pre_valid && s->pre_call == s->n && s->pre_epoch == s->epoch && !device_out) {
+            s->out_slot ^= 1;                                          // prepared during the previous call
+            s->last_presented = p;
+            if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) { s->acc_valid = true; s->acc_to = s->pre_acc_to; }
+            s->mark(7, s->out_stream); s->mark(8, s->out_stream); s->mark(9, s->out_stream);
+        } else {
+            CK(cudaStreamWaitEvent(s->out_stream, fit_event(s->n), 0));
+            s->out_slot ^= 1;
+            vstab_status st = output_into(s->n, s->out_slot, s->out_stream, false);
+            if (st != VSTAB_OK) return st;
+            CK(cudaEventRecord(s->ev_chain, s->out_stream));
+            in_call_chain = true;
+        }
+        vstab_status st = copy_out(s->out_slot);
+        if (st != VSTAB_OK) return st;
     }
+    s->pre_valid = false;
     if (trace) tr1 = now_us();
     // estimation chain.  The ring slot being overwritten held frame n-W; its readers (the warp and the
     // channel sums of an earlier call's output chain) are ordered before this copy by ev_out.
@@ -558,12 +612,26 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
             CK(cudaMemcpy2DAsync(out, out_step, slot, g.pitch, row_bytes, rows, out_kind, s->out_stream));
             s->last_presented = 0;
         } else {
-            CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit, 0));      // future == 0: needs T[n] of this call
-            st = stream_output(s, warp_dst, warp_pitch);
+            CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit[s->n & 3], 0));   // future == 0: needs T[n] of this call
+            s->out_slot ^= 1;
+            st = output_into(s->n, s->out_slot, s->out_stream, false);
             if (st != VSTAB_OK) return st;
-            if (!device_out)
-                CK(cudaMemcpy2DAsync(out, out_step, s->dout.p, g.pitch, row_bytes, rows, out_kind, s->out_stream));
+            CK(cudaEventRecord(s->ev_chain, s->out_stream));
+            in_call_chain = true;
+            st = copy_out(s->out_slot);
+            if (st != VSTAB_OK) return st;
         }
+    }
+    // the next call's output, beside this call's download (see pre_stream)
+    const bool lk_mode = s->mode != VSTAB_ORB_FULL_LOCK && s->mode != VSTAB_SIFT_FULL_LOCK;
+    if (prepare_ok && host_wait && !device_out && s->F >= 1 && lk_mode && !s->trail) {
+        const long c = s->n + 1;
+        if (in_call_chain) CK(cudaStreamWaitEvent(s->pre_stream, s->ev_chain, 0));
+        CK(cudaStreamWaitEvent(s->pre_stream, fit_event(c), 0));
+        st = output_into(c, s->out_slot ^ 1, s->pre_stream, true);
+        if (st != VSTAB_OK) return st;
+        CK(cudaEventRecord(s->ev_pre, s->pre_stream));
+        s->pre_valid = true; s->pre_call = c; s->pre_epoch = s->epoch;
     }
     s->mark(10, s->out_stream);
     CK(cudaEventRecord(s->ev_out, s->out_stream));
@@ -656,7 +724,10 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
     if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s->out_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev_fit, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[3], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s->gftt_stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -664,6 +735,9 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
         cudaEventCreateWithFlags(&s->ev_feat, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_reg, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->pre_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_chain, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_gftt, cudaEventDisableTiming) != cudaSuccess) {
         g_err = "cudaStreamCreate failed"; vstab_destroy(s); return VSTAB_ERR_CUDA;
     }
@@ -689,7 +763,7 @@ void vstab_destroy(vstab_t* s) {
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
     if (s->out_stream) { cudaStreamSynchronize(s->out_stream); cudaStreamDestroy(s->out_stream); }
     if (s->ev_in) cudaEventDestroy(s->ev_in);
-    if (s->ev_fit) cudaEventDestroy(s->ev_fit);
+    for (auto e : s->ev_fit) if (e) cudaEventDestroy(e);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
     if (s->gftt_stream) { cudaStreamSynchronize(s->gftt_stream); cudaStreamDestroy(s->gftt_stream); }
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
@@ -698,6 +772,9 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_reg) cudaEventDestroy(s->ev_reg);
     if (s->ev_pyr) cudaEventDestroy(s->ev_pyr);
     if (s->ev_gftt) cudaEventDestroy(s->ev_gftt);
+    if (s->pre_stream) { cudaStreamSynchronize(s->pre_stream); cudaStreamDestroy(s->pre_stream); }
+    if (s->ev_pre) cudaEventDestroy(s->ev_pre);
+    if (s->ev_chain) cudaEventDestroy(s->ev_chain);
     if (s->orb) orb_plan_destroy(s->orb);
     if (s->sift) sift_plan_destroy(s->sift);
     for (auto& set : s->tev) for (auto& e : set) if (e) cudaEventDestroy(e);     // VSTAB_TRACE marks
@@ -712,6 +789,8 @@ vstab_status vstab_set_mode(vstab_t* s, int mode) {
     s->feat_p = -1;                      // a pending look-ahead registration belongs to the old reference: not consumed
     s->acc_valid = false;
     s->acc_to = -1;
+    s->acc_call = -1;
+    s->epoch += 1;                       // an output prepared ahead under the old mode is dropped
     s->mode = mode;
     s->lock_call = s->n;
     return VSTAB_OK;
@@ -730,6 +809,7 @@ vstab_status vstab_synchronize(vstab_t* s) {
     CK(cudaStreamSynchronize(s->gftt_stream));
     CK(cudaStreamSynchronize(s->copy_stream));
     CK(cudaStreamSynchronize(s->feat_stream));
+    CK(cudaStreamSynchronize(s->pre_stream));
     return VSTAB_OK;
 }
 
@@ -812,9 +892,9 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
         case VSTAB_TAP_NEW_PTS: return copy(s->corners(cur), sizeof(float2) * counts[cur], counts[cur]);
         case VSTAB_TAP_T: if (last == 0) return 0; return copy(s->T.as<double>() + (size_t)(last % s->t_mod) * 9, sizeof(double) * 9, 9);
         case VSTAB_TAP_M: if (last == 0) return 0; return copy(s->Mtap.p, sizeof(double) * 6, 6);
-        case VSTAB_TAP_H_STABILIZE: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, Hw), sizeof(double) * 9, 9);
-        case VSTAB_TAP_H_SCALED: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, Hs), sizeof(double) * 9, 9);
-        case VSTAB_TAP_BORDER: if (last == 0) return 0; return copy((char*)s->wp.p + offsetof(WarpParams, border), 3, 3);
+        case VSTAB_TAP_H_STABILIZE: if (last == 0) return 0; return copy((char*)s->wp_at(s->out_slot) + offsetof(WarpParams, Hw), sizeof(double) * 9, 9);
+        case VSTAB_TAP_H_SCALED: if (last == 0) return 0; return copy((char*)s->wp_at(s->out_slot) + offsetof(WarpParams, Hs), sizeof(double) * 9, 9);
+        case VSTAB_TAP_BORDER: if (last == 0) return 0; return copy((char*)s->wp_at(s->out_slot) + offsetof(WarpParams, border), 3, 3);
         case VSTAB_TAP_EIG: return copy(s->gws.eig, sizeof(float) * g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_INLIERS: if (last == 0) return 0; return copy(s->fitc.p, sizeof(int) * 2, 2);
         case VSTAB_TAP_LOCK_H: if (!s->lock_h.p) return 0; return copy(s->lock_h.as<double>() + 9 * s->lock_slot, sizeof(double) * 9, 9);
@@ -1918,6 +1998,7 @@ extern "C" vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, i
 extern "C" vstab_status vstab_set_trail(vstab_t* s, int enable) {
     if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
     s->trail = enable != 0;
+    s->epoch += 1;                       // an output prepared ahead without the trail is dropped
     return VSTAB_OK;
 }
 
