@@ -228,10 +228,11 @@ struct vstab {
     cudaStream_t stream = nullptr;       // estimation stream: ingest -> pyramid -> LK -> fit -> corner detection
     cudaStream_t out_stream = nullptr;   // output stream: smoothing / lock -> warp -> device-to-host copy
     cudaEvent_t ev_in = nullptr;         // input frame is in the ring (caller may reuse its buffer)
-    cudaEvent_t ev_fit[4] = {};          // [n & 3]: T[n] and the channel sums of frame n are final
+    cudaEvent_t ev_fit[8] = {};          // [n & 7]: T[n] and the channel sums of frame n are final
     cudaEvent_t ev_out = nullptr;        // output chain of the previous call has finished reading the ring
-    cudaStream_t gftt_stream = nullptr;  // corner detection of frame n runs beside LK / fit of frame n
-    cudaStream_t copy_stream = nullptr;  // host-to-device upload of frame n runs beside the estimation of frame n-1
+    cudaStream_t gftt_stream[2] = {};    // corner detection of frame n on [n & 1]: beside LK / fit and beside frame n+1's
+    cudaStream_t copy_stream = nullptr;  // upload of frame n, beside everything else
+    cudaStream_t ing_stream = nullptr;   // ingest -> pyramid of frame n, beside the tracker of frame n-1 and the next upload
     // ORB / SIFT registration one call ahead: the presentation frame of call n+1 is already in the ring during call n
     // (future >= 1), so its registration is enqueued on feat_stream right after the smoothing of call n and overlaps the
     // download of call n, the host's return and the next upload.  lock_h / lock_tap are double-buffered by call parity.
@@ -254,8 +255,8 @@ struct vstab {
     unsigned long pre_epoch = 0, epoch = 0;
     long pre_acc_to = -1;                // accumulatedTransform_.to_frame_idx once the prepared output is presented
     int out_slot = 0;                    // half of wp / dout that holds the latest presented output
-    cudaEvent_t ev_pyr = nullptr;        // gray pyramid of frame n is complete
-    cudaEvent_t ev_gftt = nullptr;       // corners of frame n are complete (needed by LK of frame n+1)
+    cudaEvent_t ev_pyr[4] = {};          // [n & 3]: gray pyramid (and channel sums) of frame n are complete
+    cudaEvent_t ev_gftt[4] = {};         // [n & 3]: corners of frame n are complete (needed by LK of frame n+1)
     size_t P = 15, F = 15;
     int working_height = 360;
     int mode = VSTAB_GLOBAL_SMOOTHING;
@@ -268,11 +269,11 @@ struct vstab {
     bool inited = false;
     Geometry g;
     long W = 0;                  // window size in frames
-    DevBuf ring, sums, pyr0, pyr1, corners0, corners1, ccount, lkpts, lkstat, T, Mtap, fitc, acc, wp, gmem, dout, dout1;
+    DevBuf ring, sums, pyrs[3], corners0, corners1, ccount, lkpts, lkstat, T, Mtap, fitc, acc, wp, gmem[2], dout, dout1;
     WarpParams* wp_at(int slot) { return wp.as<WarpParams>() + (slot & 1); }
     uint8_t* dout_at(int slot) { return (slot & 1) ? dout1.as<uint8_t>() : dout.as<uint8_t>(); }
     long t_mod = 0;
-    GfttWorkspace gws{};
+    GfttWorkspace gws[2] = {};   // [n & 1]: the corner detections of two consecutive frames overlap
     // ORB registration state (reference: referenceGray_/Keypoints_/Descriptors_, hpp:447-456, and the
     // function-static previouslyReturnedH, cpp:446 -- per instance here)
     OrbPlan* orb = nullptr;
@@ -298,7 +299,7 @@ struct vstab {
     }
 
     void set_err(const std::string& e) { err = e; }
-    uint8_t* pyr(int i) { return (i & 1) ? pyr1.as<uint8_t>() : pyr0.as<uint8_t>(); }
+    uint8_t* pyr(long frame) { return pyrs[frame % 3].as<uint8_t>(); }   // three: frame n+1's is built while LK reads n-1, n
     float2* corners(int i) { return (i & 1) ? corners1.as<float2>() : corners0.as<float2>(); }
 };
 
@@ -311,8 +312,7 @@ static vstab_status stream_init(vstab* s, int rows, int cols) {
     s->t_mod = s->W + 2;
     CK(s->ring.alloc(g.frame_bytes * (size_t)s->W + 64));
     CK(s->sums.alloc(sizeof(unsigned long long) * 3 * s->W));
-    CK(s->pyr0.alloc(g.pd.frame_bytes));
-    CK(s->pyr1.alloc(g.pd.frame_bytes));
+    for (auto& b : s->pyrs) CK(b.alloc(g.pd.frame_bytes));
     CK(s->corners0.alloc(sizeof(float2) * kMaxCorners));
     CK(s->corners1.alloc(sizeof(float2) * kMaxCorners));
     CK(s->ccount.alloc(sizeof(int) * 2));
@@ -325,24 +325,30 @@ static vstab_status stream_init(vstab* s, int rows, int cols) {
     CK(s->wp.alloc(sizeof(WarpParams) * 2));
     CK(s->dout.alloc(g.frame_bytes + 64));
     CK(s->dout1.alloc(g.frame_bytes + 64));
-    size_t gbytes = gftt_workspace_bytes(g.ww, g.wh, g.min_distance, 1, &s->gws);
-    CK(s->gmem.alloc(gbytes));
-    gftt_bind_workspace(s->gmem.p, &s->gws);
+    for (int i = 0; i < 2; ++i) {
+        size_t gbytes = gftt_workspace_bytes(g.ww, g.wh, g.min_distance, 1, &s->gws[i]);
+        CK(s->gmem[i].alloc(gbytes));
+        gftt_bind_workspace(s->gmem[i].p, &s->gws[i]);
+    }
     CK(cudaMemsetAsync(s->ccount.p, 0, sizeof(int) * 2, s->stream));
     CK(cudaMemsetAsync(s->T.p, 0, sizeof(double) * 9 * s->t_mod, s->stream));
+    CK(cudaStreamSynchronize(s->stream));          // the chains of the first call start on other streams
     s->inited = true;
     return VSTAB_OK;
 }
 
-// A streaming call is two independent chains (with future >= 1 the output of
-// call n depends only on transforms up to n-1, because the reference's window average excludes the
-// newest transform, stabilizer.cpp:825-826, and ACCUMULATED lock uses T[n-F]):
-//   estimation (s->stream):  frame n -> ingest -> pyramid -> LK against frame n-1 -> fit T[n] -> corners
-//   output (s->out_stream):  [wait T[n-1]] -> lock / window average -> warp of frame n-F -> copy out
-// so the host only waits for the output chain and the upload; the estimation of frame n overlaps
-// the copy-out and the next call.  With future == 0 the output chain waits for T[n] of this call.
+// A streaming call is a set of chains with no loop-carried dependency between frames except LK(n) <- corners(n-1)
+// (with future >= 1 the output of call n depends only on transforms up to n-1, because the
+// reference's window average excludes the newest transform, stabilizer.cpp:825-826, and ACCUMULATED lock uses T[n-F]):
+//   copy_stream:        upload of frame n
+//   ing_stream:         [upload n] -> ingest -> pyramid                                 (three pyramid buffers)
+//   s->stream:          [pyramid n, corners n-1] -> LK against frame n-1 -> fit T[n]
+//   gftt_stream[n & 1]: [pyramid n] -> corner detection of frame n                      (two workspaces: frames overlap)
+//   out_stream / pre_stream: lock / window average -> warp of frame n-F -> copy out
+// so the host only waits for the upload and the copy-out, and the per-frame latency of the one-CTA corner selection
+// (~140 us) or of the tracker is not the call rate.  With future == 0 the output chain waits for T[n] of this call.
 
-// Estimation chain for frame index s->n whose pixels are (being) written to ring slot n % W on s->stream.
+// Estimation of frame index s->n whose pixels are in ring slot n % W once s->ev_in has fired.
 static vstab_status stream_estimate(vstab* s) {
     auto set_err = [&](const std::string& e) { s->err = e; };
     Geometry& g = s->g;
@@ -353,17 +359,25 @@ static vstab_status stream_estimate(vstab* s) {
     const uint8_t* frame = s->ring.as<uint8_t>() + (size_t)slot * g.frame_bytes;
     unsigned long long* sums = s->sums.as<unsigned long long>() + slot * 3;
     int* ccount = s->ccount.as<int>();
-    s->mark(2, q);
-    CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3, q));
-    launch_ingest(g.plan, frame, g.pitch, g.frame_bytes, 1, s->pyr(cur), g.pd.frame_bytes, sums, q);   // :1169-1175
-    launch_pyramid(g.pd, s->pyr(cur), 1, q);
-    CK(cudaEventRecord(s->ev_pyr, q));
-    s->mark(3, q);
+    cudaStream_t up = s->ing_stream;
+    CK(cudaStreamWaitEvent(up, s->ev_in, 0));
+    // pyramid buffer n % 3 held frame n-3: read by LK of frames n-3 and n-2 and by the corner detection of n-3
+    if (n >= 3) {
+        CK(cudaStreamWaitEvent(up, s->ev_fit[(n - 2) & 7], 0));
+        CK(cudaStreamWaitEvent(up, s->ev_gftt[(n - 3) & 3], 0));
+    }
+    s->mark(2, up);
+    CK(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3, up));
+    launch_ingest(g.plan, frame, g.pitch, g.frame_bytes, 1, s->pyr(n), g.pd.frame_bytes, sums, up);    // :1169-1175
+    launch_pyramid(g.pd, s->pyr(n), 1, up);
+    CK(cudaEventRecord(s->ev_pyr[n & 3], up));
+    s->mark(3, up);
+    CK(cudaStreamWaitEvent(q, s->ev_pyr[n & 3], 0));
     if (n > 0) {
-        CK(cudaStreamWaitEvent(q, s->ev_gftt, 0));                    // corners of frame n-1
+        CK(cudaStreamWaitEvent(q, s->ev_gftt[(n - 1) & 3], 0));       // corners of frame n-1
         s->mark(11, q);
         // :1187 trackFeatures
-        launch_lk(s->pyr(prev), s->pyr(cur), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
+        launch_lk(s->pyr(n - 1), s->pyr(n), g.pd.frame_bytes, g.pd.frame_bytes, g.pd, s->corners(prev), ccount + prev, 1,
                   s->lkpts.as<float2>(), s->lkstat.as<uint8_t>(), q);
         s->mark(12, q);
         // :1203 estimateMotion, :1209 updateTransformations
@@ -371,16 +385,19 @@ static vstab_status stream_estimate(vstab* s) {
                    g.ww / 2.0, g.wh / 2.0, s->T.as<double>() + (size_t)(n % s->t_mod) * 9, s->Mtap.as<double>(),
                    s->fitc.as<int>(), nullptr, n, q);
     }
-    CK(cudaEventRecord(s->ev_fit[n & 3], q));
+    CK(cudaEventRecord(s->ev_fit[n & 7], q));
     s->mark(4, q);
-    // corner detection of this frame (:1318 / :1179) only feeds the next call's tracker: own stream
-    CK(cudaStreamWaitEvent(s->gftt_stream, s->ev_pyr, 0));
-    s->mark(5, s->gftt_stream);
+    // corner detection of this frame (:1318 / :1179) only feeds the next call's tracker.  Its corner list (parity n & 1)
+    // was last read by the tracker / fit of frame n-1.
+    cudaStream_t qg = s->gftt_stream[cur];
+    CK(cudaStreamWaitEvent(qg, s->ev_pyr[n & 3], 0));
+    if (n > 0) CK(cudaStreamWaitEvent(qg, s->ev_fit[(n - 1) & 7], 0));
+    s->mark(5, qg);
     static const bool tap_eig = getenv("VSTAB_DEBUG_TAPS") != nullptr;   // the min-eigenvalue map is a debug tap only
-    launch_gftt(s->pyr(cur), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws,
-                s->corners(cur), ccount + cur, tap_eig ? s->gws.eig : nullptr, s->gftt_stream);
-    CK(cudaEventRecord(s->ev_gftt, s->gftt_stream));
-    s->mark(6, s->gftt_stream);
+    launch_gftt(s->pyr(n), g.pd.frame_bytes, g.ww, g.wh, 1, 0.01, g.min_distance, kMaxCorners, s->gws[cur],
+                s->corners(cur), ccount + cur, tap_eig ? s->gws[cur].eig : nullptr, qg);
+    CK(cudaEventRecord(s->ev_gftt[n & 3], qg));
+    s->mark(6, qg);
     CK(cudaGetLastError());
     return VSTAB_OK;
 }
@@ -554,11 +571,16 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
         for (auto& set : s->tev) for (auto& e : set) cudaEventCreate(&e);
     // which fit the output chain of call c has to wait for.  The window average reads T up to c-1
     // (stabilizer.cpp:825-826); every other mode reads nothing newer than the presentation frame p = c - F (its T for
-    // the ACCUMULATED product, its channel sums, its pixels), so with future >= 2 the chain does not wait for the
-    // estimation of frame c-1, which is what call c-1 left running
+    // the ACCUMULATED product, its channel sums, its pixels).  Waiting for the fit of frame c-1 or c-2 there would tie
+    // the call period to the LATENCY of a frame's estimation (upload -> pyramid -> LK -> fit, ~0.4 ms, longer than two
+    // calls); with a lag of min(F, 6) frames only its throughput matters.
     auto fit_event = [&](long c) {
-        const bool newest = s->mode == VSTAB_GLOBAL_SMOOTHING || s->F < 2 || c < 2;
-        return s->ev_fit[(c - (newest ? 1 : 2)) & 3];
+        long lag = (long)s->F < 6 ? (long)s->F : 6;
+        // ORB / SIFT lock also registers the NEXT call's presentation frame c + 1 - F from the ring (look-ahead)
+        if (s->mode == VSTAB_ORB_FULL_LOCK || s->mode == VSTAB_SIFT_FULL_LOCK) lag -= 1;
+        if (s->mode == VSTAB_GLOBAL_SMOOTHING || lag < 1) lag = 1;
+        if (lag > c) lag = c;
+        return s->ev_fit[(c - lag) & 7];
     };
     auto output_into = [&](long c, int slot, cudaStream_t q, bool ahead) -> vstab_status {
         uint8_t* dst = device_out ? out : s->dout_at(slot);
@@ -596,13 +618,12 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
     // channel sums of an earlier call's output chain) are ordered before this copy by ev_out.
     // Host input: the upload runs on its own stream, beside the estimation of the previous frame.
     // (Enqueuing the upload ahead of the output chain was measured: no gain for LK, -4 % for ORB lock.)
-    cudaStream_t up = in_kind == cudaMemcpyHostToDevice ? s->copy_stream : s->stream;
+    cudaStream_t up = s->copy_stream;
     if (s->n > 0) CK(cudaStreamWaitEvent(up, s->ev_out, 0));
     s->mark(0, up);
     CK(cudaMemcpy2DAsync(slot, g.pitch, in, step, row_bytes, rows, in_kind, up));
     s->mark(1, up);
     CK(cudaEventRecord(s->ev_in, up));
-    if (up != s->stream) CK(cudaStreamWaitEvent(s->stream, s->ev_in, 0));
     vstab_status st = stream_estimate(s);
     if (st != VSTAB_OK) return st;
     if (!out_first) {
@@ -612,7 +633,7 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
             CK(cudaMemcpy2DAsync(out, out_step, slot, g.pitch, row_bytes, rows, out_kind, s->out_stream));
             s->last_presented = 0;
         } else {
-            CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit[s->n & 3], 0));   // future == 0: needs T[n] of this call
+            CK(cudaStreamWaitEvent(s->out_stream, s->ev_fit[s->n & 7], 0));   // future == 0: needs T[n] of this call
             s->out_slot ^= 1;
             st = output_into(s->n, s->out_slot, s->out_stream, false);
             if (st != VSTAB_OK) return st;
@@ -728,17 +749,29 @@ vstab_status vstab_create(size_t past_frames, size_t future_frames, int working_
         cudaEventCreateWithFlags(&s->ev_fit[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fit[2], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fit[3], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[4], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[5], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[6], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fit[7], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&s->gftt_stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->gftt_stream[0], cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->gftt_stream[1], cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&s->ing_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s->feat_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_feat, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_reg, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_pyr[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_pyr[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_pyr[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_pyr[3], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_gftt[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_gftt[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_gftt[3], cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&s->pre_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_chain, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev_gftt, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s->ev_gftt[0], cudaEventDisableTiming) != cudaSuccess) {
         g_err = "cudaStreamCreate failed"; vstab_destroy(s); return VSTAB_ERR_CUDA;
     }
     *out = s;
@@ -765,13 +798,14 @@ void vstab_destroy(vstab_t* s) {
     if (s->ev_in) cudaEventDestroy(s->ev_in);
     for (auto e : s->ev_fit) if (e) cudaEventDestroy(e);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
-    if (s->gftt_stream) { cudaStreamSynchronize(s->gftt_stream); cudaStreamDestroy(s->gftt_stream); }
+    for (auto q : s->gftt_stream) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->ing_stream) { cudaStreamSynchronize(s->ing_stream); cudaStreamDestroy(s->ing_stream); }
     if (s->feat_stream) { cudaStreamSynchronize(s->feat_stream); cudaStreamDestroy(s->feat_stream); }
     if (s->ev_feat) cudaEventDestroy(s->ev_feat);
     if (s->ev_reg) cudaEventDestroy(s->ev_reg);
-    if (s->ev_pyr) cudaEventDestroy(s->ev_pyr);
-    if (s->ev_gftt) cudaEventDestroy(s->ev_gftt);
+    for (auto e : s->ev_pyr) if (e) cudaEventDestroy(e);
+    for (auto e : s->ev_gftt) if (e) cudaEventDestroy(e);
     if (s->pre_stream) { cudaStreamSynchronize(s->pre_stream); cudaStreamDestroy(s->pre_stream); }
     if (s->ev_pre) cudaEventDestroy(s->ev_pre);
     if (s->ev_chain) cudaEventDestroy(s->ev_chain);
@@ -806,8 +840,10 @@ vstab_status vstab_synchronize(vstab_t* s) {
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->out_stream));
-    CK(cudaStreamSynchronize(s->gftt_stream));
+    CK(cudaStreamSynchronize(s->gftt_stream[0]));
+    CK(cudaStreamSynchronize(s->gftt_stream[1]));
     CK(cudaStreamSynchronize(s->copy_stream));
+    CK(cudaStreamSynchronize(s->ing_stream));
     CK(cudaStreamSynchronize(s->feat_stream));
     CK(cudaStreamSynchronize(s->pre_stream));
     return VSTAB_OK;
@@ -869,7 +905,8 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
     if (cudaSetDevice(s->device) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s->out_stream) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(s->gftt_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s->gftt_stream[0]) != cudaSuccess || cudaStreamSynchronize(s->gftt_stream[1]) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s->copy_stream) != cudaSuccess || cudaStreamSynchronize(s->ing_stream) != cudaSuccess) return -1;
     Geometry& g = s->g;
     const long last = s->n - 1;                 // index of the most recent frame
     const int cur = (int)(last & 1), prev = cur ^ 1;
@@ -881,10 +918,10 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
     int counts[2] = {0, 0};
     if (cudaMemcpy(counts, s->ccount.p, sizeof(counts), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     switch (tap) {
-        case VSTAB_TAP_GRAY: return copy(s->pyr(cur) + g.pd.off[0], (size_t)g.ww * g.wh, (long)g.ww * g.wh);
+        case VSTAB_TAP_GRAY: return copy(s->pyr(last) + g.pd.off[0], (size_t)g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_PYR1: case VSTAB_TAP_PYR2: case VSTAB_TAP_PYR3: {
             const int l = tap - VSTAB_TAP_PYR1 + 1;
-            return copy(s->pyr(cur) + g.pd.off[l], (size_t)g.pd.w[l] * g.pd.h[l], (long)g.pd.w[l] * g.pd.h[l]);
+            return copy(s->pyr(last) + g.pd.off[l], (size_t)g.pd.w[l] * g.pd.h[l], (long)g.pd.w[l] * g.pd.h[l]);
         }
         case VSTAB_TAP_PREV_PTS: if (last == 0) return 0; return copy(s->corners(prev), sizeof(float2) * counts[prev], counts[prev]);
         case VSTAB_TAP_LK_PTS: if (last == 0) return 0; return copy(s->lkpts.p, sizeof(float2) * counts[prev], counts[prev]);
@@ -895,7 +932,7 @@ long vstab_read_tap(vstab_t* s, int tap, void* dst, size_t dst_bytes) {
         case VSTAB_TAP_H_STABILIZE: if (last == 0) return 0; return copy((char*)s->wp_at(s->out_slot) + offsetof(WarpParams, Hw), sizeof(double) * 9, 9);
         case VSTAB_TAP_H_SCALED: if (last == 0) return 0; return copy((char*)s->wp_at(s->out_slot) + offsetof(WarpParams, Hs), sizeof(double) * 9, 9);
         case VSTAB_TAP_BORDER: if (last == 0) return 0; return copy((char*)s->wp_at(s->out_slot) + offsetof(WarpParams, border), 3, 3);
-        case VSTAB_TAP_EIG: return copy(s->gws.eig, sizeof(float) * g.ww * g.wh, (long)g.ww * g.wh);
+        case VSTAB_TAP_EIG: return copy(s->gws[cur].eig, sizeof(float) * g.ww * g.wh, (long)g.ww * g.wh);
         case VSTAB_TAP_INLIERS: if (last == 0) return 0; return copy(s->fitc.p, sizeof(int) * 2, 2);
         case VSTAB_TAP_LOCK_H: if (!s->lock_h.p) return 0; return copy(s->lock_h.as<double>() + 9 * s->lock_slot, sizeof(double) * 9, 9);
         case VSTAB_TAP_ORB_COUNTS: if (!s->lock_tap.p) return 0; return copy(s->lock_tap.as<int>() + 8 * s->lock_slot, sizeof(int) * 5, 5);
