@@ -101,6 +101,11 @@ public:
     // `#if 0`; here it is a run-time switch, off by default.
     void setTrailCompositing(bool enable) { check(vstab_set_trail(h_, enable ? 1 : 0)); }
 
+    // TRANSLATION_LOCK / ROTATION_LOCK evaluate to the identity in the reference (include/stabilizer.hpp:23 "@todo fix
+    // partial locking modes"); with this switch its formulas (src/stabilizer.cpp:1246-1260) are fed with the accumulated
+    // lock, which is what they were written for.  Off by default.
+    void setPartialLockFix(bool enable) { check(vstab_set_partial_lock_fix(h_, enable ? 1 : 0)); }
+
     inline size_t totalFrameWindowSize() const { return totalPastFrames_ + 1 + totalFutureFrames_; }
 
     // static bool decomposeHomography(const cv::Mat& H, HomographyParameters&, cv::Point2d rot_center = {0,0})

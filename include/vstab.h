@@ -102,6 +102,15 @@ void vstab_compose_homography(const vstab_hparams* p, double cx, double cy, doub
  * accelerated implementations", include/stabilizer.hpp:255-259): every output is copyFeathered(presentation frame,
  * trail background, H) and becomes the next trail background (zeros at the start, :128-130).  Off by default. */
 vstab_status vstab_set_trail(vstab_t* s, int enable);
+
+/* TRANSLATION_LOCK / ROTATION_LOCK as the reference's own formulas intend them (src/stabilizer.cpp:1246-1260:
+ * R = getRotationMatrix2D(centre, theta(H_lock)), H_translation_lock = R * H_lock, H_rotation_lock = R^-1).  In the
+ * reference calculateFullLockStabilization returns the identity in these two modes (:311-441), so both evaluate to the
+ * identity ("@todo fix partial locking modes", include/stabilizer.hpp:23); that behaviour is the default here.  With
+ * enable != 0 the two modes are fed with the ACCUMULATED_FULL_LOCK product (:317-338, anchor = the call after
+ * setStabilizationMode): translation lock keeps the accumulated rotation and cancels the drift of the image centre,
+ * rotation lock cancels only the accumulated rotation about the image centre.  Per-frame API only. */
+vstab_status vstab_set_partial_lock_fix(vstab_t* s, int enable);
 const char* vstab_last_error(const vstab_t* s);      /* message of the last non-OK status */
 const char* vstab_status_string(vstab_status st);
 int vstab_abi_version(void);

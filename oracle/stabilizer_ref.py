@@ -212,7 +212,7 @@ class StabilizerRef:
 
     def __init__(self, past_frames: int = 15, future_frames: int = 15,
                  working_height: int = 360, faithful_waste: bool = True,
-                 exact_sift_matcher: bool = False, trail: bool = False):
+                 exact_sift_matcher: bool = False, trail: bool = False, partial_lock_fix: bool = False):
         # stabilizer.cpp:36-53
         if past_frames == 0 and future_frames == 0:
             raise ValueError("Stabilizer: pastFrames and futureFrames cannot both be 0")
@@ -224,6 +224,9 @@ class StabilizerRef:
         self.faithful_waste = faithful_waste
         self.exact_sift_matcher = exact_sift_matcher
         self.trail = trail                      # take the `#if 0` copyFeathered branch of stabilizeFrame (:1303-1307)
+        # TRANSLATION_/ROTATION_LOCK: feed :1246-1260 with the accumulated lock instead of the identity :311-441 returns
+        # in those modes (the hpp:23 @todo; vstab_set_partial_lock_fix).  Not reference behaviour: off by default.
+        self.partial_lock_fix = partial_lock_fix
         self.scale = 1.0
         self.orig_size = (0, 0)      # (w, h)
         self.work_size = (0, 0)
@@ -369,7 +372,7 @@ class StabilizerRef:
     def _full_lock(self, p):                     # stabilizer.cpp:311-791
         if self.mode == GLOBAL_SMOOTHING:
             return np.eye(3)
-        if self.mode == ACCUMULATED_FULL_LOCK:
+        if self.mode == ACCUMULATED_FULL_LOCK or (self.partial_lock_fix and self.mode in (TRANSLATION_LOCK, ROTATION_LOCK)):
             fidx = self.frames[p][1]
             if self.acc_H is None:
                 self.acc_H = np.eye(3)

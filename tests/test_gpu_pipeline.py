@@ -27,9 +27,11 @@ def _corner_diff(Ha, Hb, W, H):
     return float(np.abs(a[:2] / a[2] - b[:2] / b[2]).max())
 
 
-def _run_both(frames, P, F, wh, lock_at=None, mode=None):
-    ref = sr.StabilizerRef(P, F, wh)
+def _run_both(frames, P, F, wh, lock_at=None, mode=None, partial_lock_fix=False):
+    ref = sr.StabilizerRef(P, F, wh, partial_lock_fix=partial_lock_fix)
     st = vs.Stabilizer(P, F, wh)
+    if partial_lock_fix:
+        st.set_partial_lock_fix(True)
     H, W = frames[0].shape[:2]
     stats = dict(h=0.0, t=0.0, pix=0, ndiff=0, frac_gt1=0.0, lk=0.0, corners_differ=0, status=0)
     for i, f in enumerate(frames):
@@ -115,6 +117,42 @@ def test_translation_rotation_lock_identity(golden):
         assert np.array_equal(st.tap(vs.TAP_H_STABILIZE), np.eye(3))
         assert np.array_equal(out, golden["clip"][5 - 3])       # identity warp of the presented frame
         st.close()
+
+
+@pytest.mark.parametrize("mode", [sr.TRANSLATION_LOCK, sr.ROTATION_LOCK])
+def test_partial_lock_fix_matches_oracle(texture, mode):
+    """SURVEY 8(f4), the reference's "@todo fix partial locking modes" (include/stabilizer.hpp:23): its formulas
+    (src/stabilizer.cpp:1246-1260) fed with the accumulated lock (vstab_set_partial_lock_fix) against the oracle doing the same."""
+    frames = render_clip(texture, 1280, 720, 40)
+    s = _run_both(frames, 12, 8, 360, lock_at=20, mode=mode, partial_lock_fix=True)
+    assert s["corners_differ"] == 0 and s["status"] == 0 and s["lk"] == 0.0
+    assert s["h"] <= H_ACHIEVED_PX
+    assert s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
+
+
+def test_partial_lock_fix_is_not_the_identity(texture):
+    """With the switch on, TRANSLATION_LOCK cancels the drift of the image centre and leaves the rotation, ROTATION_LOCK
+    is a pure rotation about the working-size centre by the accumulated angle."""
+    frames = render_clip(texture, 640, 360, 30)
+    Hs = {}
+    for mode in (vs.ACCUMULATED_FULL_LOCK, vs.TRANSLATION_LOCK, vs.ROTATION_LOCK):
+        st = vs.Stabilizer(6, 4, 180)
+        st.set_partial_lock_fix(True)
+        for i, f in enumerate(frames):
+            if i == 10:
+                st.set_stabilization_mode(mode)
+            st.stabilize_frame(f)
+        Hs[mode] = st.tap(vs.TAP_H_STABILIZE)
+        st.close()
+    full, tl, rl = Hs[vs.ACCUMULATED_FULL_LOCK], Hs[vs.TRANSLATION_LOCK], Hs[vs.ROTATION_LOCK]
+    th = np.arctan2(full[1, 0], full[0, 0])
+    assert abs(th) > 1e-4 and not np.allclose(tl, np.eye(3)) and not np.allclose(rl, np.eye(3))
+    assert abs(np.arctan2(tl[1, 0], tl[0, 0])) < 1e-12                    # no rotation left in the translation lock
+    c = np.array([160.0, 90.0, 1.0])                                      # 640x360 at working height 180
+    assert np.allclose(rl @ c, c, atol=1e-9)                              # rotation lock keeps the centre fixed
+    assert abs(np.arctan2(rl[1, 0], rl[0, 0]) - th) < 1e-12              # and carries the accumulated angle
+    # translation lock = R * H_lock with R a rotation about the centre: the centre is displaced as far as under the full lock
+    assert abs(np.linalg.norm((tl @ c - c)[:2]) - np.linalg.norm((full @ c - c)[:2])) < 1e-9
 
 
 def test_api_errors(golden):

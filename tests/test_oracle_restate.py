@@ -209,3 +209,33 @@ def test_copy_feathered_restatement_equals_opencv():
         assert np.array_equal(R.copy_feathered(fg, bg, Hm), sr.copy_feathered(fg, bg, Hm))
     with pytest.raises(ValueError):
         sr.copy_feathered(fg, bg[:-1], Hm)
+
+
+def test_oracle_partial_lock_fix_feeds_the_reference_formulas():
+    """StabilizerRef(partial_lock_fix=True): :1246-1260 fed with the accumulated lock; off (the reference) they see the identity."""
+    from oracle import stabilizer_ref as sr, synth as osynth, camera_engine_ref as ce
+    tex = osynth.make_texture(512)
+    path = osynth.camera_path(16)
+    frames = [ce.render_frame(tex, path[i], 320, 180, osynth.focal_for_width(320)) for i in range(16)]
+    out = {}
+    for fix in (False, True):
+        for mode in (sr.TRANSLATION_LOCK, sr.ROTATION_LOCK, sr.ACCUMULATED_FULL_LOCK):
+            ref = sr.StabilizerRef(4, 3, 180, faithful_waste=False, partial_lock_fix=fix)
+            for i, f in enumerate(frames):
+                if i == 6:
+                    ref.set_stabilization_mode(mode)
+                ref.stabilize_frame(f)
+            out[(fix, mode)] = ref.taps.H_stabilize.copy()
+    eye = np.eye(3)
+    assert np.array_equal(out[(False, sr.TRANSLATION_LOCK)], eye) and np.array_equal(out[(False, sr.ROTATION_LOCK)], eye)
+    full = out[(True, sr.ACCUMULATED_FULL_LOCK)]
+    assert np.array_equal(full, out[(False, sr.ACCUMULATED_FULL_LOCK)])
+    tl, rl = out[(True, sr.TRANSLATION_LOCK)], out[(True, sr.ROTATION_LOCK)]
+    th = np.arctan2(full[1, 0], full[0, 0])
+    assert abs(th) > 1e-5
+    assert abs(np.arctan2(tl[1, 0], tl[0, 0])) < 1e-12
+    assert abs(np.arctan2(rl[1, 0], rl[0, 0]) - th) < 1e-12
+    c = np.array([160.0, 90.0, 1.0])
+    assert np.allclose(rl @ c, c, atol=1e-9)
+    # translation lock = R * H_lock with R a rotation about the centre: the centre is displaced as far as under the full lock
+    assert abs(np.linalg.norm((tl @ c - c)[:2]) - np.linalg.norm((full @ c - c)[:2])) < 1e-9

@@ -9,6 +9,7 @@ import torch
 import vstab_b200 as vs
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+lock = not (len(sys.argv) > 2 and sys.argv[2] == "smooth")     # "smooth": stay in GLOBAL_SMOOTHING
 W, H = 1920, 1080
 from oracle import synth as osynth, camera_engine_ref as ce
 tex = osynth.make_texture(2048)
@@ -24,7 +25,7 @@ np.ctypeslib.as_array((C.c_uint8 * (len(host) * nbytes)).from_address(hin)).resh
 st = vs.Stabilizer(60, 45, 360, device=0)
 t0 = 0.0
 for i in range(n):
-    if i == 46:
+    if i == 46 and lock:
         st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
     if i == 50:
         st.synchronize(); t0 = time.perf_counter()

@@ -280,6 +280,7 @@ struct vstab {
     SiftPlan* sift = nullptr;
     bool has_reference = false;
     bool trail = false;                     // copyFeathered branch of stabilizeFrame (:1303-1307)
+    bool partial_fix = false;               // TRANSLATION_/ROTATION_LOCK fed with the accumulated lock (hpp:23 @todo)
     DevBuf trail_bg, trail_ws;              // trail_background_ (:129) and K14 scratch
     DevBuf feat_ws, feat_gray, nn_x, nn_y, ref_kps, ref_desc, cur_kps, cur_desc, orb_counts, m_idx, m_d0, m_d1, m_good,
         m_ref, m_cur, m_status, lock_fit, lock_h, lock_tap;
@@ -485,7 +486,8 @@ static vstab_status stream_output(vstab* s, long n, uint8_t* d_out, size_t out_p
     Geometry& g = s->g;
     const long p = n - (long)s->F > 0 ? n - (long)s->F : 0;                                            // :1226-1229
     if (!prepared_ahead) s->mark(7, q);
-    if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) {                                                      // :317-338
+    const bool partial = s->partial_fix && (s->mode == VSTAB_TRANSLATION_LOCK || s->mode == VSTAB_ROTATION_LOCK);
+    if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK || partial) {                                           // :317-338
         // (acc_call == n: a prepared-ahead chain that was dropped afterwards has already made this call's update)
         if (s->acc_call != n) launch_acc_update(s->T.as<double>(), s->t_mod, p, s->acc_valid ? 0 : 1, s->acc.as<double>(), q);
         s->acc_call = n;
@@ -517,6 +519,8 @@ static vstab_status stream_output(vstab* s, long n, uint8_t* d_out, size_t out_p
     a.scale = g.scale;
     a.sums = s->sums.as<unsigned long long>(); a.sums_mod = s->W; a.frame_base = 0;
     a.npix = (double)g.rows * (double)g.cols;
+    a.partial_fix = s->partial_fix ? 1 : 0;
+    a.cx = (double)(float)(g.ww / 2.0); a.cy = (double)(float)(g.wh / 2.0);                            // Point2f centre
     launch_smooth(a, n, 1, wp, q);                                                                     // :1234-1296
     if (!prepared_ahead) s->mark(8, q);
     static const bool lookahead = !(getenv("VSTAB_LOOKAHEAD") && atoi(getenv("VSTAB_LOOKAHEAD")) == 0);
@@ -599,7 +603,9 @@ static vstab_status stream_call(vstab* s, const uint8_t* in, int rows, int cols,
         if (s->pre_valid && s->pre_call == s->n && s->pre_epoch == s->epoch && !device_out) {
             s->out_slot ^= 1;                                          // prepared during the previous call
             s->last_presented = p;
-            if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK) { s->acc_valid = true; s->acc_to = s->pre_acc_to; }
+            if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK || (s->partial_fix && (s->mode == VSTAB_TRANSLATION_LOCK || s->mode == VSTAB_ROTATION_LOCK))) {
+                s->acc_valid = true; s->acc_to = s->pre_acc_to;
+            }
             s->mark(7, s->out_stream); s->mark(8, s->out_stream); s->mark(9, s->out_stream);
         } else {
             CK(cudaStreamWaitEvent(s->out_stream, fit_event(s->n), 0));
@@ -698,7 +704,9 @@ static vstab_status stream_check_args(vstab* s, const void* in, int rows, int co
         s->err = "Stabilizer: Frame size has changed. This is not supported.";
         return VSTAB_ERR_SIZE_CHANGED;
     }
-    if (s->mode == VSTAB_ACCUMULATED_FULL_LOCK && s->acc_valid) {
+    const bool acc_mode = s->mode == VSTAB_ACCUMULATED_FULL_LOCK ||
+                          (s->partial_fix && (s->mode == VSTAB_TRANSLATION_LOCK || s->mode == VSTAB_ROTATION_LOCK));
+    if (acc_mode && s->acc_valid) {
         // the reference asserts presentation_frame_idx > 0 and from_frame_idx == acc.to (:329-332);
         // both fail exactly when the presentation frame did not advance
         const long p = s->n - (long)s->F > 0 ? s->n - (long)s->F : 0;
@@ -2029,6 +2037,19 @@ extern "C" vstab_status vstab_k_warp(int device, const uint8_t* bgr, int rows, i
     launch_warp(src.as<uint8_t>(), pitch, 0, 0, wp.as<WarpParams>(), 1, cols, rows, dst.as<uint8_t>(), pitch, 0, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy2D(out, out_step, dst.p, pitch, (size_t)cols * 3, rows, cudaMemcpyDeviceToHost));
+    return VSTAB_OK;
+}
+
+extern "C" vstab_status vstab_set_partial_lock_fix(vstab_t* s, int enable) {
+    if (!s) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (s->partial_fix == (enable != 0)) return VSTAB_OK;
+    s->partial_fix = enable != 0;
+    s->epoch += 1;
+    if (s->mode == VSTAB_TRANSLATION_LOCK || s->mode == VSTAB_ROTATION_LOCK) {
+        // the lock starts at the next call, as after setStabilizationMode (:55-70)
+        s->acc_valid = false; s->acc_to = -1; s->acc_call = -1;
+        s->lock_call = s->n;
+    }
     return VSTAB_OK;
 }
 

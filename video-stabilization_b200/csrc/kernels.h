@@ -113,6 +113,8 @@ struct SmoothArgs {
     long sums_mod;               // slot = abs frame % sums_mod   (ring) or abs - frame_base (offline: see frame_base)
     long frame_base;             // offline: slot = abs - frame_base; streaming: 0 with modulo
     double npix;                 // rows*cols
+    int partial_fix;             // TRANSLATION_/ROTATION_LOCK from the accumulated product (vstab_set_partial_lock_fix)
+    double cx, cy;               // working-size centre (rot_center, :1237)
 };
 void launch_smooth(const SmoothArgs& a, long call_first, int ncalls, WarpParams* out, cudaStream_t st);
 // ORB / SIFT registration: fold one fit result into the "previously returned H" state (:724-787)

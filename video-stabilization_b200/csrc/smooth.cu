@@ -99,11 +99,27 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
     // ---- full-lock transform -------------------------------------------------------------
     double Hl[9];
     eye3(Hl);
-    if (mode == 0) {
+    const bool partial = a.partial_fix && (mode == 3 || mode == 4);
+    if (mode == 0 || partial) {
         const double* accp = a.acc + (size_t)(a.acc_mod > 0 ? (p % a.acc_mod) : 0) * 9;
         invert3(accp, Hl);                                // accumulatedTransform_.H.inv(), :438
         HParams hp;
-        if (!decompose_h(Hl, 0.0, 0.0, &hp)) eye3(Hl);    // :1240-1244
+        if (!decompose_h(Hl, 0.0, 0.0, &hp)) { eye3(Hl); hp.theta = 0.0; }   // :1240-1244
+        if (partial) {
+            // :1246-1260 as written, fed with the accumulated lock instead of the identity the reference's
+            // calculateFullLockStabilization returns in these modes (the @todo of include/stabilizer.hpp:23):
+            // R = getRotationMatrix2D(rot_center, theta in degrees, 1), H_translation_lock = R * H_lock (the accumulated
+            // rotation is put back, the translation stays locked), H_rotation_lock = R^-1 (only the rotation is cancelled)
+            // cv::getRotationMatrix2D: angle *= CV_PI / 180 (one constant), alpha = cos, beta = sin, Point2f centre
+            const double kDegToRad = 3.1415926535897932384626433832795 / 180.0;
+            const double ang = (hp.theta * 180.0 / 3.14159265358979323846) * kDegToRad;
+            const double al = cos(ang), be = sin(ang);
+            double R[9] = {al, be, (1.0 - al) * a.cx - be * a.cy, -be, al, be * a.cx + (1.0 - al) * a.cy, 0.0, 0.0, 1.0};
+            double tmp[9];
+            if (mode == 3) matmul3(R, Hl, tmp);
+            else invert3(R, tmp);
+            for (int i = 0; i < 9; ++i) Hl[i] = tmp[i];
+        }
     }
     if ((mode == 1 || mode == 2) && a.reg) {
         // offline: the matrix returned at call c is the registration of the latest presented frame that
@@ -120,7 +136,7 @@ smooth_kernel(SmoothArgs a, long call_first, int ncalls, WarpParams* __restrict_
     }
     double H[9];
     if (mode == 5) { for (int i = 0; i < 9; ++i) H[i] = Hs[i]; }
-    else if (mode == 0 || mode == 1 || mode == 2) { for (int i = 0; i < 9; ++i) H[i] = Hl[i]; }
+    else if (mode == 0 || mode == 1 || mode == 2 || partial) { for (int i = 0; i < 9; ++i) H[i] = Hl[i]; }
     else { eye3(H); }                                     // T/R lock: identity
 
     WarpParams wp;

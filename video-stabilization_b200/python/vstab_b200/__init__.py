@@ -81,6 +81,7 @@ SYMBOLS = {
     "vstab_compose_homography": (None, [C.POINTER(HParams), C.c_double, C.c_double, _f64p]),
     "vstab_last_error": (C.c_char_p, [_vp]),
     "vstab_set_trail": (C.c_int, [_vp, C.c_int]),
+    "vstab_set_partial_lock_fix": (C.c_int, [_vp, C.c_int]),
     "vstab_k_copy_feathered": (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _f64p, _vp, C.c_size_t]),
     "vstab_host_alloc": (_vp, [C.c_size_t]),
     "vstab_host_free": (None, [_vp]),
@@ -226,6 +227,11 @@ class Stabilizer:
     def set_trail(self, enable: bool) -> None:
         """The copyFeathered branch of stabilizeFrame (src/stabilizer.cpp:1303-1307), off by default as in the reference."""
         _check(self._lib.vstab_set_trail(self._h, 1 if enable else 0), self._h)
+
+    def set_partial_lock_fix(self, enable: bool) -> None:
+        """TRANSLATION_/ROTATION_LOCK from the accumulated lock (src/stabilizer.cpp:1246-1260 fed as intended; the
+        reference returns the identity in these modes, which stays the default)."""
+        _check(self._lib.vstab_set_partial_lock_fix(self._h, 1 if enable else 0), self._h)
 
     def set_stabilization_mode(self, mode: int) -> None:
         _check(self._lib.vstab_set_mode(self._h, int(mode)), self._h)
