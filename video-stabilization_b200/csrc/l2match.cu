@@ -4,16 +4,17 @@
 // FLANN's randomised KD-trees are approximate and not reproducible call to call; this
 // kernel returns the exact nearest neighbour, which equals cv::BFMatcher(NORM_L2).match 100 %:
 //   ||a_i - b_j||^2 = ||a_i||^2 + ||b_j||^2 - 2 a_i . b_j
-// SIFT descriptors are integers 0..255, exact in fp16; products <= 65025 and the
-// 128-term sums <= 8.4e6 < 2^24, so the fp32 accumulation in TMEM is exact and the squared
-// distances are exact integers.
+// SIFT descriptors are integers 0..255: the dot products are exact integers <= 128 * 255^2 = 8.3e6.
 //
-// One CTA owns 128 reference rows.  A (128 x 128 fp16) is staged once, B tiles of 128 current rows
-// stream through shared memory, both K-major in the 128-byte swizzle the UMMA descriptors name.  One
-// elected thread issues 8 x tcgen05.mma (M128 N128 K16, kind::f16) per tile into a 128-column TMEM
-// accumulator, commits to an mbarrier; the four warps then read their 32-lane TMEM quarter with
-// tcgen05.ld and fold the tile into a running row-wise arg-min -- the distance matrix never
-// leaves the SM.
+// Default path, l2_nn_i8_kernel (further down): tcgen05 kind::i8 on the raw descriptor bytes (u8 x u8 -> s32), operand
+// tiles by TMA (SWIZZLE_128B: a descriptor row is one 128-byte swizzle row), a 4-stage ring of B tiles with full / empty
+// mbarriers, two 128-column TMEM accumulators, warp-specialised CTAs (producer lane, MMA lane, four epilogue warps), a
+// whole batch of frames along grid.z.  The epilogue folds each 128 x 128 tile into a row-wise arg-min on the packed key
+// (|b|^2 - 2 a.b) * 128 + column; the distance matrix never leaves the SM.
+//
+// VSTAB_L2_VARIANT=0 keeps round 1's kernel below for comparison (l2_nn_kernel): descriptors converted to fp16 by the
+// CTA itself (exact: 0..255; fp32 accumulation of 128 products <= 8.4e6 < 2^24 is exact), one shared-memory stage, one
+// 128-column accumulator, 8 x tcgen05.mma (M128 N128 K16, kind::f16) per tile, MMA -> commit -> wait -> epilogue in series.
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
