@@ -599,6 +599,21 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
     dt_copy = max_over_ranks(time.perf_counter() - t0)
     host_copy_gbs_total = world * 2 * (2 * n_clip * nbytes) / dt_copy / 1e9      # bytes read + bytes written, all ranks
 
+    # ---- what the links give these ranks at the same time: the same pinned buffers copied host -> device and device -> host
+    # on two streams, chunked like the e2e leg, no kernels.  This is the ceiling of the e2e leg on this box at this N.
+    chunk = max(1, min(args.e2e_batch, n_clip))
+    secs = C.c_double(0.0)
+
+    def link_pass(passes):
+        st = lib.vstab_debug_link_probe(local, C.c_void_p(hin), C.c_void_p(hout), n_clip * nbytes, chunk * nbytes, passes, C.byref(secs))
+        if st != 0:
+            raise SystemExit("vstab_debug_link_probe failed")
+        return secs.value
+    link_pass(1)
+    sync_all()
+    dt_link = max_over_ranks(link_pass(2))
+    link_gbs_per_gpu = 2 * n_clip * nbytes / dt_link / 1e9                        # per direction, both directions busy
+
     # ---- whole clip, pipelined (each rank stabilizes its own clip: replicas, no collective) --------
     off = offline.OfflineStabilizer(PAST, FUTURE, WH, H, W, args.e2e_batch, device=local)
     for _ in range(2):
@@ -638,6 +653,10 @@ def run_e2e(args, torch, vs, lib, frames, local, world, dev, dist):
             "h2d_bytes_per_step": n_clip * nbytes, "d2h_bytes_per_step": n_clip * nbytes,
             # every frame crosses PCIe once per direction, both directions at the same time: the leg is bound by the link
             "pcie": {"gbs_per_direction_per_gpu": per_gpu_gbs, "frac_of_gen5_x16": per_gpu_gbs / 63.0,
+                     "measured_copy_only_gbs_per_direction_per_gpu": link_gbs_per_gpu,
+                     "frac_of_measured": per_gpu_gbs / link_gbs_per_gpu,
+                     "measured": "pinned cudaMemcpyAsync H2D || D2H of the same buffers and chunk size on two streams, no "
+                                 "kernels, all ranks at the same time (max over ranks): the ceiling of this leg on this box at this N",
                      "peak": "63.0 GB/s per direction nominal (PCIe Gen5 x16); ~55 GB/s is what pinned cudaMemcpy reaches"},
             "replicas": world,
             "host_dram": {"numpy_copy_gbs_all_ranks": host_copy_gbs_total,

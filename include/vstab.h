@@ -219,6 +219,11 @@ void vstab_offline_set_timing(vstab_offline_t* o, int enable);
 vstab_status vstab_offline_stage_times(vstab_offline_t* o, float* ms, int* counts);
 /* number of this library's kernels launched by the process so far */
 long long vstab_launch_count(void);
+/* Measurement aid for bench.py's e2e leg: what the host link gives `device` with both directions busy.  Copies `bytes` of
+ * pinned host memory host -> device (from host_in) and device -> host (into host_out) on two streams, in pieces of
+ * chunk_bytes, `passes` times, no kernels; *seconds = wall time of the whole exchange. */
+vstab_status vstab_debug_link_probe(int device, const void* host_in, void* host_out, size_t bytes, size_t chunk_bytes,
+                                    int passes, double* seconds);
 /* VSTAB_GUARD=1 in the environment puts every device buffer of the library between two 4 KB guard bands; when a buffer is
  * released the bands are read back.  Bytes found overwritten so far (out-of-bounds writes) / buffers allocated with bands. */
 long long vstab_debug_guard_violations(void);

@@ -1534,6 +1534,37 @@ extern "C" vstab_status vstab_offline_stage_times(vstab_offline_t* o, float* ms,
 
 extern "C" long long vstab_launch_count(void) { return vstabk::launch_count(); }
 // VSTAB_GUARD=1: bytes found overwritten in the guard bands of released device buffers so far, and buffers checked
+extern "C" vstab_status vstab_debug_link_probe(int device, const void* host_in, void* host_out, size_t bytes, size_t chunk_bytes,
+                                               int passes, double* seconds) {
+    auto set_err = [&](const std::string& e) { g_err = e; };
+    if (!host_in || !host_out || !seconds || bytes == 0 || chunk_bytes == 0 || passes < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    if (!device_ok(device, g_err)) return VSTAB_ERR_CUDA;
+    DevBuf din, dout;
+    cudaStream_t qi = nullptr, qo = nullptr;
+    CK(din.alloc(chunk_bytes));
+    CK(dout.alloc(chunk_bytes));
+    CK(cudaMemset(dout.p, 0, chunk_bytes));
+    CK(cudaStreamCreateWithFlags(&qi, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&qo, cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());
+    const auto t0 = std::chrono::steady_clock::now();
+    vstab_status st = VSTAB_OK;
+    for (int p = 0; p < passes && st == VSTAB_OK; ++p)
+        for (size_t o = 0; o < bytes; o += chunk_bytes) {
+            const size_t n = bytes - o < chunk_bytes ? bytes - o : chunk_bytes;
+            if (cudaMemcpyAsync(din.p, (const char*)host_in + o, n, cudaMemcpyHostToDevice, qi) != cudaSuccess ||
+                cudaMemcpyAsync((char*)host_out + o, dout.p, n, cudaMemcpyDeviceToHost, qo) != cudaSuccess) {
+                g_err = "cudaMemcpyAsync failed in the link probe"; st = VSTAB_ERR_CUDA; break;
+            }
+        }
+    cudaStreamSynchronize(qi);
+    cudaStreamSynchronize(qo);
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    cudaStreamDestroy(qi);
+    cudaStreamDestroy(qo);
+    return st;
+}
+
 extern "C" long long vstab_debug_guard_violations(void) { return g_guard_violations.load(); }
 extern "C" long long vstab_debug_guard_buffers(void) { return g_guard_buffers.load(); }
 

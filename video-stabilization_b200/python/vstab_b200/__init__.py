@@ -114,6 +114,7 @@ SYMBOLS = {
     "vstab_offline_stage_times": (C.c_int, [_vp, _f32p, C.POINTER(C.c_int)]),
     "vstab_launch_count": (C.c_longlong, []),
     "vstab_debug_guard_violations": (C.c_longlong, []),
+    "vstab_debug_link_probe": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "vstab_debug_guard_buffers": (C.c_longlong, []),
     "vstab_offline_read_h": (C.c_long, [_vp, _f64p, C.c_size_t]),
     "vstab_offline_stream": (C.c_size_t, [_vp]),
