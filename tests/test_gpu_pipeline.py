@@ -85,6 +85,19 @@ def test_config2_accumulated_lock_1080p(texture):
     assert s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
 
 
+@pytest.mark.parametrize("P,F,lock_at", [(5, 0, 7), (5, 1, 8), (0, 3, None), (3, 2, 8), (2, 7, 10), (1, 1, 6)])
+def test_window_shapes_match_oracle(texture_small, P, F, lock_at):
+    """Every shape of the frame window the reference accepts (future == 0: the output needs this call's transform;
+    past == 0; future shorter / longer than the lag the streaming chains run at), window average first, ACCUMULATED lock
+    from `lock_at` on (not with past == 0: the presentation index inside the window is then always 0 and the reference asserts,
+    stabilizer.cpp:329): the engine's stream / event choreography depends on these, the bytes must not."""
+    frames = render_clip(texture_small, 640, 360, 20)
+    s = _run_both(frames, P, F, 180, lock_at=lock_at, mode=sr.ACCUMULATED_FULL_LOCK)
+    assert s["corners_differ"] == 0 and s["status"] == 0 and s["lk"] == 0.0
+    assert s["h"] <= H_ACHIEVED_PX
+    assert s["frac_gt1"] <= FRAC_GT1 and s["pix"] <= MAX_Q5_STEP
+
+
 def test_golden_clip(golden):
     clip = golden["clip"]
     for name, lock_at in (("smooth", None), ("lock", 7)):
