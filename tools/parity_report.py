@@ -1,4 +1,5 @@
 """Full-length parity of the streaming Stabilizer (C ABI) against the oracle on BASELINE's configurations.
+TEST INFRASTRUCTURE (same standing as tests/): oracle/ is imported here as the checker, never as the thing measured.
 Runs on the GPU box.  Frames come from the K13 device renderer (bit-exact with the simulator restatement,
 tests/test_gpu_offline.py::test_render_matches_camera_engine; every `--check-render`-th frame is re-rendered
 by the numpy oracle here and compared), so 2000-frame 1080p clips are affordable.

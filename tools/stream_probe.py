@@ -7,14 +7,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-stabilization_b200", "python")]
 import torch
 import vstab_b200 as vs
+from vstab_b200 import offline, synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 lock = not (len(sys.argv) > 2 and sys.argv[2] == "smooth")     # "smooth": stay in GLOBAL_SMOOTHING
 W, H = 1920, 1080
-from oracle import synth as osynth, camera_engine_ref as ce
-tex = osynth.make_texture(2048)
-path = osynth.camera_path(8)
-host = [ce.render_frame(tex, path[i], W, H, osynth.focal_for_width(W)) for i in range(8)]
+# 8 frames of the scripted path, rendered by the library's own simulator kernel (K13)
+tex = torch.from_numpy(synth.make_texture(2048)).cuda()
+clip = torch.empty((8, H, W, 3), dtype=torch.uint8, device="cuda")
+offline.render_frames(tex, synth.camera_path(8), H, W, synth.focal_for_width(W), clip)
+host = list(clip.cpu().numpy())
 host = host + host[-2:0:-1]          # ping-pong
 lib = vs.load_library()
 lib.vstab_host_alloc.restype = C.c_void_p
