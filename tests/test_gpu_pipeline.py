@@ -422,3 +422,28 @@ def test_trail_branch_matches_oracle(texture_small):
         want, got = ref.stabilize_frame(f), st.stabilize_frame(f)
         assert np.array_equal(got, want), f"call {i}: {int(np.abs(got.astype(int) - want).max())} LSB"
     st.close()
+
+
+def test_switches_between_calls_match_oracle(texture_small):
+    """Mode, trail and partial-lock switches between calls: each one drops the output the engine prepared one call ahead
+    (and, in ACCUMULATED lock, must not apply that call's product update twice).  Byte-identical to the oracle on every call."""
+    frames = render_clip(texture_small, 480, 270, 44)
+    ref = sr.StabilizerRef(5, 3, 135)
+    st = vs.Stabilizer(5, 3, 135)
+    script = {8: ("mode", sr.ACCUMULATED_FULL_LOCK), 13: ("trail", True), 17: ("trail", False), 21: ("mode", sr.GLOBAL_SMOOTHING),
+              25: ("mode", sr.ACCUMULATED_FULL_LOCK), 26: ("trail", True), 27: ("trail", False), 31: ("partial", True),
+              32: ("mode", sr.TRANSLATION_LOCK), 36: ("mode", sr.ROTATION_LOCK), 40: ("mode", sr.ACCUMULATED_FULL_LOCK)}
+    for i, f in enumerate(frames):
+        if i in script:
+            what, v = script[i]
+            if what == "mode":
+                ref.set_stabilization_mode(v); st.set_stabilization_mode(v)
+            elif what == "trail":
+                ref.trail = v; st.set_trail(v)
+            else:
+                ref.partial_lock_fix = v; st.set_partial_lock_fix(v)
+        want, got = ref.stabilize_frame(f), st.stabilize_frame(f)
+        assert np.array_equal(got, want), f"call {i}: {int(np.abs(got.astype(int) - want).max())} LSB, {int((got != want).sum())} bytes"
+        if i:
+            assert _corner_diff(st.tap(vs.TAP_H_SCALED), ref.taps.H_scaled, 480, 270) <= H_ACHIEVED_PX
+    st.close()
