@@ -32,6 +32,26 @@ def test_render_matches_camera_engine(texture_small, W, H):
         assert np.array_equal(frames[i].cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("rows,cols", [(384, 512), (512, 300)])
+def test_render_non_square_texture(texture_small, rows, cols):
+    """tileHeight = 1 / aspect != 1 (camera_engine.cpp:81-88): worldY / tileHeight is a real division per pixel; 7 frames,
+    so that the per-thread frame loop (4 frames per thread) has a partial last group."""
+    W, H, n = 640, 360, 7
+    tex_np = np.ascontiguousarray(texture_small[:rows, :cols])
+    frames, path = _dev_clip(tex_np, W, H, n, start=3)
+    got = frames.cpu().numpy()
+    for i in range(n):
+        ref = ce.render_frame(tex_np, path[i], W, H, synth.focal_for_width(W))
+        assert np.array_equal(got[i], ref), i
+    # the job's renderer (ray table + BGRX texture) against the stand-alone one (rays computed, BGR texture)
+    off = offline.OfflineStabilizer(3, 2, 180, H, W, 3)
+    off.comm_init(0, 1)
+    a = off.run(n, vs.GLOBAL_SMOOTHING, 0, texture=torch.from_numpy(tex_np).cuda(), poses=path, focal=synth.focal_for_width(W))
+    b = off.run(n, vs.GLOBAL_SMOOTHING, 0, host_frames=got)
+    off.close()
+    assert np.array_equal(a["checksums"], b["checksums"])
+
+
 def test_render_sky_and_tilted_pose(texture_small):
     """A tilted camera sees the horizon: sky colour above it (camera_engine.cpp:119), floor below."""
     W, H = 320, 240
@@ -258,3 +278,30 @@ def test_offline_run_resident_source_equals_simulator_source(texture_small):
     for c in range(n):
         assert int(b["checksums"][c]) == vs.frame_checksum(got[c])
     off.close()
+
+
+@pytest.mark.parametrize("B", [2, 3, 16, 64])
+def test_offline_run_fused_pass_ring_shapes(texture_small, B):
+    """GLOBAL_SMOOTHING from a staged source is one fused pass over a ring of ceil((F-1)/B)+1 chunks (vstab_offline_run):
+    every ring depth (B < F-1: several chunks of lag; B > clip: one chunk) returns the streaming calls' bytes, from the
+    simulator source and from host frames, and equals the two-pass schedule (VSTAB_SRC_DEVICE never fuses)."""
+    W, H, wh, n, P, F = 480, 270, 135, 41, 7, 9
+    frames, path = _dev_clip(texture_small, W, H, n)
+    frames_np = frames.cpu().numpy()
+    want = _streaming_mode(frames_np, P, F, wh, vs.GLOBAL_SMOOTHING, None)
+    tex = torch.from_numpy(texture_small).cuda()
+    off = offline.OfflineStabilizer(P, F, wh, H, W, B)
+    off.comm_init(0, 1)
+    out_sim = np.zeros((n, H, W, 3), np.uint8)
+    r = off.run(n, vs.GLOBAL_SMOOTHING, 0, texture=tex, poses=path, focal=synth.focal_for_width(W), host_out=out_sim)
+    out_host = np.zeros_like(out_sim)
+    r2 = off.run(n, vs.GLOBAL_SMOOTHING, 0, host_frames=frames_np, host_out=out_host, want_T=True)
+    out_dev = torch.zeros((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    r3 = off.run(n, vs.GLOBAL_SMOOTHING, 0, device_frames=frames, device_out=out_dev, want_T=True)
+    off.close()
+    for c in range(n):
+        assert np.array_equal(out_sim[c], want[c]), f"simulator source, call {c}"
+        assert np.array_equal(out_host[c], want[c]), f"host source, call {c}"
+    assert np.array_equal(r["checksums"], r2["checksums"]) and np.array_equal(r["checksums"], r3["checksums"])
+    assert np.array_equal(r2["T"], r3["T"])
+    assert np.array_equal(out_dev.cpu().numpy(), out_host)

@@ -1341,7 +1341,8 @@ static vstab_status offline_render_impl(vstab_offline_t* o, const uint8_t* d_fra
                                         const double* d_T_all, long n_total, int mode, long lock_call,
                                         const unsigned long long* d_sums,
                                         uint8_t* d_out, size_t out_frame_stride, size_t out_step,
-                                        unsigned long long* d_check /* [n] pre-zeroed, or null */) {
+                                        unsigned long long* d_check /* [n] pre-zeroed, or null */,
+                                        long slot_mod = 0 /* > 0: d_frames is a ring, frame f sits in slot (f - frame_base) % slot_mod */) {
     if (!o || !d_frames || !d_T_all || !d_out || !d_sums || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
     auto set_err = [&](const std::string& e) { o->err = e; };
     if (n > o->max_batch + 1) { o->err = "n exceeds max_batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
@@ -1378,7 +1379,7 @@ static vstab_status offline_render_impl(vstab_offline_t* o, const uint8_t* d_fra
     launch_smooth(a, call_first, n, o->wp.as<WarpParams>(), q);
     o->timer.end(ST_SMOOTH, q);
     o->timer.begin(ST_WARP, q);
-    launch_warp(d_frames, step, frame_stride, 0, o->wp.as<WarpParams>(), n, g.cols, g.rows, d_out, out_step,
+    launch_warp(d_frames, step, frame_stride, slot_mod, o->wp.as<WarpParams>(), n, g.cols, g.rows, d_out, out_step,
                 out_frame_stride, q, d_check);
     o->timer.end(ST_WARP, q);
     CK(cudaGetLastError());
@@ -1730,13 +1731,21 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     enum { PH_SOURCE = 0, PH_ESTIMATE = 1, PH_EXCHANGE = 2, PH_RENDER = 3 };
 
     // ---- buffers: one chunk of frames (+ halo), one chunk of outputs, transforms, sums, checksums -----------------
+    // GLOBAL_SMOOTHING from a staged source (simulator, host) is ONE pass: the window of call c reads T[c-P-F+1 .. c-1] and
+    // nothing else, so the calls whose windows are complete are warped right behind the estimation, from a ring of the last
+    // ceil((F-1)/B) + 1 chunks -- every frame is rendered / uploaded once instead of twice.  The calls whose windows reach
+    // into a neighbour's shard (the first P-1 and the last F-1 of a rank in a world > 1) wait for the all-gather as before.
+    static const bool fuse_ok = !(getenv("VSTAB_OFFLINE_FUSED") && atoi(getenv("VSTAB_OFFLINE_FUSED")) == 0);
+    const bool fused = fuse_ok && !resident && mode == VSTAB_GLOBAL_SMOOTHING;
+    const long ring_chunks = fused ? (F > 1 ? (F - 1 + B - 1) / B : 0) + 1 : 1;
+    const long ring_frames = ring_chunks * B;                       // + one slot for the halo frame of the first chunk
     DevBuf& chunk = o->job_chunk; DevBuf& outc = o->job_out;
-    if (!(resident && cfg->d_out) && o->job_chunk_frames < (size_t)B + 1) {
-        CK(chunk.alloc(g.frame_bytes * ((size_t)B + 1) + 64));
+    if (!(resident && cfg->d_out) && o->job_chunk_frames < (size_t)ring_frames + 1) {
+        CK(chunk.alloc(g.frame_bytes * ((size_t)ring_frames + 1) + 64));
         CK(outc.alloc(g.frame_bytes * (size_t)B + 64));
-        o->job_chunk_frames = (size_t)B + 1;
+        o->job_chunk_frames = (size_t)ring_frames + 1;
     }
-    DevBuf T_local, T_gather, T_all, sums, checks, poses_d, rays_d, reg_local, reg_gather, reg_all;
+    DevBuf T_local, T_gather, T_all, sums, checks, poses_d, rays_d, tex4_d, reg_local, reg_gather, reg_all;
     CK(T_local.alloc(sizeof(double) * 9 * (size_t)L));
     CK(T_all.alloc(sizeof(double) * 9 * (size_t)N));
     if (world > 1) CK(T_gather.alloc(sizeof(double) * 9 * (size_t)L * world));
@@ -1758,6 +1767,8 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         // the camera rays do not depend on the pose: once per job (24 bytes per pixel), not once per pixel and frame
         CK(rays_d.alloc(sizeof(double) * 3 * (size_t)g.cols * g.rows));
         launch_render_rays(g.cols, g.rows, cfg->focal, rays_d.as<double>(), q);
+        CK(tex4_d.alloc(sizeof(unsigned) * (size_t)cfg->tex_rows * cfg->tex_cols));
+        launch_render_tex4(cfg->d_texture, cfg->tex_rows, cfg->tex_cols, tex4_d.as<unsigned>(), q);
         CK(cudaStreamSynchronize(q));                               // hp goes out of scope
     }
     // frames [f0, f0 + n) of the clip -> chunk slots [slot, slot + n)
@@ -1766,7 +1777,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         clock.begin(PH_SOURCE, q);
         if (sim) {
             launch_render(cfg->d_texture, cfg->tex_rows, cfg->tex_cols, poses_d.as<RenderPose>() + f0, (int)n, g.cols, g.rows, cfg->focal,
-                          cb + (size_t)slot * fb, g.pitch, fb, q, rays_d.as<double>());
+                          cb + (size_t)slot * fb, g.pitch, fb, q, rays_d.as<double>(), tex4_d.as<unsigned>());
         } else {
             for (long i = 0; i < n; ++i) {
                 const long f = f0 + i;
@@ -1811,8 +1822,71 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         CK(cudaMemsetAsync(reg_local.p, 0, sizeof(double) * 10 * (size_t)L, q));
     }
 
+    // warps the calls [c0, c1) (at most B per launch); ring > 0: their presentation frames are in the ring already
+    auto render_calls = [&](long c0, long c1, long ring) -> vstab_status {
+        for (long c = c0; c < c1; c += B) {
+            const long n = c1 - c < B ? c1 - c : B;
+            const long p_lo = c - F > 0 ? c - F : 0, p_hi = c + n - 1 - F > 0 ? c + n - 1 - F : 0;
+            vstab_status s2;
+            if (ring == 0 && (s2 = fetch(p_lo, p_hi - p_lo + 1, 0)) != VSTAB_OK) return s2;
+            clock.begin(PH_RENDER, q);
+            uint8_t* dst = cfg->d_out ? cfg->d_out + (size_t)(c - pl.call_first) * cfg->out_frame_stride : outc.as<uint8_t>();
+            const long base = ring > 0 ? pl.first : p_lo;          // frame held by slot 0 (ring: modulo `ring`)
+            s2 = offline_render_impl(o, resident ? dframe(p_lo) : cb, src_fs, src_step, base, (int)n, c, T_all.as<double>(), N, mode,
+                                     cfg->lock_call, sums.as<unsigned long long>() + (size_t)(base - pl.first) * 3, dst,
+                                     cfg->d_out ? cfg->out_frame_stride : fb, cfg->d_out ? cfg->out_step : g.pitch,
+                                     cfg->checksums ? checks.as<unsigned long long>() + (c - pl.call_first) : nullptr, ring);
+            clock.end(q);
+            if (s2 != VSTAB_OK) return s2;
+            if (cfg->host_out) {
+                for (long i = 0; i < n; ++i)
+                    CK(cudaMemcpy2DAsync(cfg->host_out + (size_t)(c - pl.call_first + i) * cfg->out_frame_stride, cfg->out_step,
+                                         outc.as<uint8_t>() + (size_t)i * fb, g.pitch, row_bytes, g.rows, cudaMemcpyDeviceToHost, q));
+            }
+        }
+        return VSTAB_OK;
+    };
+    // calls [call_first, c_head) and [c_tail, call_last) are warped after the exchange; the fused pass serves the rest
+    long c_head = pl.call_first, c_tail = pl.call_first;
+
+    // ---- fused pass: estimate chunk k, then warp every call whose window is complete -----------------------------------
+    if (fused) {
+        CK(cudaMemsetAsync(T_all.p, 0, sizeof(double) * 9 * (size_t)N, q));
+        // first call of this rank whose window starts inside its own transforms T[first ..]
+        if (pl.first > 0 && pl.first + (long)o->P + F - 1 > c_head) c_head = pl.first + (long)o->P + F - 1;
+        if (c_head > pl.call_last) c_head = pl.call_last;
+        c_tail = c_head;
+        long k = 0;
+        for (long f0 = pl.first; f0 < pl.last; f0 += B, ++k) {
+            const long n = pl.last - f0 < B ? pl.last - f0 : B;
+            const long slot0 = (k % ring_chunks) * B;
+            const uint8_t* hl = nullptr;
+            if (f0 == pl.first) {
+                if (f0 > 0) { if ((st = fetch(f0 - 1, 1, (int)ring_frames)) != VSTAB_OK) return st; hl = cb + (size_t)ring_frames * fb; }
+            } else {
+                hl = cb + (size_t)(((k - 1) % ring_chunks) * B + B - 1) * fb;      // the previous chunk's last frame, still in the ring
+            }
+            if ((st = fetch(f0, n, (int)slot0)) != VSTAB_OK) return st;
+            clock.begin(PH_ESTIMATE, q);
+            st = vstab_offline_estimate(o, cb + (size_t)slot0 * fb, src_fs, src_step, (int)n, f0, hl, T_all.as<double>() + (size_t)f0 * 9,
+                                        sums.as<unsigned long long>() + (size_t)(f0 - pl.first) * 3);
+            clock.end(q);
+            if (st != VSTAB_OK) return st;
+            // call c reads transforms up to T[c - 1]
+            const long c_ok = f0 + n + 1 < pl.call_last ? f0 + n + 1 : pl.call_last;
+            if (c_ok > c_tail) {
+                const long p_lo = c_tail - F > 0 ? c_tail - F : 0;
+                if (p_lo < pl.first || p_lo - pl.first < (k - (ring_chunks - 1)) * B) { o->err = "internal: presentation frame left the ring"; return VSTAB_ERR_STATE; }
+                if ((st = render_calls(c_tail, c_ok, ring_frames)) != VSTAB_OK) return st;
+                c_tail = c_ok;
+            }
+        }
+        if (n_local > 0)
+            CK(cudaMemcpyAsync(T_local.p, T_all.as<double>() + (size_t)pl.first * 9, sizeof(double) * 9 * (size_t)n_local, cudaMemcpyDeviceToDevice, q));
+    }
+
     // ---- pass 1: estimate T[f] for f in [first, last), chunk by chunk ----------------------------------------------
-    for (long f0 = pl.first; f0 < pl.last; f0 += B) {
+    for (long f0 = pl.first; f0 < pl.last && !fused; f0 += B) {
         const long n = pl.last - f0 < B ? pl.last - f0 : B;
         if (!resident) {
             if (f0 == pl.first) {
@@ -1860,25 +1934,9 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     if ((st = vstab_offline_prepare(o, T_all.as<double>(), N, mode, cfg->lock_call)) != VSTAB_OK) return st;
     clock.end(q);
 
-    // ---- pass 2: the calls whose presentation frame this rank owns -------------------------------------------------
-    for (long c0 = pl.call_first; c0 < pl.call_last; c0 += B) {
-        const long n = pl.call_last - c0 < B ? pl.call_last - c0 : B;
-        const long p_lo = c0 - F > 0 ? c0 - F : 0, p_hi = c0 + n - 1 - F > 0 ? c0 + n - 1 - F : 0;
-        if ((st = fetch(p_lo, p_hi - p_lo + 1, 0)) != VSTAB_OK) return st;
-        clock.begin(PH_RENDER, q);
-        uint8_t* dst = cfg->d_out ? cfg->d_out + (size_t)(c0 - pl.call_first) * cfg->out_frame_stride : outc.as<uint8_t>();
-        st = offline_render_impl(o, resident ? dframe(p_lo) : cb, src_fs, src_step, p_lo, (int)n, c0, T_all.as<double>(), N, mode,
-                                 cfg->lock_call, sums.as<unsigned long long>() + (size_t)(p_lo - pl.first) * 3, dst,
-                                 cfg->d_out ? cfg->out_frame_stride : fb, cfg->d_out ? cfg->out_step : g.pitch,
-                                 cfg->checksums ? checks.as<unsigned long long>() + (c0 - pl.call_first) : nullptr);
-        clock.end(q);
-        if (st != VSTAB_OK) return st;
-        if (cfg->host_out) {
-            for (long i = 0; i < n; ++i)
-                CK(cudaMemcpy2DAsync(cfg->host_out + (size_t)(c0 - pl.call_first + i) * cfg->out_frame_stride, cfg->out_step,
-                                     outc.as<uint8_t>() + (size_t)i * fb, g.pitch, row_bytes, g.rows, cudaMemcpyDeviceToHost, q));
-        }
-    }
+    // ---- pass 2: the calls whose presentation frame this rank owns (all of them, or what the fused pass left) ----------
+    if ((st = render_calls(pl.call_first, c_head, 0)) != VSTAB_OK) return st;
+    if ((st = render_calls(c_tail, pl.call_last, 0)) != VSTAB_OK) return st;
     if (cfg->checksums && n_calls > 0)
         CK(cudaMemcpyAsync(cfg->checksums, checks.p, sizeof(unsigned long long) * (size_t)n_calls, cudaMemcpyDeviceToHost, q));
     if (cfg->T_all) CK(cudaMemcpyAsync(cfg->T_all, T_all.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, q));

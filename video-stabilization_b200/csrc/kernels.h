@@ -265,7 +265,10 @@ void launch_l2_nn_batch(const uint8_t* ref_desc, const int* nref, uint8_t* cur_d
 struct RenderPose { double R[9]; double cam[3]; };
 void launch_render(const uint8_t* tex, int tex_rows, int tex_cols, const RenderPose* poses_dev, int n,
                    int w, int h, double focal, uint8_t* out, size_t pitch, size_t frame_stride,
-                   cudaStream_t st, const double* rays = nullptr /* [3][h][w] from launch_render_rays, or null */);
+                   cudaStream_t st, const double* rays = nullptr /* [3][h][w] from launch_render_rays, or null */,
+                   const unsigned* tex4 = nullptr /* the texture as B G R x words from launch_render_tex4, or null */);
+// the texture repacked to one 32-bit word per texel (one load per pixel instead of three)
+void launch_render_tex4(const uint8_t* tex, int tex_rows, int tex_cols, unsigned* tex4, cudaStream_t st);
 // the pose-independent camera rays of every pixel (24 bytes per pixel), for jobs that render many frames
 void launch_render_rays(int w, int h, double focal, double* rays, cudaStream_t st);
 
