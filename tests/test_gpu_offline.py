@@ -282,7 +282,7 @@ def test_offline_run_resident_source_equals_simulator_source(texture_small):
 
 @pytest.mark.parametrize("B", [2, 3, 16, 64])
 def test_offline_run_fused_pass_ring_shapes(texture_small, B):
-    """GLOBAL_SMOOTHING from a staged source is one fused pass over a ring of ceil((F-1)/B)+1 chunks (vstab_offline_run):
+    """GLOBAL_SMOOTHING from a staged source is one fused pass over a ring of ceil((F-1)/B)+3 chunks (vstab_offline_run):
     every ring depth (B < F-1: several chunks of lag; B > clip: one chunk) returns the streaming calls' bytes, from the
     simulator source and from host frames, and equals the two-pass schedule (VSTAB_SRC_DEVICE never fuses)."""
     W, H, wh, n, P, F = 480, 270, 135, 41, 7, 9

@@ -1342,7 +1342,8 @@ static vstab_status offline_render_impl(vstab_offline_t* o, const uint8_t* d_fra
                                         const unsigned long long* d_sums,
                                         uint8_t* d_out, size_t out_frame_stride, size_t out_step,
                                         unsigned long long* d_check /* [n] pre-zeroed, or null */,
-                                        long slot_mod = 0 /* > 0: d_frames is a ring, frame f sits in slot (f - frame_base) % slot_mod */) {
+                                        long slot_mod = 0 /* > 0: d_frames is a ring, frame f sits in slot (f - frame_base) % slot_mod */,
+                                        cudaStream_t on = nullptr /* stream of the two launches; null: the instance stream */) {
     if (!o || !d_frames || !d_T_all || !d_out || !d_sums || n < 1) return VSTAB_ERR_INVALID_ARGUMENT;
     auto set_err = [&](const std::string& e) { o->err = e; };
     if (n > o->max_batch + 1) { o->err = "n exceeds max_batch"; return VSTAB_ERR_INVALID_ARGUMENT; }
@@ -1357,7 +1358,7 @@ static vstab_status offline_render_impl(vstab_offline_t* o, const uint8_t* d_fra
     }
     CK(cudaSetDevice(o->device));
     Geometry& g = o->g;
-    cudaStream_t q = o->stream;
+    cudaStream_t q = on ? on : o->stream;
     if (mode == VSTAB_ACCUMULATED_FULL_LOCK) {
         const long anchor = lock_call - (long)o->F;
         if (o->acc_T != d_T_all || o->acc_n_total != n_total || o->acc_anchor != anchor) {
@@ -1733,11 +1734,11 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     // ---- buffers: one chunk of frames (+ halo), one chunk of outputs, transforms, sums, checksums -----------------
     // GLOBAL_SMOOTHING from a staged source (simulator, host) is ONE pass: the window of call c reads T[c-P-F+1 .. c-1] and
     // nothing else, so the calls whose windows are complete are warped right behind the estimation, from a ring of the last
-    // ceil((F-1)/B) + 1 chunks -- every frame is rendered / uploaded once instead of twice.  The calls whose windows reach
+    // ceil((F-1)/B) + 3 chunks -- every frame is rendered / uploaded once instead of twice.  The calls whose windows reach
     // into a neighbour's shard (the first P-1 and the last F-1 of a rank in a world > 1) wait for the all-gather as before.
     static const bool fuse_ok = !(getenv("VSTAB_OFFLINE_FUSED") && atoi(getenv("VSTAB_OFFLINE_FUSED")) == 0);
     const bool fused = fuse_ok && !resident && mode == VSTAB_GLOBAL_SMOOTHING;
-    const long ring_chunks = fused ? (F > 1 ? (F - 1 + B - 1) / B : 0) + 1 : 1;
+    const long ring_chunks = fused ? (F > 1 ? (F - 1 + B - 1) / B : 0) + 3 : 1;     // + 2: the three streams of the fused pass
     const long ring_frames = ring_chunks * B;                       // + one slot for the halo frame of the first chunk
     DevBuf& chunk = o->job_chunk; DevBuf& outc = o->job_out;
     if (!(resident && cfg->d_out) && o->job_chunk_frames < (size_t)ring_frames + 1) {
@@ -1772,7 +1773,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         CK(cudaStreamSynchronize(q));                               // hp goes out of scope
     }
     // frames [f0, f0 + n) of the clip -> chunk slots [slot, slot + n)
-    auto fetch = [&](long f0, long n, int slot) -> vstab_status {
+    auto fetch = [&](long f0, long n, int slot, cudaStream_t q) -> vstab_status {
         if (n <= 0 || resident) return VSTAB_OK;
         clock.begin(PH_SOURCE, q);
         if (sim) {
@@ -1804,7 +1805,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         DevBuf pack;
         CK(pack.alloc(vstab_offline_reference_bytes()));
         if (rank == owner) {
-            if ((st = fetch(anchor, 1, 0)) != VSTAB_OK) return st;
+            if ((st = fetch(anchor, 1, 0, q)) != VSTAB_OK) return st;
             if ((st = vstab_offline_reference_capture(o, resident ? dframe(anchor) : cb, src_step, mode)) != VSTAB_OK) return st;
             if ((st = vstab_offline_reference_export(o, pack.p)) != VSTAB_OK) return st;
         }
@@ -1822,26 +1823,26 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         CK(cudaMemsetAsync(reg_local.p, 0, sizeof(double) * 10 * (size_t)L, q));
     }
 
-    // warps the calls [c0, c1) (at most B per launch); ring > 0: their presentation frames are in the ring already
-    auto render_calls = [&](long c0, long c1, long ring) -> vstab_status {
+    // warps the calls [c0, c1) (at most B per launch) on stream qw; ring > 0: their presentation frames are in the ring already
+    auto render_calls = [&](long c0, long c1, long ring, cudaStream_t qw) -> vstab_status {
         for (long c = c0; c < c1; c += B) {
             const long n = c1 - c < B ? c1 - c : B;
             const long p_lo = c - F > 0 ? c - F : 0, p_hi = c + n - 1 - F > 0 ? c + n - 1 - F : 0;
             vstab_status s2;
-            if (ring == 0 && (s2 = fetch(p_lo, p_hi - p_lo + 1, 0)) != VSTAB_OK) return s2;
-            clock.begin(PH_RENDER, q);
+            if (ring == 0 && (s2 = fetch(p_lo, p_hi - p_lo + 1, 0, qw)) != VSTAB_OK) return s2;
+            clock.begin(PH_RENDER, qw);
             uint8_t* dst = cfg->d_out ? cfg->d_out + (size_t)(c - pl.call_first) * cfg->out_frame_stride : outc.as<uint8_t>();
             const long base = ring > 0 ? pl.first : p_lo;          // frame held by slot 0 (ring: modulo `ring`)
             s2 = offline_render_impl(o, resident ? dframe(p_lo) : cb, src_fs, src_step, base, (int)n, c, T_all.as<double>(), N, mode,
                                      cfg->lock_call, sums.as<unsigned long long>() + (size_t)(base - pl.first) * 3, dst,
                                      cfg->d_out ? cfg->out_frame_stride : fb, cfg->d_out ? cfg->out_step : g.pitch,
-                                     cfg->checksums ? checks.as<unsigned long long>() + (c - pl.call_first) : nullptr, ring);
-            clock.end(q);
+                                     cfg->checksums ? checks.as<unsigned long long>() + (c - pl.call_first) : nullptr, ring, qw);
+            clock.end(qw);
             if (s2 != VSTAB_OK) return s2;
             if (cfg->host_out) {
                 for (long i = 0; i < n; ++i)
                     CK(cudaMemcpy2DAsync(cfg->host_out + (size_t)(c - pl.call_first + i) * cfg->out_frame_stride, cfg->out_step,
-                                         outc.as<uint8_t>() + (size_t)i * fb, g.pitch, row_bytes, g.rows, cudaMemcpyDeviceToHost, q));
+                                         outc.as<uint8_t>() + (size_t)i * fb, g.pitch, row_bytes, g.rows, cudaMemcpyDeviceToHost, qw));
             }
         }
         return VSTAB_OK;
@@ -1850,37 +1851,65 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     long c_head = pl.call_first, c_tail = pl.call_first;
 
     // ---- fused pass: estimate chunk k, then warp every call whose window is complete -----------------------------------
+    // Three streams, so that the source (f64 rendering, or PCIe uploads), the estimation and the warps of neighbouring chunks
+    // overlap -- they load different pipes of the SM: source of chunk k+1, k+2 (qs) || estimate k (q) || warp step k-1 (qw).
+    // Chunk j is written by S(j) and read by E(j), E(j+1) (halo) and the warp steps W(j) .. W(j + lag); S(j) overwrites
+    // chunk j - ring_chunks, so it waits for W(j-3) (lag = ring_chunks - 3) and E(j-2).
     if (fused) {
+        if (!o->copy_in) CK(cudaStreamCreateWithFlags(&o->copy_in, cudaStreamNonBlocking));
+        if (!o->copy_out) CK(cudaStreamCreateWithFlags(&o->copy_out, cudaStreamNonBlocking));
+        cudaStream_t qs = o->copy_in, qw = o->copy_out;
+        constexpr int kEv = 8;
+        cudaEvent_t evS[kEv], evE[kEv], evW[kEv];
+        for (int i = 0; i < kEv; ++i) { evS[i] = clock.get(); evE[i] = clock.get(); evW[i] = clock.get(); }
         CK(cudaMemsetAsync(T_all.p, 0, sizeof(double) * 9 * (size_t)N, q));
+        cudaEvent_t ev_ready = clock.get();                        // the job's buffers are reset (q) before qs / qw touch them
+        CK(cudaEventRecord(ev_ready, q));
+        CK(cudaStreamWaitEvent(qs, ev_ready, 0));
+        CK(cudaStreamWaitEvent(qw, ev_ready, 0));
         // first call of this rank whose window starts inside its own transforms T[first ..]
         if (pl.first > 0 && pl.first + (long)o->P + F - 1 > c_head) c_head = pl.first + (long)o->P + F - 1;
         if (c_head > pl.call_last) c_head = pl.call_last;
         c_tail = c_head;
-        long k = 0;
-        for (long f0 = pl.first; f0 < pl.last; f0 += B, ++k) {
-            const long n = pl.last - f0 < B ? pl.last - f0 : B;
+        const long nchunks = (n_local + B - 1) / B;
+        auto source = [&](long k) -> vstab_status {               // S(k)
+            const long f0 = pl.first + k * B, n = pl.last - f0 < B ? pl.last - f0 : B;
+            if (k >= 3) CK(cudaStreamWaitEvent(qs, evW[(k - 3) % kEv], 0));
+            if (k >= 2) CK(cudaStreamWaitEvent(qs, evE[(k - 2) % kEv], 0));
+            vstab_status s2;
+            if (k == 0 && f0 > 0 && (s2 = fetch(f0 - 1, 1, (int)ring_frames, qs)) != VSTAB_OK) return s2;
+            if ((s2 = fetch(f0, n, (int)((k % ring_chunks) * B), qs)) != VSTAB_OK) return s2;
+            CK(cudaEventRecord(evS[k % kEv], qs));
+            return VSTAB_OK;
+        };
+        if (nchunks > 0 && (st = source(0)) != VSTAB_OK) return st;
+        if (nchunks > 1 && (st = source(1)) != VSTAB_OK) return st;
+        for (long k = 0; k < nchunks; ++k) {
+            const long f0 = pl.first + k * B, n = pl.last - f0 < B ? pl.last - f0 : B;
             const long slot0 = (k % ring_chunks) * B;
             const uint8_t* hl = nullptr;
-            if (f0 == pl.first) {
-                if (f0 > 0) { if ((st = fetch(f0 - 1, 1, (int)ring_frames)) != VSTAB_OK) return st; hl = cb + (size_t)ring_frames * fb; }
-            } else {
-                hl = cb + (size_t)(((k - 1) % ring_chunks) * B + B - 1) * fb;      // the previous chunk's last frame, still in the ring
-            }
-            if ((st = fetch(f0, n, (int)slot0)) != VSTAB_OK) return st;
+            if (k == 0) { if (f0 > 0) hl = cb + (size_t)ring_frames * fb; }
+            else hl = cb + (size_t)(((k - 1) % ring_chunks) * B + B - 1) * fb;      // the previous chunk's last frame, still in the ring
+            CK(cudaStreamWaitEvent(q, evS[k % kEv], 0));
             clock.begin(PH_ESTIMATE, q);
             st = vstab_offline_estimate(o, cb + (size_t)slot0 * fb, src_fs, src_step, (int)n, f0, hl, T_all.as<double>() + (size_t)f0 * 9,
                                         sums.as<unsigned long long>() + (size_t)(f0 - pl.first) * 3);
             clock.end(q);
             if (st != VSTAB_OK) return st;
-            // call c reads transforms up to T[c - 1]
+            CK(cudaEventRecord(evE[k % kEv], q));
+            if (k + 2 < nchunks && (st = source(k + 2)) != VSTAB_OK) return st;
+            // W(k): call c reads transforms up to T[c - 1]
+            CK(cudaStreamWaitEvent(qw, evE[k % kEv], 0));
             const long c_ok = f0 + n + 1 < pl.call_last ? f0 + n + 1 : pl.call_last;
             if (c_ok > c_tail) {
                 const long p_lo = c_tail - F > 0 ? c_tail - F : 0;
-                if (p_lo < pl.first || p_lo - pl.first < (k - (ring_chunks - 1)) * B) { o->err = "internal: presentation frame left the ring"; return VSTAB_ERR_STATE; }
-                if ((st = render_calls(c_tail, c_ok, ring_frames)) != VSTAB_OK) return st;
+                if (p_lo < pl.first || p_lo - pl.first < (k - (ring_chunks - 3)) * B) { o->err = "internal: presentation frame left the ring"; return VSTAB_ERR_STATE; }
+                if ((st = render_calls(c_tail, c_ok, ring_frames, qw)) != VSTAB_OK) return st;
                 c_tail = c_ok;
             }
+            CK(cudaEventRecord(evW[k % kEv], qw));
         }
+        if (nchunks > 0) CK(cudaStreamWaitEvent(q, evW[(nchunks - 1) % kEv], 0));
         if (n_local > 0)
             CK(cudaMemcpyAsync(T_local.p, T_all.as<double>() + (size_t)pl.first * 9, sizeof(double) * 9 * (size_t)n_local, cudaMemcpyDeviceToDevice, q));
     }
@@ -1890,12 +1919,12 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         const long n = pl.last - f0 < B ? pl.last - f0 : B;
         if (!resident) {
             if (f0 == pl.first) {
-                if (f0 > 0 && (st = fetch(f0 - 1, 1, 0)) != VSTAB_OK) return st;        // halo frame
+                if (f0 > 0 && (st = fetch(f0 - 1, 1, 0, q)) != VSTAB_OK) return st;     // halo frame
             } else {
                 // the last frame of the previous chunk is this chunk's halo
                 CK(cudaMemcpyAsync(cb, cb + (size_t)B * fb, fb, cudaMemcpyDeviceToDevice, q));
             }
-            if ((st = fetch(f0, n, 1)) != VSTAB_OK) return st;
+            if ((st = fetch(f0, n, 1, q)) != VSTAB_OK) return st;
         }
         const uint8_t* fr = resident ? dframe(f0) : cb + fb;
         const uint8_t* hl = f0 > 0 ? (resident ? dframe(f0 - 1) : cb) : nullptr;
@@ -1935,8 +1964,8 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     clock.end(q);
 
     // ---- pass 2: the calls whose presentation frame this rank owns (all of them, or what the fused pass left) ----------
-    if ((st = render_calls(pl.call_first, c_head, 0)) != VSTAB_OK) return st;
-    if ((st = render_calls(c_tail, pl.call_last, 0)) != VSTAB_OK) return st;
+    if ((st = render_calls(pl.call_first, c_head, 0, q)) != VSTAB_OK) return st;
+    if ((st = render_calls(c_tail, pl.call_last, 0, q)) != VSTAB_OK) return st;
     if (cfg->checksums && n_calls > 0)
         CK(cudaMemcpyAsync(cfg->checksums, checks.p, sizeof(unsigned long long) * (size_t)n_calls, cudaMemcpyDeviceToHost, q));
     if (cfg->T_all) CK(cudaMemcpyAsync(cfg->T_all, T_all.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, q));
