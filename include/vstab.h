@@ -238,13 +238,19 @@ uintptr_t vstab_offline_stream(vstab_offline_t* o);
  * (rank 0 makes the id, the host program ships its 128 bytes to the others any way it likes), and every rank calls
  * vstab_offline_run with the same n_total / mode / lock_call:
  *   pass 1   rank r estimates T[f] for its contiguous range [first, last) (+ the halo frame first-1), chunk by chunk:
- *            at most max_batch + 1 frames are resident at any time (the reference's window bound, stabilizer.cpp:160-167);
+ *            a bounded number of frames is resident at any time (max_batch + 1; the fused pass below: its ring) -- the
+ *            reference bounds memory the same way with its past+1+future window, stabilizer.cpp:160-167;
  *   exchange ONE ncclAllGather of 72 bytes per frame (ORB / SIFT lock: + one ncclBroadcast of the packed reference set
  *            and one all-gather of 80 bytes per frame {H, valid});
  *   pass 2   global prefix / window average for the calls whose presentation frame the rank owns, warp, sink.
- * Frames come from host memory (this rank's shard; re-read in pass 2) or from the simulator (K13 renders each
- * chunk on the device from `poses`, in both passes: nothing of the clip is ever stored).  Outputs go to host memory
- * and / or are reduced to one 64-bit checksum per call (see vstab_frame_checksum).  With no communicator the
+ * Frames come from host memory (this rank's shard), from device memory, or from the simulator (K13 renders each
+ * chunk on the device from `poses`: nothing of the clip is ever stored).  GLOBAL_SMOOTHING from a staged source (host,
+ * simulator) runs the two passes as ONE: the window of call c reads T[c-P-F+1 .. c-1] only, so every call whose
+ * window lies inside the rank's own transforms is warped right behind the estimation, out of a ring of the last
+ * ceil((F-1)/max_batch) + 3 chunks (source, estimation and warp on three streams) -- a frame is uploaded / rendered
+ * once; only the first P-1 and last F-1 calls of a rank in a world > 1 wait for the exchange and fetch their frames
+ * again.  The other modes need the global prefix / the broadcast reference and fetch every frame in both passes.
+ * Outputs go to host memory and / or are reduced to one 64-bit checksum per call (see vstab_frame_checksum).  With no communicator the
  * instance is a world of one.  Replaces the reference's --file / --simulator loop around stabilizeFrame
  * (src/main_utils.cpp:397-417, 459-493) for clips that are sharded over GPUs. */
 typedef struct vstab_nccl_id { char bytes[128]; } vstab_nccl_id;
