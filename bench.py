@@ -379,6 +379,19 @@ def run_ours(args):
                         "frac": path_bytes * value / 1e9 / max(world, 1) / peak, "unit": "GB/s per GPU"}
     roofline["hbm_bound_stages"] = {k: {"achieved": stage_rows[k]["achieved_gbs"], "frac": stage_rows[k]["frac"]}
                                     for k in ("ingest", "warp") if k in stage_rows}
+    # the dominant kernel against the roofline that does bound it: warp instructions per launch (committed ncu capture, scaled
+    # to this run's frames per launch) / live launch time, against SMs x 4 schedulers x the SM clock sampled during the run
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        inst = float(tj["inst"][dom]) * min(args.batch, n_local) / float(tj.get("frames_per_launch", 256))
+        sms_n = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms_n * 4 * float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        roofline["issue"] = {"warp_instructions_per_launch": inst, "achieved_ginst_s": inst / (d["avg_launch_ms"] * 1e-3) / 1e9,
+                             "peak_ginst_s": issue_peak / 1e9, "frac": inst / (d["avg_launch_ms"] * 1e-3) / issue_peak,
+                             "source": "profiles/traffic.json inst (ncu smsp__inst_executed.sum of the same kernel)"}
+    except Exception:
+        roofline["issue"] = None
     roofline["note"] = ("the dominant kernel (pyramidal LK, one warp per feature) moves 0.6 MB of algorithmic bytes per "
                         "frame and is bound by instruction issue on the integer ALU pipe (ncu: profiles/), not by HBM; "
                         "ingest and warp are the stages an HBM roofline describes")
