@@ -260,6 +260,13 @@ vstab_status vstab_offline_comm_init(vstab_offline_t* o, const vstab_nccl_id* id
  * frame 0 also produces the `future` warm-up calls; the last `future` frames are never presented) */
 typedef struct vstab_shard_plan { long first, last, call_first, call_last; } vstab_shard_plan;
 vstab_status vstab_offline_plan(long n_total, int world, int rank, size_t future_frames, vstab_shard_plan* out);
+/* the fused GLOBAL_SMOOTHING pass of a rank (staged sources): chunk k = frames [first + k*max_batch, ...) sits in ring slot
+ * k % ring_chunks; the calls [fused_first, fused_last) are warped right behind the estimation (after chunk k: every call
+ * c <= last frame of chunk k + 1), the calls [call_first, fused_first) and [fused_last, call_last) -- windows that reach
+ * into a neighbour's shard -- after the all-gather.  The window of call c reads T[max(1, c-P-F+1) .. c-1]. */
+typedef struct vstab_fused_plan { long ring_chunks, fused_first, fused_last; } vstab_fused_plan;
+vstab_status vstab_offline_fused_plan(long n_total, int world, int rank, size_t past_frames, size_t future_frames,
+                                      int max_batch, vstab_fused_plan* out);
 
 typedef enum vstab_frame_source { VSTAB_SRC_HOST = 0, VSTAB_SRC_SIMULATOR = 1, VSTAB_SRC_DEVICE = 2 } vstab_frame_source;
 typedef struct vstab_offline_cfg {

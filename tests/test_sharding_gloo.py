@@ -53,6 +53,48 @@ def test_c_abi_shard_plan_equals_python_plan():
     assert lib.vstab_offline_plan(10, 2, 2, 3, C.byref(pl)) != 0 and lib.vstab_offline_plan(0, 1, 0, 3, C.byref(pl)) != 0
 
 
+def test_c_abi_fused_plan_covers_every_call_once_with_complete_windows():
+    """vstab_offline_fused_plan (the one-pass GLOBAL_SMOOTHING schedule of vstab_offline_run): on every rank the fused calls
+    read only transforms the rank estimates itself, present frames that are still in the ring when their window completes,
+    and together with the deferred head / tail calls make up the rank's calls exactly once."""
+    import ctypes as C
+    import vstab_b200 as vs
+    lib = vs.load_library()
+    cases = [(100, 1, 6, 4, 7), (100, 3, 6, 4, 7), (1000, 8, 60, 45, 32), (1000, 8, 60, 45, 128), (391, 2, 60, 45, 100),
+             (41, 1, 7, 9, 2), (41, 2, 7, 9, 3), (64, 8, 5, 3, 1), (30, 4, 0, 5, 4), (30, 4, 5, 0, 4), (9, 8, 3, 2, 4),
+             (100000, 8, 60, 45, 128)]
+    for n_total, world, P, F, B in cases:
+        seen = []
+        for r in range(world):
+            pl, fp = vs.ShardPlan(), vs.FusedPlan()
+            assert lib.vstab_offline_plan(n_total, world, r, F, C.byref(pl)) == 0
+            assert lib.vstab_offline_fused_plan(n_total, world, r, P, F, B, C.byref(fp)) == 0
+            assert pl.call_first <= fp.fused_first <= fp.fused_last <= pl.call_last
+            lag = fp.ring_chunks - 3
+            assert lag == (0 if F <= 1 else -(-(F - 1) // B))
+            step = max(1, (fp.fused_last - fp.fused_first) // 300)          # sample the long ranges
+            for c in list(range(fp.fused_first, fp.fused_last, step)) + ([fp.fused_last - 1] if fp.fused_last > fp.fused_first else []):
+                lo_t, hi_t = max(1, c - P - F + 1), c - 1                    # T indices the window of call c reads
+                if hi_t >= lo_t:
+                    assert lo_t >= pl.first and hi_t <= pl.last - 1, (n_total, world, r, c)
+                p = max(0, c - F)
+                assert pl.first <= p < pl.last
+                # the call is issued after the chunk holding frame c - 1 (or chunk 0 for c = 0); its frame is <= lag chunks older
+                k_issue = (max(c - 1, pl.first) - pl.first) // B
+                assert k_issue - (p - pl.first) // B <= lag, (n_total, world, r, c)
+            deferred = (fp.fused_first - pl.call_first) + (pl.call_last - fp.fused_last)
+            if r > 0 and pl.call_last > pl.call_first:
+                assert deferred <= max(P - 1, 0) + max(F - 1, 0)
+            if world == 1:
+                assert deferred == 0
+            seen += [(pl.call_first, fp.fused_first), (fp.fused_first, fp.fused_last), (fp.fused_last, pl.call_last)]
+        covered = sorted((a, b) for a, b in seen if b > a)
+        assert covered[0][0] == 0 and covered[-1][1] == n_total
+        assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+    fp = vs.FusedPlan()
+    assert lib.vstab_offline_fused_plan(10, 2, 0, 3, 2, 0, C.byref(fp)) != 0
+
+
 def test_frame_checksum_c_equals_numpy_and_is_position_sensitive():
     import ctypes as C
     import vstab_b200 as vs

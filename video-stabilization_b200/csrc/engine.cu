@@ -1683,6 +1683,25 @@ extern "C" vstab_status vstab_offline_plan(long n_total, int world, int rank, si
     return VSTAB_OK;
 }
 
+extern "C" vstab_status vstab_offline_fused_plan(long n_total, int world, int rank, size_t past_frames, size_t future_frames,
+                                                 int max_batch, vstab_fused_plan* out) {
+    vstab_shard_plan pl;
+    if (!out || max_batch < 1) return VSTAB_ERR_INVALID_ARGUMENT;
+    const vstab_status st = vstab_offline_plan(n_total, world, rank, future_frames, &pl);
+    if (st != VSTAB_OK) return st;
+    const long P = (long)past_frames, F = (long)future_frames, B = max_batch;
+    out->ring_chunks = (F > 1 ? (F - 1 + B - 1) / B : 0) + 3;      // lag of the warp step + 2 for the three streams
+    // first call whose window starts inside the rank's own transforms T[first ..] (rank 0: T[0] is never read)
+    long head = pl.call_first;
+    if (pl.first > 0 && pl.first + P + F - 1 > head) head = pl.first + P + F - 1;
+    if (head > pl.call_last) head = pl.call_last;
+    // call c reads transforms up to T[c - 1]: the last one the rank estimates itself is T[last - 1]
+    long tail = pl.last + 1 < pl.call_last ? pl.last + 1 : pl.call_last;
+    if (tail < head) tail = head;
+    out->fused_first = head; out->fused_last = tail;
+    return VSTAB_OK;
+}
+
 extern "C" uint64_t vstab_frame_checksum(const uint8_t* bgr, int rows, int cols, size_t step) {
     uint64_t sum = 0;
     const int groups = (cols + 3) / 4;
@@ -1738,7 +1757,9 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
     // into a neighbour's shard (the first P-1 and the last F-1 of a rank in a world > 1) wait for the all-gather as before.
     static const bool fuse_ok = !(getenv("VSTAB_OFFLINE_FUSED") && atoi(getenv("VSTAB_OFFLINE_FUSED")) == 0);
     const bool fused = fuse_ok && !resident && mode == VSTAB_GLOBAL_SMOOTHING;
-    const long ring_chunks = fused ? (F > 1 ? (F - 1 + B - 1) / B : 0) + 3 : 1;     // + 2: the three streams of the fused pass
+    vstab_fused_plan fp;
+    vstab_offline_fused_plan(N, world, rank, o->P, o->F, B, &fp);
+    const long ring_chunks = fused ? fp.ring_chunks : 1;
     const long ring_frames = ring_chunks * B;                       // + one slot for the halo frame of the first chunk
     DevBuf& chunk = o->job_chunk; DevBuf& outc = o->job_out;
     if (!(resident && cfg->d_out) && o->job_chunk_frames < (size_t)ring_frames + 1) {
@@ -1867,10 +1888,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
         CK(cudaEventRecord(ev_ready, q));
         CK(cudaStreamWaitEvent(qs, ev_ready, 0));
         CK(cudaStreamWaitEvent(qw, ev_ready, 0));
-        // first call of this rank whose window starts inside its own transforms T[first ..]
-        if (pl.first > 0 && pl.first + (long)o->P + F - 1 > c_head) c_head = pl.first + (long)o->P + F - 1;
-        if (c_head > pl.call_last) c_head = pl.call_last;
-        c_tail = c_head;
+        c_head = c_tail = fp.fused_first;
         const long nchunks = (n_local + B - 1) / B;
         auto source = [&](long k) -> vstab_status {               // S(k)
             const long f0 = pl.first + k * B, n = pl.last - f0 < B ? pl.last - f0 : B;
@@ -1900,7 +1918,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
             if (k + 2 < nchunks && (st = source(k + 2)) != VSTAB_OK) return st;
             // W(k): call c reads transforms up to T[c - 1]
             CK(cudaStreamWaitEvent(qw, evE[k % kEv], 0));
-            const long c_ok = f0 + n + 1 < pl.call_last ? f0 + n + 1 : pl.call_last;
+            const long c_ok = f0 + n + 1 < fp.fused_last ? f0 + n + 1 : fp.fused_last;
             if (c_ok > c_tail) {
                 const long p_lo = c_tail - F > 0 ? c_tail - F : 0;
                 if (p_lo < pl.first || p_lo - pl.first < (k - (ring_chunks - 3)) * B) { o->err = "internal: presentation frame left the ring"; return VSTAB_ERR_STATE; }
@@ -1910,6 +1928,7 @@ extern "C" vstab_status vstab_offline_run(vstab_offline_t* o, const vstab_offlin
             CK(cudaEventRecord(evW[k % kEv], qw));
         }
         if (nchunks > 0) CK(cudaStreamWaitEvent(q, evW[(nchunks - 1) % kEv], 0));
+        if (c_tail != fp.fused_last) { o->err = "internal: the fused pass did not reach its last call"; return VSTAB_ERR_STATE; }
         if (n_local > 0)
             CK(cudaMemcpyAsync(T_local.p, T_all.as<double>() + (size_t)pl.first * 9, sizeof(double) * 9 * (size_t)n_local, cudaMemcpyDeviceToDevice, q));
     }

@@ -46,6 +46,10 @@ class ShardPlan(C.Structure):
     _fields_ = [("first", C.c_long), ("last", C.c_long), ("call_first", C.c_long), ("call_last", C.c_long)]
 
 
+class FusedPlan(C.Structure):           # vstab_fused_plan
+    _fields_ = [("ring_chunks", C.c_long), ("fused_first", C.c_long), ("fused_last", C.c_long)]
+
+
 class OfflineCfg(C.Structure):          # vstab_offline_cfg
     _fields_ = [("n_total", C.c_long), ("mode", C.c_int), ("lock_call", C.c_long), ("source", C.c_int),
                 ("host_frames", C.c_void_p), ("frame_stride", C.c_size_t), ("step", C.c_size_t), ("host_halo", C.c_void_p),
@@ -107,6 +111,7 @@ SYMBOLS = {
     "vstab_nccl_get_unique_id": (C.c_int, [C.POINTER(NcclId)]),
     "vstab_offline_comm_init": (C.c_int, [_vp, C.POINTER(NcclId), C.c_int, C.c_int]),
     "vstab_offline_plan": (C.c_int, [C.c_long, C.c_int, C.c_int, C.c_size_t, C.POINTER(ShardPlan)]),
+    "vstab_offline_fused_plan": (C.c_int, [C.c_long, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(FusedPlan)]),
     "vstab_offline_run": (C.c_int, [_vp, C.POINTER(OfflineCfg), C.POINTER(OfflineReport)]),
     "vstab_frame_checksum": (C.c_uint64, [_vp, C.c_int, C.c_int, C.c_size_t]),
     "vstab_offline_prepare": (C.c_int, [_vp, _vp, C.c_long, C.c_int, C.c_long]),
