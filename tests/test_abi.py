@@ -173,3 +173,67 @@ def test_file_front_end_equals_streaming_api(tmp_path, side_by_side):
         for j in range(n - F):
             assert np.array_equal(got[j][:, :W], frames[j]), j            # delayed original = presentation frame
             assert np.array_equal(got[j][:, W:], want[j + F]), j
+
+
+def _offline_front_end():
+    exe = os.path.join(os.path.dirname(os.path.dirname(vs.LIB_PATH)), "bin", "vstab_offline")
+    assert os.path.exists(exe), "video-stabilization_b200/bin/vstab_offline is built by make (__graft_entry__.build())"
+    return exe
+
+
+def test_offline_front_end_usage_and_argument_errors(tmp_path):
+    """examples/vstab_offline.cpp (the sharded job from a C++ host, one process per GPU): usage errors and the constructor's
+    argument checks (src/stabilizer.cpp:40-49) surface as exit status 1 before any device is used; I/O errors as 2."""
+    import subprocess
+    exe = _offline_front_end()
+    assert subprocess.run([exe], capture_output=True).returncode == 1
+    clip = tmp_path / "c.bgr"
+    clip.write_bytes(bytes(64 * 48 * 3 * 2))
+    base = [exe, "--file", str(clip), "--width", "64", "--height", "48", "--out", str(tmp_path / "o.bgr")]
+    r = subprocess.run(base + ["--working-height", "90"], capture_output=True, text=True)
+    assert r.returncode == 1 and "workingHeight" in r.stderr
+    assert subprocess.run(base + ["--past-window", "0", "--future-window", "0"], capture_output=True).returncode == 1
+    assert subprocess.run(base + ["--world", "2", "--rank", "1"], capture_output=True).returncode == 1     # no --id-file
+    assert subprocess.run(base + ["--world", "2", "--rank", "2", "--id-file", str(tmp_path / "id")], capture_output=True).returncode == 1
+    assert subprocess.run(base + ["--mode", "nonsense"], capture_output=True).returncode == 1
+    r = subprocess.run([exe, "--file", str(tmp_path / "missing.bgr"), "--width", "64", "--height", "48", "--out", str(tmp_path / "o.bgr")],
+                       capture_output=True, text=True)
+    assert r.returncode == 2
+    r = subprocess.run([exe, "--file", str(clip), "--width", "640", "--height", "480", "--out", str(tmp_path / "o.bgr")],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "no complete" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,mode_at", [("global", 0), ("lock", 5)])
+def test_offline_front_end_world_of_one_equals_streaming_api(tmp_path, mode, mode_at):
+    """The C++ host of the sharded job (vstab_offline_run behind examples/vstab_offline.cpp) as a world of one: the raw
+    BGR24 file it writes holds the frames the per-frame streaming API returns, and its checksum file their checksums.
+    `global` takes the fused one-pass schedule (chunks of 4 frames, ring of 4 chunks), `lock` the two passes."""
+    import subprocess
+    import numpy as np
+    from conftest import render_clip
+    from oracle import synth
+    W, H, n, P, F, wh = 320, 240, 19, 4, 3, 120
+    frames = render_clip(synth.make_texture(512), W, H, n)
+    clip = tmp_path / "in.bgr"
+    clip.write_bytes(b"".join(f.tobytes() for f in frames))
+    out, sums = tmp_path / "out.bgr", tmp_path / "sums.txt"
+    cmd = [_offline_front_end(), "--file", str(clip), "--width", str(W), "--height", str(H), "--out", str(out),
+           "--past-window", str(P), "--future-window", str(F), "--working-height", str(wh), "--batch", "4",
+           "--mode", mode, "--mode-at", str(mode_at), "--checksums", str(sums), "--device", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    st = vs.Stabilizer(P, F, wh)
+    want = []
+    for i, f in enumerate(frames):
+        if mode == "lock" and i == mode_at:
+            st.set_stabilization_mode(vs.ACCUMULATED_FULL_LOCK)
+        want.append(st.stabilize_frame(f))
+    st.close()
+    got = np.frombuffer(out.read_bytes(), np.uint8).reshape(n, H, W, 3)
+    lines = [ln.split() for ln in sums.read_text().splitlines()]
+    assert [int(a) for a, _ in lines] == list(range(n))
+    for i in range(n):
+        assert np.array_equal(got[i], want[i]), i
+        assert int(lines[i][1], 16) == vs.frame_checksum(want[i]), i
